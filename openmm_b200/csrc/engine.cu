@@ -1,0 +1,947 @@
+// engine.cu -- host side of libb200md.so: the C-ABI of include/b200md.h over the CUDA kernels of this directory.
+// No CPU fallback exists: every compute entry point needs a CUDA device and fails loudly without one.
+#include "engine.h"
+#include "../../include/b200md.h"
+#include <stdexcept>
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <cstdlib>
+#include <map>
+#include <set>
+#include <dlfcn.h>
+
+static std::string g_create_error;
+
+template <class T> struct DevBuf {
+    T* p = nullptr; size_t n = 0;
+    void alloc(size_t count) { free(); n = count; if (count) CUDA_CHECK(cudaMalloc(&p, count*sizeof(T))); }
+    void upload(const std::vector<T>& v) { if (v.size() > n) alloc(v.size()); if (!v.empty()) CUDA_CHECK(cudaMemcpy(p, v.data(), v.size()*sizeof(T), cudaMemcpyHostToDevice)); }
+    void zero() { if (n) CUDA_CHECK(cudaMemset(p, 0, n*sizeof(T))); }
+    void free() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    ~DevBuf() { free(); }
+};
+
+// ---- minimal NCCL binding, resolved at run time so that libb200md.so has no link-time NCCL dependency ----
+struct NcclUid { char b[128]; };      // ncclUniqueId is passed BY VALUE to ncclCommInitRank
+struct NcclApi {
+    typedef NcclUid Uid;
+    void* lib = nullptr;
+    int (*GetUniqueId)(void*) = nullptr;
+    int (*CommInitRank)(void**, int, NcclUid, int) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    bool load(std::string& err) {
+        if (lib) return true;
+        const char* names[] = {getenv("B200MD_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+        for (const char* nm : names) { if (nm && (lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL))) break; }
+        if (!lib) { err = "cannot dlopen libnccl (set B200MD_NCCL_LIB)"; return false; }
+        GetUniqueId = (decltype(GetUniqueId)) dlsym(lib, "ncclGetUniqueId");
+        CommInitRank = (decltype(CommInitRank)) dlsym(lib, "ncclCommInitRank");
+        AllReduce = (decltype(AllReduce)) dlsym(lib, "ncclAllReduce");
+        CommDestroy = (decltype(CommDestroy)) dlsym(lib, "ncclCommDestroy");
+        GetErrorString = (decltype(GetErrorString)) dlsym(lib, "ncclGetErrorString");
+        if (!GetUniqueId || !CommInitRank || !AllReduce) { err = "libnccl lacks required symbols"; return false; }
+        return true;
+    }
+};
+static NcclApi g_nccl;
+enum { NCCL_INT64 = 4, NCCL_FLOAT32 = 7, NCCL_FLOAT64 = 8, NCCL_SUM = 0 };
+
+struct b200md_ctx {
+    int device = 0;
+    int natoms = 0, npad = 0, nblocks = 0;
+    bool finalized = false;
+    std::string err;
+    cudaStream_t stream = nullptr;
+    // ---- host copy of the system definition ----
+    std::vector<double> mass, charge, sigma, epsilon;
+    b200md_nonbonded_desc nbdesc{};
+    bool haveNb = false;
+    std::vector<int> excI, excJ; std::vector<double> excQQ, excSig, excEps;
+    std::vector<int> bondI, bondJ; std::vector<double> bondR0, bondK;
+    std::vector<int> angI, angJ, angK; std::vector<double> angT0, angKK;
+    std::vector<int> torI, torJ, torK, torL, torN; std::vector<double> torPhase, torKK;
+    std::vector<int> conI, conJ; std::vector<double> conD;
+    int cmFreq = 0;
+    double boxA[3] = {0, 0, 0}, boxB[3] = {0, 0, 0}, boxC[3] = {0, 0, 0};
+    bool haveBox = false;
+    double padFrac = 0.10;
+    // ---- device state ----
+    DevBuf<float4> posq, velm, sposq, sshift, refPos, atomShift, blockCenter, blockHalf;
+    DevBuf<float2> sigeps, ssigeps;
+    DevBuf<long long> force;
+    DevBuf<double> energy, cmScratch;
+    DevBuf<int> sorig, sortedOf, cellRank, cellCount, cellFill, atomCell, tmpSorted, tileI, tileJ, tileMask, counters, exclStart, exclList;
+    DevBuf<unsigned int> maskPool;
+    DevBuf<unsigned long long> stepCounter;
+    DevBuf<float> grid, eterm;
+    DevBuf<float2> cgrid;
+    DevBuf<float2> tw[3];
+    DevBuf<double> moduli[3];
+    DevBuf<int2> bondAtoms, excAtoms; DevBuf<double2> bondParams, angleParams;
+    DevBuf<int4> angleAtoms, torsionAtoms, unitAtoms; DevBuf<double4> torsionParams, excParams;
+    DevBuf<int> unitType; DevBuf<float4> unitParams;
+    NbDev nb{};
+    PmeDev pme{};
+    BondedDev bd{};
+    UnitDev units{};
+    IntegDev integ{};
+    bool haveIntegrator = false;
+    double dt = 0, temperature = 0, friction = 0;
+    double time = 0;
+    int64_t stepCount = 0;
+    double selfEnergy = 0, dispersionCoefficient = 0;
+    // ---- stats ----
+    int64_t forceEvals = 0, kernelLaunches = 0;
+    // ---- graph ----
+    cudaGraphExec_t stepGraph = nullptr;
+    bool graphValid = false;
+    bool useGraph = true;
+    int stepLaunches = 0;
+    // ---- multi-GPU ----
+    void* comm = nullptr;
+    int rank = 0, world = 1;
+    std::vector<float4> hbuf4;
+    std::vector<long long> hforce;
+};
+
+#define API_BEGIN(ctx) if (!(ctx)) return -1; try { CUDA_CHECK(cudaSetDevice((ctx)->device));
+#define API_END(ctx) } catch (std::exception& e) { (ctx)->err = e.what(); return -1; } return 0;
+
+static void require(bool cond, const char* msg) { if (!cond) throw std::runtime_error(msg); }
+
+extern "C" const char* b200md_version(void) { return "b200md 0.1 (sm_100a)"; }
+extern "C" const char* b200md_last_error(const b200md_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+extern "C" int b200md_create(b200md_ctx** out, int device, int natoms) {
+    try {
+        require(out != nullptr && natoms > 0, "b200md_create: bad arguments");
+        int count = 0;
+        cudaError_t e = cudaGetDeviceCount(&count);
+        if (e != cudaSuccess || count == 0)
+            throw std::runtime_error(std::string("b200md_create: no CUDA device available (") + cudaGetErrorString(e) + "); this library has no CPU fallback");
+        require(device >= 0 && device < count, "b200md_create: device index out of range");
+        CUDA_CHECK(cudaSetDevice(device));
+        b200md_ctx* c = new b200md_ctx();
+        c->device = device;
+        c->natoms = natoms;
+        c->npad = ((natoms + 31)/32)*32;
+        c->nblocks = c->npad/32;
+        CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        c->mass.assign(natoms, 1.0);
+        c->charge.assign(natoms, 0.0); c->sigma.assign(natoms, 1.0); c->epsilon.assign(natoms, 0.0);
+        const char* pf = getenv("B200MD_PAD_FRACTION");
+        if (pf) c->padFrac = atof(pf);
+        const char* ug = getenv("B200MD_USE_GRAPH");
+        if (ug) c->useGraph = atoi(ug) != 0;
+        *out = c;
+        return 0;
+    } catch (std::exception& e) { g_create_error = e.what(); return -1; }
+}
+
+extern "C" void b200md_destroy(b200md_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    if (ctx->stepGraph) cudaGraphExecDestroy(ctx->stepGraph);
+    if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+extern "C" int b200md_set_masses(b200md_ctx* ctx, const double* mass) {
+    API_BEGIN(ctx)
+    require(!ctx->finalized, "set_masses after finalize");
+    ctx->mass.assign(mass, mass + ctx->natoms);
+    API_END(ctx)
+}
+
+extern "C" int b200md_set_nonbonded(b200md_ctx* ctx, const b200md_nonbonded_desc* d, const double* q, const double* sig, const double* eps) {
+    API_BEGIN(ctx)
+    require(!ctx->finalized, "set_nonbonded after finalize");
+    require(d->method != B200MD_NB_EWALD && d->method != B200MD_NB_LJPME, "nonbonded method not supported by the B200 platform (only NoCutoff, CutoffNonPeriodic, CutoffPeriodic, PME)");
+    ctx->nbdesc = *d;
+    ctx->haveNb = true;
+    ctx->charge.assign(q, q + ctx->natoms);
+    ctx->sigma.assign(sig, sig + ctx->natoms);
+    ctx->epsilon.assign(eps, eps + ctx->natoms);
+    ctx->dispersionCoefficient = d->dispersion_coefficient;
+    API_END(ctx)
+}
+
+extern "C" int b200md_set_exceptions(b200md_ctx* ctx, int n, const int* p1, const int* p2, const double* qq, const double* sig, const double* eps) {
+    API_BEGIN(ctx)
+    require(!ctx->finalized, "set_exceptions after finalize");
+    ctx->excI.assign(p1, p1+n); ctx->excJ.assign(p2, p2+n);
+    ctx->excQQ.assign(qq, qq+n); ctx->excSig.assign(sig, sig+n); ctx->excEps.assign(eps, eps+n);
+    API_END(ctx)
+}
+extern "C" int b200md_set_bonds(b200md_ctx* ctx, int n, const int* p1, const int* p2, const double* len, const double* k) {
+    API_BEGIN(ctx)
+    require(!ctx->finalized, "set_bonds after finalize");
+    ctx->bondI.assign(p1, p1+n); ctx->bondJ.assign(p2, p2+n); ctx->bondR0.assign(len, len+n); ctx->bondK.assign(k, k+n);
+    API_END(ctx)
+}
+extern "C" int b200md_set_angles(b200md_ctx* ctx, int n, const int* p1, const int* p2, const int* p3, const double* a, const double* k) {
+    API_BEGIN(ctx)
+    require(!ctx->finalized, "set_angles after finalize");
+    ctx->angI.assign(p1, p1+n); ctx->angJ.assign(p2, p2+n); ctx->angK.assign(p3, p3+n); ctx->angT0.assign(a, a+n); ctx->angKK.assign(k, k+n);
+    API_END(ctx)
+}
+extern "C" int b200md_set_torsions(b200md_ctx* ctx, int n, const int* p1, const int* p2, const int* p3, const int* p4, const int* per, const double* ph, const double* k) {
+    API_BEGIN(ctx)
+    require(!ctx->finalized, "set_torsions after finalize");
+    ctx->torI.assign(p1, p1+n); ctx->torJ.assign(p2, p2+n); ctx->torK.assign(p3, p3+n); ctx->torL.assign(p4, p4+n);
+    ctx->torN.assign(per, per+n); ctx->torPhase.assign(ph, ph+n); ctx->torKK.assign(k, k+n);
+    API_END(ctx)
+}
+extern "C" int b200md_set_constraints(b200md_ctx* ctx, int n, const int* p1, const int* p2, const double* d) {
+    API_BEGIN(ctx)
+    require(!ctx->finalized, "set_constraints after finalize");
+    ctx->conI.assign(p1, p1+n); ctx->conJ.assign(p2, p2+n); ctx->conD.assign(d, d+n);
+    API_END(ctx)
+}
+extern "C" int b200md_set_cm_remover(b200md_ctx* ctx, int freq) {
+    if (!ctx) return -1;
+    ctx->cmFreq = freq;
+    return 0;
+}
+
+// ---------------------------------------------------------------- Hilbert curve over the binning cells
+static unsigned long long hilbert_index(unsigned int x, unsigned int y, unsigned int z, int bits) {
+    unsigned int X[3] = {x, y, z};
+    const unsigned int M = 1u << (bits-1);
+    for (unsigned int Q = M; Q > 1; Q >>= 1) {           // Skilling, "Programming the Hilbert curve" (2004)
+        const unsigned int P = Q - 1;
+        for (int i = 0; i < 3; i++) {
+            if (X[i] & Q) X[0] ^= P;
+            else { unsigned int t = (X[0] ^ X[i]) & P; X[0] ^= t; X[i] ^= t; }
+        }
+    }
+    for (int i = 1; i < 3; i++) X[i] ^= X[i-1];
+    unsigned int t = 0;
+    for (unsigned int Q = M; Q > 1; Q >>= 1) if (X[2] & Q) t ^= Q - 1;
+    for (int i = 0; i < 3; i++) X[i] ^= t;
+    unsigned long long h = 0;
+    for (int b = bits-1; b >= 0; b--)
+        for (int i = 0; i < 3; i++) h = (h << 1) | ((X[i] >> b) & 1u);
+    return h;
+}
+
+static void setup_cells(b200md_ctx* c) {
+    int nc[3] = {1, 1, 1};
+    if (c->nb.box.periodic) {
+        const double vol = c->boxA[0]*c->boxB[1]*c->boxC[2];
+        const double density = c->natoms/vol;
+        double edge = std::cbrt(4.0/density);
+        const double L[3] = {c->boxA[0], c->boxB[1], c->boxC[2]};
+        for (int d = 0; d < 3; d++) nc[d] = std::max(1, std::min(128, (int) std::floor(L[d]/edge)));
+    }
+    const int ncells = nc[0]*nc[1]*nc[2];
+    if (ncells != c->nb.ncells || nc[0] != c->nb.ncell[0] || nc[1] != c->nb.ncell[1] || nc[2] != c->nb.ncell[2]) {
+        int bits = 1;
+        while ((1 << bits) < std::max(nc[0], std::max(nc[1], nc[2]))) bits++;
+        std::vector<std::pair<unsigned long long, int> > order(ncells);
+        for (int x = 0; x < nc[0]; x++) for (int y = 0; y < nc[1]; y++) for (int z = 0; z < nc[2]; z++) {
+            int lin = (x*nc[1] + y)*nc[2] + z;
+            order[lin] = std::make_pair(hilbert_index(x, y, z, bits), lin);
+        }
+        std::sort(order.begin(), order.end());
+        std::vector<int> rank(ncells);
+        for (int r = 0; r < ncells; r++) rank[order[r].second] = r;
+        c->cellRank.upload(rank);
+        c->cellCount.alloc(ncells + 1);
+        c->cellFill.alloc(ncells);
+        c->nb.ncells = ncells;
+        for (int d = 0; d < 3; d++) c->nb.ncell[d] = nc[d];
+        c->nb.cellRank = c->cellRank.p; c->nb.cellCount = c->cellCount.p; c->nb.cellFill = c->cellFill.p;
+    }
+}
+
+static void invalidate_graph(b200md_ctx* c) { c->graphValid = false; }
+
+static void apply_box(b200md_ctx* c) {
+    BoxDev& b = c->nb.box;
+    const int m = c->nbdesc.method;
+    b.periodic = (m == B200MD_NB_CUTOFF_PERIODIC || m == B200MD_NB_PME) ? 1 : 0;
+    if (c->haveBox) {
+        b.ax = (float) c->boxA[0]; b.bx = (float) c->boxB[0]; b.by = (float) c->boxB[1];
+        b.cx = (float) c->boxC[0]; b.cy = (float) c->boxC[1]; b.cz = (float) c->boxC[2];
+        b.invAx = (float) (1.0/c->boxA[0]); b.invBy = (float) (1.0/c->boxB[1]); b.invCz = (float) (1.0/c->boxC[2]);
+        b.triclinic = (c->boxB[0] != 0 || c->boxC[0] != 0 || c->boxC[1] != 0) ? 1 : 0;
+        const double det = c->boxA[0]*c->boxB[1]*c->boxC[2];
+        const double s = 1.0/det;
+        double* R = b.recip;       // invert_box_vectors, ReferencePME.cpp:196-204
+        R[0] = c->boxB[1]*c->boxC[2]*s; R[1] = 0; R[2] = 0;
+        R[3] = -c->boxB[0]*c->boxC[2]*s; R[4] = c->boxA[0]*c->boxC[2]*s; R[5] = 0;
+        R[6] = (c->boxB[0]*c->boxC[1] - c->boxB[1]*c->boxC[0])*s; R[7] = -c->boxA[0]*c->boxC[1]*s; R[8] = c->boxA[0]*c->boxB[1]*s;
+        b.volume = det;
+    }
+    else {
+        require(!b.periodic, "periodic nonbonded method needs box vectors (b200md_set_box)");
+        b.ax = b.by = b.cz = 1.f; b.bx = b.cx = b.cy = 0.f; b.invAx = b.invBy = b.invCz = 1.f; b.triclinic = 0;
+        for (int i = 0; i < 9; i++) b.recip[i] = 0; b.volume = 1;
+    }
+    if (b.periodic) {
+        const double rc = c->nbdesc.cutoff;
+        require(c->boxA[0] >= 1.999999*rc && c->boxB[1] >= 1.999999*rc && c->boxC[2] >= 1.999999*rc,
+                "The periodic box size has decreased to less than twice the nonbonded cutoff.");   // ReferenceKernels.cpp:983-985
+    }
+    if (c->finalized) {
+        setup_cells(c);
+        if (m == B200MD_NB_PME) { launch_pme_eterm(c->nb, c->pme, c->stream); c->kernelLaunches++; }
+        const int one = 1;
+        CUDA_CHECK(cudaMemcpyAsync(&c->counters.p[2], &one, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        invalidate_graph(c);
+    }
+}
+
+extern "C" int b200md_set_box(b200md_ctx* ctx, const double a[3], const double b[3], const double c[3]) {
+    API_BEGIN(ctx)
+    for (int i = 0; i < 3; i++) { ctx->boxA[i] = a[i]; ctx->boxB[i] = b[i]; ctx->boxC[i] = c[i]; }
+    ctx->haveBox = true;
+    if (ctx->finalized) apply_box(ctx);
+    API_END(ctx)
+}
+extern "C" int b200md_get_box(b200md_ctx* ctx, double a[3], double b[3], double c[3]) {
+    if (!ctx) return -1;
+    for (int i = 0; i < 3; i++) { a[i] = ctx->boxA[i]; b[i] = ctx->boxB[i]; c[i] = ctx->boxC[i]; }
+    return 0;
+}
+
+// per-atom and per-exception parameters -> device (computeParameters, ReferenceKernels.cpp:1077-1121)
+static void upload_params(b200md_ctx* c) {
+    const int N = c->natoms;
+    const double sk = std::sqrt(B200MD_ONE_4PI_EPS0);
+    std::vector<float2> se(c->npad, make_float2(0.f, 0.f));
+    for (int i = 0; i < N; i++) se[i] = make_float2((float) (0.5*c->sigma[i]), (float) (2.0*std::sqrt(c->epsilon[i])));
+    c->sigeps.upload(se);
+    // charges live in posq.w; keep positions
+    std::vector<float4> p(c->npad);
+    CUDA_CHECK(cudaMemcpy(p.data(), c->posq.p, sizeof(float4)*c->npad, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < N; i++) p[i].w = (float) (c->charge[i]*sk);
+    CUDA_CHECK(cudaMemcpy(c->posq.p, p.data(), sizeof(float4)*c->npad, cudaMemcpyHostToDevice));
+    const int ne = (int) c->excI.size();
+    std::vector<int2> ea(ne); std::vector<double4> ep(ne);
+    for (int e = 0; e < ne; e++) {
+        ea[e] = make_int2(c->excI[e], c->excJ[e]);
+        ep[e] = make_double4(B200MD_ONE_4PI_EPS0*c->excQQ[e], c->excSig[e], 4.0*c->excEps[e],
+                             B200MD_ONE_4PI_EPS0*c->charge[c->excI[e]]*c->charge[c->excJ[e]]);
+    }
+    c->excAtoms.upload(ea); c->excParams.upload(ep);
+    c->bd.nexc = ne; c->bd.excAtoms = c->excAtoms.p; c->bd.excParams = c->excParams.p;
+    double self = 0;
+    if (c->nbdesc.method == B200MD_NB_PME)
+        for (int i = 0; i < N; i++) self -= B200MD_ONE_4PI_EPS0*c->charge[i]*c->charge[i]*c->nbdesc.ewald_alpha/std::sqrt(M_PI);
+    c->selfEnergy = self;
+}
+
+static void build_units(b200md_ctx* c) {
+    const int N = c->natoms;
+    const int nc = (int) c->conI.size();
+    std::vector<std::vector<std::pair<int, double> > > adj(N);
+    for (int k = 0; k < nc; k++) {
+        adj[c->conI[k]].push_back(std::make_pair(c->conJ[k], c->conD[k]));
+        adj[c->conJ[k]].push_back(std::make_pair(c->conI[k], c->conD[k]));
+    }
+    std::vector<int> assigned(N, 0);
+    std::vector<int4> ua; std::vector<int> ut; std::vector<float4> up;
+    std::vector<std::pair<int, int> > order;      // (first atom, unit index) for sorting
+    auto dist = [&](int a, int b) -> double { for (auto& pr : adj[a]) if (pr.first == b) return pr.second; return -1.0; };
+    // SETTLE: closed triangles with two equal sides (compared as float, ReferenceConstraints.cpp:73-77,111-137)
+    for (int a = 0; a < N; a++) {
+        if (assigned[a] || adj[a].size() != 2) continue;
+        int b = adj[a][0].first, d = adj[a][1].first;
+        if (adj[b].size() != 2 || adj[d].size() != 2 || assigned[b] || assigned[d]) continue;
+        if (dist(b, d) < 0) continue;
+        const float dab = (float) dist(a, b), dad = (float) dist(a, d), dbd = (float) dist(b, d);
+        int apex, o1, o2; float d1, d2;
+        if (dab == dad) { apex = a; o1 = b; o2 = d; d1 = dab; d2 = dbd; }
+        else if (dab == dbd) { apex = b; o1 = a; o2 = d; d1 = dab; d2 = dad; }
+        else if (dad == dbd) { apex = d; o1 = a; o2 = b; d1 = dad; d2 = dab; }
+        else continue;
+        if (c->mass[apex] == 0 || c->mass[o1] == 0 || c->mass[o2] == 0) continue;
+        assigned[a] = assigned[b] = assigned[d] = 1;
+        order.push_back(std::make_pair(std::min(a, std::min(b, d)), (int) ua.size()));
+        ua.push_back(make_int4(apex, o1, o2, -1)); ut.push_back(1); up.push_back(make_float4(d1, d2, 0.f, 0.f));
+    }
+    // SHAKE clusters: a centre whose partners are each constrained only to it (IntegrationUtilities.cpp:204-277)
+    for (int a = 0; a < N; a++) {
+        if (assigned[a] || adj[a].empty()) continue;
+        bool centre = adj[a].size() <= 3;
+        for (auto& pr : adj[a]) if (adj[pr.first].size() != 1 || assigned[pr.first]) centre = false;
+        if (adj[a].size() == 1 && adj[adj[a][0].first].size() == 1) {
+            // isolated pair: the heavier atom is the centre, ties -> lower index
+            int b = adj[a][0].first;
+            if (c->mass[b] > c->mass[a] || (c->mass[b] == c->mass[a] && b < a)) centre = false;
+        }
+        if (!centre) continue;
+        int at[4] = {a, -1, -1, -1}; float dd[3] = {0, 0, 0};
+        for (size_t k = 0; k < adj[a].size(); k++) { at[k+1] = adj[a][k].first; dd[k] = (float) adj[a][k].second; assigned[adj[a][k].first] = 1; }
+        assigned[a] = 1;
+        order.push_back(std::make_pair(a, (int) ua.size()));
+        ua.push_back(make_int4(at[0], at[1], at[2], at[3])); ut.push_back(2); up.push_back(make_float4(dd[0], dd[1], dd[2], 0.f));
+    }
+    for (int a = 0; a < N; a++) {
+        if (!assigned[a] && !adj[a].empty())
+            throw std::runtime_error("B200 platform: unsupported constraint topology (only rigid 3-atom molecules and X-H_n clusters; general CCMA constraints are not implemented)");
+        if (!assigned[a]) {
+            order.push_back(std::make_pair(a, (int) ua.size()));
+            ua.push_back(make_int4(a, -1, -1, -1)); ut.push_back(0); up.push_back(make_float4(0, 0, 0, 0));
+        }
+    }
+    std::sort(order.begin(), order.end());
+    std::vector<int4> ua2(ua.size()); std::vector<int> ut2(ua.size()); std::vector<float4> up2(ua.size());
+    for (size_t k = 0; k < order.size(); k++) { ua2[k] = ua[order[k].second]; ut2[k] = ut[order[k].second]; up2[k] = up[order[k].second]; }
+    c->unitAtoms.upload(ua2); c->unitType.upload(ut2); c->unitParams.upload(up2);
+    c->units.nunits = (int) ua2.size();
+    c->units.unitAtoms = c->unitAtoms.p; c->units.unitType = c->unitType.p; c->units.unitParams = c->unitParams.p;
+}
+
+// B-spline moduli (pme_calculate_bsplines_moduli, ReferencePME.cpp:98-193)
+static std::vector<double> bspline_moduli(int n) {
+    const int order = B200MD_PME_ORDER;
+    std::vector<double> data(order, 0.0), bs(std::max(n, order+1), 0.0), mod(n);
+    data[order-1] = 0; data[1] = 0; data[0] = 1;
+    for (int k = 3; k < order; k++) {
+        double div = 1.0/(k-1.0);
+        data[k-1] = 0;
+        for (int l = 1; l < k-1; l++) data[k-l-1] = div*(l*data[k-l-2] + (k-l)*data[k-l-1]);
+        data[0] = div*data[0];
+    }
+    double div = 1.0/(order-1);
+    data[order-1] = 0;
+    for (int l = 1; l < order-1; l++) data[order-l-1] = div*(l*data[order-l-2] + (order-l)*data[order-l-1]);
+    data[0] = div*data[0];
+    for (int i = 1; i <= order; i++) bs[i] = data[i-1];
+    for (int i = 0; i < n; i++) {
+        double sc = 0, ss = 0;
+        for (int j = 0; j < n && j < (int) bs.size(); j++) {
+            double arg = (2.0*M_PI*i*j)/n;
+            sc += bs[j]*std::cos(arg); ss += bs[j]*std::sin(arg);
+        }
+        mod[i] = sc*sc + ss*ss;
+    }
+    for (int i = 0; i < n; i++)
+        if (mod[i] < 1.0e-7) mod[i] = (mod[(i-1+n)%n] + mod[(i+1)%n])/2;
+    return mod;
+}
+
+static void make_fft_plan(int n, FftPlanDev& plan, DevBuf<float2>& tw) {
+    plan.n = n;
+    if (!fft_make_radices(n, plan.radix, &plan.nstages))
+        throw std::runtime_error("B200 platform: PME grid dimension " + std::to_string(n) + " has a prime factor > 13; choose a dimension that factors into radices <= 16");
+    std::vector<float2> t(n);
+    for (int k = 0; k < n; k++) { double a = -2.0*M_PI*k/n; t[k] = make_float2((float) std::cos(a), (float) std::sin(a)); }
+    tw.upload(t);
+    plan.tw = tw.p;
+}
+
+static void setup_pme(b200md_ctx* c, int nx, int ny, int nz, double alpha) {
+    PmeDev& p = c->pme;
+    p.nx = nx; p.ny = ny; p.nz = nz; p.nzc = nz/2 + 1; p.alpha = alpha;
+    int dev = 0, maxSmem = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&maxSmem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    if (fft_plane_smem_bytes(ny, nz) > (size_t) maxSmem || fft_line_smem_bytes(nx) > (size_t) maxSmem)
+        throw std::runtime_error("B200 platform: PME grid plane does not fit in shared memory (max about 160x160 per slab)");
+    c->grid.alloc((size_t) nx*ny*nz);
+    c->cgrid.alloc((size_t) nx*ny*p.nzc);
+    c->eterm.alloc((size_t) nx*ny*p.nzc);
+    p.grid = c->grid.p; p.cgrid = c->cgrid.p; p.eterm = c->eterm.p;
+    const int n[3] = {nx, ny, nz};
+    for (int d = 0; d < 3; d++) {
+        make_fft_plan(n[d], p.plan[d], c->tw[d]);
+        c->moduli[d].upload(bspline_moduli(n[d]));
+        p.moduli[d] = c->moduli[d].p;
+    }
+}
+
+extern "C" int b200md_finalize(b200md_ctx* ctx) {
+    API_BEGIN(ctx)
+    require(!ctx->finalized, "finalize called twice");
+    b200md_ctx* c = ctx;
+    const int N = c->natoms, NP = c->npad;
+    if (!c->haveNb) { c->nbdesc = b200md_nonbonded_desc{}; c->nbdesc.method = B200MD_NB_NOCUTOFF; }
+    NbDev& nb = c->nb;
+    nb.natoms = N; nb.npad = NP; nb.nblocks = c->nblocks;
+    nb.method = c->nbdesc.method;
+    nb.rank = c->rank; nb.world = c->world;
+    // ---- state arrays ----
+    c->posq.alloc(NP); c->posq.zero(); c->velm.alloc(NP); c->velm.zero();
+    c->sposq.alloc(NP); c->sposq.zero(); c->sshift.alloc(NP); c->sshift.zero(); c->refPos.alloc(NP); c->refPos.zero(); c->atomShift.alloc(NP);
+    c->sigeps.alloc(NP); c->ssigeps.alloc(NP); c->ssigeps.zero();
+    c->force.alloc((size_t) 3*NP); c->force.zero();
+    c->energy.alloc(B200MD_NUM_ENERGY); c->energy.zero(); c->cmScratch.alloc(4);
+    c->sorig.alloc(NP); c->sortedOf.alloc(NP); c->atomCell.alloc(NP); c->tmpSorted.alloc(NP);
+    c->blockCenter.alloc(c->nblocks); c->blockHalf.alloc(c->nblocks);
+    c->counters.alloc(16); c->counters.zero();
+    c->stepCounter.alloc(1); c->stepCounter.zero();
+    std::vector<float4> vm(NP, make_float4(0, 0, 0, 0));
+    for (int i = 0; i < N; i++) vm[i].w = (c->mass[i] > 0) ? (float) (1.0/c->mass[i]) : 0.f;
+    c->velm.upload(vm);
+    nb.posq = c->posq.p; nb.velm = c->velm.p; nb.sigeps = c->sigeps.p; nb.force = c->force.p; nb.energy = c->energy.p;
+    nb.sposq = c->sposq.p; nb.ssigeps = c->ssigeps.p; nb.sshift = c->sshift.p; nb.sorig = c->sorig.p; nb.sortedOf = c->sortedOf.p;
+    nb.refPos = c->refPos.p; nb.atomCell = c->atomCell.p; nb.tmpSorted = c->tmpSorted.p; nb.atomShift = c->atomShift.p;
+    nb.blockCenter = c->blockCenter.p; nb.blockHalf = c->blockHalf.p; nb.counters = c->counters.p;
+    // ---- cutoffs ----
+    const double rc = c->nbdesc.cutoff;
+    if (nb.method == B200MD_NB_NOCUTOFF) {
+        nb.cutoff = 1e18f; nb.cutoff2 = 3e38f; nb.paddedCutoff2 = 3e38f; nb.halfPad2 = 3e38f;
+    }
+    else {
+        const double pad = c->padFrac*rc;
+        nb.cutoff = (float) rc; nb.cutoff2 = (float) (rc*rc); nb.paddedCutoff2 = (float) ((rc+pad)*(rc+pad)); nb.halfPad2 = (float) (0.25*pad*pad);
+    }
+    nb.useSwitch = c->nbdesc.use_switch; nb.switchDist = (float) c->nbdesc.switch_distance;
+    nb.alpha = (float) c->nbdesc.ewald_alpha;
+    if (nb.method == B200MD_NB_CUTOFF_PERIODIC || nb.method == B200MD_NB_CUTOFF_NONPERIODIC) {
+        const double eps = c->nbdesc.rf_dielectric;
+        nb.krf = (float) (std::pow(rc, -3.0)*(eps-1.0)/(2.0*eps+1.0));
+        nb.crf = (float) ((1.0/rc)*(3.0*eps)/(2.0*eps+1.0));
+    }
+    // ---- exclusions (every exception is an exclusion) ----
+    {
+        std::vector<std::vector<int> > ex(N);
+        for (size_t e = 0; e < c->excI.size(); e++) { ex[c->excI[e]].push_back(c->excJ[e]); ex[c->excJ[e]].push_back(c->excI[e]); }
+        std::vector<int> start(N+1, 0), list;
+        for (int i = 0; i < N; i++) {
+            std::sort(ex[i].begin(), ex[i].end());
+            ex[i].erase(std::unique(ex[i].begin(), ex[i].end()), ex[i].end());
+            start[i+1] = start[i] + (int) ex[i].size();
+            list.insert(list.end(), ex[i].begin(), ex[i].end());
+        }
+        if (list.empty()) list.push_back(0);
+        c->exclStart.upload(start); c->exclList.upload(list);
+        nb.exclStart = c->exclStart.p; nb.exclList = c->exclList.p;
+    }
+    // ---- tile capacity ----
+    {
+        const double nbk = c->nblocks;
+        double cap = nbk*(nbk+1)/2 + nbk + 64;
+        if (nb.method != B200MD_NB_NOCUTOFF && c->haveBox) {
+            const double vol = c->boxA[0]*c->boxB[1]*c->boxC[2];
+            const double rp = rc*(1.0 + c->padFrac);
+            const double pairs = 0.5*N*(N/vol)*(4.0/3.0*M_PI*rp*rp*rp);
+            const double est = pairs/(1024.0*0.15) + 2*nbk + 1024;
+            cap = std::min(cap, est);
+        }
+        cap = std::min(cap, 16.0e6);
+        nb.maxTiles = (int) cap;
+        c->tileI.alloc(nb.maxTiles); c->tileJ.alloc((size_t) nb.maxTiles*32); c->tileMask.alloc(nb.maxTiles); c->maskPool.alloc((size_t) nb.maxTiles*32);
+        nb.tileI = c->tileI.p; nb.tileJ = c->tileJ.p; nb.tileMask = c->tileMask.p; nb.maskPool = c->maskPool.p;
+    }
+    // ---- bonded ----
+    {
+        const int nbnd = (int) c->bondI.size(), na = (int) c->angI.size(), nt = (int) c->torI.size();
+        std::vector<int2> ba(nbnd); std::vector<double2> bp(nbnd);
+        for (int i = 0; i < nbnd; i++) { ba[i] = make_int2(c->bondI[i], c->bondJ[i]); bp[i] = make_double2(c->bondR0[i], c->bondK[i]); }
+        std::vector<int4> aa(na); std::vector<double2> ap(na);
+        for (int i = 0; i < na; i++) { aa[i] = make_int4(c->angI[i], c->angJ[i], c->angK[i], 0); ap[i] = make_double2(c->angT0[i], c->angKK[i]); }
+        std::vector<int4> ta(nt); std::vector<double4> tp(nt);
+        for (int i = 0; i < nt; i++) { ta[i] = make_int4(c->torI[i], c->torJ[i], c->torK[i], c->torL[i]); tp[i] = make_double4(c->torKK[i], c->torPhase[i], (double) c->torN[i], 0); }
+        c->bondAtoms.upload(ba); c->bondParams.upload(bp); c->angleAtoms.upload(aa); c->angleParams.upload(ap);
+        c->torsionAtoms.upload(ta); c->torsionParams.upload(tp);
+        c->bd.nbonds = nbnd; c->bd.nangles = na; c->bd.ntorsions = nt;
+        c->bd.bondAtoms = c->bondAtoms.p; c->bd.bondParams = c->bondParams.p; c->bd.angleAtoms = c->angleAtoms.p; c->bd.angleParams = c->angleParams.p;
+        c->bd.torsionAtoms = c->torsionAtoms.p; c->bd.torsionParams = c->torsionParams.p;
+        c->bd.excPeriodic = c->nbdesc.exceptions_periodic;
+    }
+    upload_params(c);
+    build_units(c);
+    if (nb.method == B200MD_NB_PME) setup_pme(c, c->nbdesc.grid[0], c->nbdesc.grid[1], c->nbdesc.grid[2], c->nbdesc.ewald_alpha);
+    c->finalized = true;
+    apply_box(c);
+    c->integ.stepCounter = c->stepCounter.p;
+    API_END(ctx)
+}
+
+extern "C" int b200md_update_nonbonded_params(b200md_ctx* ctx, const double* q, const double* sig, const double* eps,
+                                              int nexc, const double* eqq, const double* esig, const double* eeps, double dispCoef) {
+    API_BEGIN(ctx)
+    require(ctx->finalized, "update params before finalize");
+    require(nexc == (int) ctx->excI.size(), "update_nonbonded_params: the number of exceptions cannot change");
+    ctx->charge.assign(q, q + ctx->natoms); ctx->sigma.assign(sig, sig + ctx->natoms); ctx->epsilon.assign(eps, eps + ctx->natoms);
+    if (nexc) { ctx->excQQ.assign(eqq, eqq+nexc); ctx->excSig.assign(esig, esig+nexc); ctx->excEps.assign(eeps, eeps+nexc); }
+    ctx->dispersionCoefficient = dispCoef;
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    upload_params(ctx);
+    const int one = 1;
+    CUDA_CHECK(cudaMemcpy(&ctx->counters.p[2], &one, sizeof(int), cudaMemcpyHostToDevice));   // sorted copies of the parameters
+    invalidate_graph(ctx);
+    API_END(ctx)
+}
+
+// ---------------------------------------------------------------- state
+extern "C" int b200md_set_positions(b200md_ctx* ctx, const double* x) {
+    API_BEGIN(ctx)
+    require(ctx->finalized, "set_positions before finalize");
+    const int N = ctx->natoms;
+    const double sk = std::sqrt(B200MD_ONE_4PI_EPS0);
+    ctx->hbuf4.resize(ctx->npad);
+    for (int i = 0; i < N; i++) ctx->hbuf4[i] = make_float4((float) x[3*i], (float) x[3*i+1], (float) x[3*i+2], (float) (ctx->charge[i]*sk));
+    for (int i = N; i < ctx->npad; i++) ctx->hbuf4[i] = make_float4(0, 0, 0, 0);
+    CUDA_CHECK(cudaMemcpyAsync(ctx->posq.p, ctx->hbuf4.data(), sizeof(float4)*ctx->npad, cudaMemcpyHostToDevice, ctx->stream));
+    const int one = 1;
+    CUDA_CHECK(cudaMemcpyAsync(&ctx->counters.p[2], &one, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    API_END(ctx)
+}
+extern "C" int b200md_get_positions(b200md_ctx* ctx, double* x) {
+    API_BEGIN(ctx)
+    ctx->hbuf4.resize(ctx->npad);
+    CUDA_CHECK(cudaMemcpyAsync(ctx->hbuf4.data(), ctx->posq.p, sizeof(float4)*ctx->npad, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < ctx->natoms; i++) { x[3*i] = ctx->hbuf4[i].x; x[3*i+1] = ctx->hbuf4[i].y; x[3*i+2] = ctx->hbuf4[i].z; }
+    API_END(ctx)
+}
+extern "C" int b200md_set_velocities(b200md_ctx* ctx, const double* v) {
+    API_BEGIN(ctx)
+    require(ctx->finalized, "set_velocities before finalize");
+    ctx->hbuf4.resize(ctx->npad);
+    for (int i = 0; i < ctx->npad; i++) ctx->hbuf4[i] = make_float4(0, 0, 0, 0);
+    for (int i = 0; i < ctx->natoms; i++)
+        ctx->hbuf4[i] = make_float4((float) v[3*i], (float) v[3*i+1], (float) v[3*i+2], ctx->mass[i] > 0 ? (float) (1.0/ctx->mass[i]) : 0.f);
+    CUDA_CHECK(cudaMemcpyAsync(ctx->velm.p, ctx->hbuf4.data(), sizeof(float4)*ctx->npad, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    API_END(ctx)
+}
+extern "C" int b200md_get_velocities(b200md_ctx* ctx, double* v) {
+    API_BEGIN(ctx)
+    ctx->hbuf4.resize(ctx->npad);
+    CUDA_CHECK(cudaMemcpyAsync(ctx->hbuf4.data(), ctx->velm.p, sizeof(float4)*ctx->npad, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < ctx->natoms; i++) { v[3*i] = ctx->hbuf4[i].x; v[3*i+1] = ctx->hbuf4[i].y; v[3*i+2] = ctx->hbuf4[i].z; }
+    API_END(ctx)
+}
+extern "C" int b200md_get_forces(b200md_ctx* ctx, double* f) {
+    API_BEGIN(ctx)
+    ctx->hforce.resize((size_t) 3*ctx->npad);
+    CUDA_CHECK(cudaMemcpyAsync(ctx->hforce.data(), ctx->force.p, sizeof(long long)*3*ctx->npad, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    const double s = 1.0/B200MD_FORCE_SCALE;
+    for (int i = 0; i < ctx->natoms; i++)
+        for (int k = 0; k < 3; k++) f[3*i+k] = s*(double) ctx->hforce[(size_t) k*ctx->npad + i];
+    API_END(ctx)
+}
+extern "C" int b200md_set_time(b200md_ctx* ctx, double t) { if (!ctx) return -1; ctx->time = t; return 0; }
+extern "C" double b200md_get_time(b200md_ctx* ctx) { return ctx ? ctx->time : 0.0; }
+extern "C" int64_t b200md_get_step_count(b200md_ctx* ctx) { return ctx ? ctx->stepCount : 0; }
+extern "C" void* b200md_cuda_stream(b200md_ctx* ctx) { return ctx ? (void*) ctx->stream : nullptr; }
+extern "C" int b200md_synchronize(b200md_ctx* ctx) {
+    API_BEGIN(ctx)
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    API_END(ctx)
+}
+
+// ---------------------------------------------------------------- checkpoint
+struct CkptHeader { char magic[8]; int version; int natoms; double time; int64_t stepCount; double box[9]; unsigned long long rngStep; };
+extern "C" int64_t b200md_checkpoint_save(b200md_ctx* ctx, void* buf, int64_t cap) {
+    if (!ctx) return -1;
+    const int64_t need = sizeof(CkptHeader) + 2*sizeof(float4)*(int64_t) ctx->npad;
+    if (!buf) return need;
+    try {
+        CUDA_CHECK(cudaSetDevice(ctx->device));
+        require(cap >= need, "checkpoint buffer too small");
+        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+        CkptHeader h; memset(&h, 0, sizeof(h));
+        memcpy(h.magic, "B200MDCK", 8); h.version = 1; h.natoms = ctx->natoms; h.time = ctx->time; h.stepCount = ctx->stepCount;
+        for (int i = 0; i < 3; i++) { h.box[i] = ctx->boxA[i]; h.box[3+i] = ctx->boxB[i]; h.box[6+i] = ctx->boxC[i]; }
+        CUDA_CHECK(cudaMemcpy(&h.rngStep, ctx->stepCounter.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        char* p = (char*) buf;
+        memcpy(p, &h, sizeof(h)); p += sizeof(h);
+        CUDA_CHECK(cudaMemcpy(p, ctx->posq.p, sizeof(float4)*ctx->npad, cudaMemcpyDeviceToHost)); p += sizeof(float4)*ctx->npad;
+        CUDA_CHECK(cudaMemcpy(p, ctx->velm.p, sizeof(float4)*ctx->npad, cudaMemcpyDeviceToHost));
+        return need;
+    } catch (std::exception& e) { ctx->err = e.what(); return -1; }
+}
+extern "C" int b200md_checkpoint_load(b200md_ctx* ctx, const void* buf, int64_t size) {
+    API_BEGIN(ctx)
+    const int64_t need = sizeof(CkptHeader) + 2*sizeof(float4)*(int64_t) ctx->npad;
+    require(size >= need, "checkpoint blob too small");
+    CkptHeader h; memcpy(&h, buf, sizeof(h));
+    require(memcmp(h.magic, "B200MDCK", 8) == 0 && h.version == 1 && h.natoms == ctx->natoms, "checkpoint blob does not match this context");
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    ctx->time = h.time; ctx->stepCount = h.stepCount;
+    for (int i = 0; i < 3; i++) { ctx->boxA[i] = h.box[i]; ctx->boxB[i] = h.box[3+i]; ctx->boxC[i] = h.box[6+i]; }
+    const char* p = (const char*) buf + sizeof(h);
+    CUDA_CHECK(cudaMemcpy(ctx->posq.p, p, sizeof(float4)*ctx->npad, cudaMemcpyHostToDevice)); p += sizeof(float4)*ctx->npad;
+    CUDA_CHECK(cudaMemcpy(ctx->velm.p, p, sizeof(float4)*ctx->npad, cudaMemcpyHostToDevice));
+    CUDA_CHECK(cudaMemcpy(ctx->stepCounter.p, &h.rngStep, sizeof(unsigned long long), cudaMemcpyHostToDevice));
+    if (ctx->haveBox) apply_box(ctx);
+    const int one = 1;
+    CUDA_CHECK(cudaMemcpy(&ctx->counters.p[2], &one, sizeof(int), cudaMemcpyHostToDevice));
+    API_END(ctx)
+}
+
+// ---------------------------------------------------------------- force evaluation
+// Enqueue one force evaluation on the stream (no host sync).  Returns the number of kernels launched.
+static int enqueue_forces(b200md_ctx* c, int terms, bool energy) {
+    int launches = 0;
+    cudaStream_t s = c->stream;
+    CUDA_CHECK(cudaMemsetAsync(c->force.p, 0, sizeof(long long)*3*c->npad, s));
+    if (energy) CUDA_CHECK(cudaMemsetAsync(c->energy.p, 0, sizeof(double)*B200MD_NUM_ENERGY, s));
+    const bool direct = (terms & B200MD_TERM_NB_DIRECT) && c->haveNb;
+    const bool recip = (terms & B200MD_TERM_NB_RECIP) && c->haveNb && c->nb.method == B200MD_NB_PME;
+    if (direct || recip) {
+        launch_check_displacement(c->nb, s); launches++;
+        launch_list_build(c->nb, s); launches += list_build_launch_count();
+        launch_gather_sorted(c->nb, s); launches++;
+    }
+    if (direct) { launch_pair(c->nb, energy, s); launches++; }
+    if (recip) {
+        launch_pme_spread(c->nb, c->pme, s); launches++;
+        if (c->world > 1 && c->comm) {
+            int rc = g_nccl.AllReduce(c->grid.p, c->grid.p, (size_t) c->pme.nx*c->pme.ny*c->pme.nz, NCCL_FLOAT32, NCCL_SUM, c->comm, s);
+            if (rc != 0) throw std::runtime_error("ncclAllReduce(grid) failed");
+        }
+        launch_pme_fft_conv(c->nb, c->pme, energy && c->rank == 0, s); launches += 3;
+        launch_pme_gather(c->nb, c->pme, s); launches++;
+    }
+    int bterms = terms & (B200MD_TERM_BONDS | B200MD_TERM_ANGLES | B200MD_TERM_TORSIONS);
+    if (c->haveNb) bterms |= terms & (B200MD_TERM_NB_DIRECT | B200MD_TERM_NB_RECIP);
+    const int nbonded = c->bd.nbonds + c->bd.nangles + c->bd.ntorsions + c->bd.nexc;
+    if (bterms && nbonded > 0) { launch_bonded(c->nb, c->bd, bterms, energy, s); launches++; }
+    if (c->world > 1 && c->comm) {
+        int rc = g_nccl.AllReduce(c->force.p, c->force.p, (size_t) 3*c->npad, NCCL_INT64, NCCL_SUM, c->comm, s);
+        if (rc != 0) throw std::runtime_error("ncclAllReduce(force) failed");
+        if (energy) {
+            rc = g_nccl.AllReduce(c->energy.p, c->energy.p, B200MD_NUM_ENERGY, NCCL_FLOAT64, NCCL_SUM, c->comm, s);
+            if (rc != 0) throw std::runtime_error("ncclAllReduce(energy) failed");
+        }
+    }
+    CUDA_CHECK(cudaGetLastError());
+    return launches;
+}
+
+static void check_flags(b200md_ctx* c) {
+    int h[8];
+    CUDA_CHECK(cudaMemcpyAsync(h, c->counters.p, sizeof(int)*8, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    if (h[3]) throw std::runtime_error("B200 platform: neighbour-list tile capacity exceeded (" + std::to_string(c->nb.maxTiles) + " tiles)");
+}
+
+extern "C" int b200md_compute(b200md_ctx* ctx, int terms, int want_forces, double* energy) {
+    API_BEGIN(ctx)
+    (void) want_forces;
+    require(ctx->finalized, "compute before finalize");
+    const bool wantE = energy != nullptr;
+    ctx->kernelLaunches += enqueue_forces(ctx, terms, wantE);
+    ctx->forceEvals++;
+    if (wantE) {
+        double h[B200MD_NUM_ENERGY];
+        CUDA_CHECK(cudaMemcpyAsync(h, ctx->energy.p, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+        check_flags(ctx);
+        double e = 0;
+        if (terms & B200MD_TERM_BONDS) e += h[EN_BOND];
+        if (terms & B200MD_TERM_ANGLES) e += h[EN_ANGLE];
+        if (terms & B200MD_TERM_TORSIONS) e += h[EN_TORSION];
+        if (ctx->haveNb) {
+            if (terms & (B200MD_TERM_NB_DIRECT | B200MD_TERM_NB_RECIP)) e += h[EN_EXC];
+            if (terms & B200MD_TERM_NB_DIRECT) {
+                e += h[EN_NB];
+                const int m = ctx->nb.method;
+                if (m == B200MD_NB_CUTOFF_PERIODIC || m == B200MD_NB_PME)      // ReferenceKernels.cpp:1008-1011
+                    e += ctx->dispersionCoefficient/ctx->nb.box.volume;
+            }
+            if ((terms & B200MD_TERM_NB_RECIP) && ctx->nb.method == B200MD_NB_PME) e += h[EN_RECIP] + ctx->selfEnergy;
+        }
+        *energy = e;
+    }
+    API_END(ctx)
+}
+
+// ---------------------------------------------------------------- integration
+extern "C" int b200md_set_integrator(b200md_ctx* ctx, int kind, double dt, double temperature, double friction, int seed, double tol) {
+    API_BEGIN(ctx)
+    require(kind >= 0 && kind <= 2, "unknown integrator kind");
+    IntegDev& in = ctx->integ;
+    in.kind = kind; in.dt = (float) dt; in.tol = (float) tol; in.seed = (unsigned int) seed;
+    const double kT = B200MD_BOLTZ*temperature;
+    in.kT = (float) kT;
+    const double vscale = std::exp(-dt*friction);
+    in.vscale = (float) vscale;
+    in.fscale = (float) (friction == 0 ? dt : (1-vscale)/friction);
+    in.noisescale = (float) (kind == B200MD_INT_LANGEVIN_MIDDLE ? std::sqrt(1-vscale*vscale) : std::sqrt(kT*(1-vscale*vscale)));
+    in.stepCounter = ctx->stepCounter.p;
+    ctx->dt = dt; ctx->temperature = temperature; ctx->friction = friction;
+    ctx->haveIntegrator = true;
+    invalidate_graph(ctx);
+    API_END(ctx)
+}
+
+static int enqueue_step(b200md_ctx* c) {
+    int launches = enqueue_forces(c, B200MD_TERM_ALL, false);
+    launch_integrate(c->nb, c->units, c->integ, c->stream); launches += 2;
+    return launches;
+}
+
+extern "C" int b200md_integrate_only(b200md_ctx* ctx) {
+    API_BEGIN(ctx)
+    require(ctx->finalized && ctx->haveIntegrator, "integrate before finalize / set_integrator");
+    launch_integrate(ctx->nb, ctx->units, ctx->integ, ctx->stream);
+    ctx->kernelLaunches += 2;
+    ctx->time += ctx->dt; ctx->stepCount++;
+    CUDA_CHECK(cudaGetLastError());
+    API_END(ctx)
+}
+
+extern "C" int b200md_step(b200md_ctx* ctx, int nsteps) {
+    API_BEGIN(ctx)
+    require(ctx->finalized && ctx->haveIntegrator, "step before finalize / set_integrator");
+    b200md_ctx* c = ctx;
+    for (int i = 0; i < nsteps; i++) {
+        if (c->cmFreq > 0 && c->stepCount % c->cmFreq == 0) { launch_remove_cm(c->nb, c->cmScratch.p, c->stream); c->kernelLaunches += 2; }
+        if (c->useGraph) {
+            if (!c->graphValid) {
+                if (c->stepGraph) { cudaGraphExecDestroy(c->stepGraph); c->stepGraph = nullptr; }
+                cudaGraph_t g;
+                CUDA_CHECK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+                int l = 0;
+                try { l = enqueue_step(c); } catch (...) { cudaStreamEndCapture(c->stream, &g); throw; }
+                CUDA_CHECK(cudaStreamEndCapture(c->stream, &g));
+                CUDA_CHECK(cudaGraphInstantiate(&c->stepGraph, g, 0));
+                cudaGraphDestroy(g);
+                c->stepLaunches = l;
+                c->graphValid = true;
+            }
+            CUDA_CHECK(cudaGraphLaunch(c->stepGraph, c->stream));
+            c->kernelLaunches += c->stepLaunches;
+        }
+        else
+            c->kernelLaunches += enqueue_step(c);
+        c->forceEvals++;
+        c->stepCount++;
+        c->time += c->dt;
+    }
+    CUDA_CHECK(cudaGetLastError());
+    API_END(ctx)
+}
+
+extern "C" int b200md_kinetic_energy(b200md_ctx* ctx, double* ke) {
+    API_BEGIN(ctx)
+    require(ctx->finalized, "kinetic_energy before finalize");
+    const float shift = (ctx->haveIntegrator && ctx->integ.kind != B200MD_INT_LANGEVIN_MIDDLE) ? 0.5f*ctx->integ.dt : 0.f;
+    CUDA_CHECK(cudaMemsetAsync(ctx->energy.p + EN_KE, 0, sizeof(double), ctx->stream));
+    launch_kinetic_energy(ctx->nb, ctx->units, ctx->integ, shift, ctx->stream);
+    ctx->kernelLaunches++;
+    CUDA_CHECK(cudaMemcpyAsync(ke, ctx->energy.p + EN_KE, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    API_END(ctx)
+}
+extern "C" int b200md_apply_constraints(b200md_ctx* ctx, double tol) {
+    API_BEGIN(ctx)
+    launch_constrain_positions(ctx->nb, ctx->units, (float) tol, ctx->stream);
+    ctx->kernelLaunches++;
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    API_END(ctx)
+}
+extern "C" int b200md_apply_velocity_constraints(b200md_ctx* ctx, double tol) {
+    API_BEGIN(ctx)
+    launch_constrain_velocities(ctx->nb, ctx->units, (float) tol, ctx->stream);
+    ctx->kernelLaunches++;
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    API_END(ctx)
+}
+
+// ---------------------------------------------------------------- multi-GPU
+extern "C" int b200md_comm_unique_id(void* id128) {
+    std::string err;
+    if (!g_nccl.load(err)) { g_create_error = err; return -1; }
+    return g_nccl.GetUniqueId(id128) == 0 ? 0 : -1;
+}
+extern "C" int b200md_comm_init(b200md_ctx* ctx, int rank, int world, const void* id128) {
+    API_BEGIN(ctx)
+    require(!ctx->finalized, "comm_init must precede finalize");
+    std::string err;
+    if (!g_nccl.load(err)) throw std::runtime_error(err);
+    NcclApi::Uid uid; memcpy(uid.b, id128, 128);
+    int rc = g_nccl.CommInitRank(&ctx->comm, world, uid, rank);
+    if (rc != 0) throw std::runtime_error(std::string("ncclCommInitRank failed: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?"));
+    ctx->rank = rank; ctx->world = world;
+    API_END(ctx)
+}
+
+// ---------------------------------------------------------------- introspection
+extern "C" int b200md_get_stats(b200md_ctx* ctx, b200md_stats* out) {
+    API_BEGIN(ctx)
+    memset(out, 0, sizeof(*out));
+    out->natoms = ctx->natoms; out->padded_atoms = ctx->npad; out->num_blocks = ctx->nblocks;
+    if (ctx->finalized) {
+        launch_count_pairs(ctx->nb, ctx->stream);
+        int h[8];
+        CUDA_CHECK(cudaMemcpyAsync(h, ctx->counters.p, sizeof(int)*8, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+        out->num_tiles = h[0]; out->num_mask_tiles = h[1]; out->overflow = h[3]; out->list_builds = h[4]; out->pairs_in_cutoff = h[5];
+    }
+    out->force_evals = ctx->forceEvals; out->kernel_launches = ctx->kernelLaunches;
+    out->pme_grid[0] = ctx->pme.nx; out->pme_grid[1] = ctx->pme.ny; out->pme_grid[2] = ctx->pme.nz; out->ewald_alpha = ctx->pme.alpha;
+    API_END(ctx)
+}
+
+extern "C" int b200md_time_phase(b200md_ctx* ctx, int phase, int reps, double* ms_mean) {
+    API_BEGIN(ctx)
+    require(ctx->finalized, "time_phase before finalize");
+    b200md_ctx* c = ctx;
+    cudaStream_t s = c->stream;
+    cudaEvent_t e0, e1;
+    CUDA_CHECK(cudaEventCreate(&e0)); CUDA_CHECK(cudaEventCreate(&e1));
+    const int one = 1;
+    double total = 0;
+    for (int r = -2; r < reps; r++) {
+        if (phase == 5) CUDA_CHECK(cudaMemcpyAsync(&c->counters.p[2], &one, sizeof(int), cudaMemcpyHostToDevice, s));
+        if (phase == 1) CUDA_CHECK(cudaMemsetAsync(c->grid.p, 0, sizeof(float)*c->grid.n, s));
+        CUDA_CHECK(cudaEventRecord(e0, s));
+        switch (phase) {
+            case 0: launch_pair(c->nb, false, s); break;
+            case 1: launch_pme_spread(c->nb, c->pme, s); break;
+            case 2: launch_pme_fft_conv(c->nb, c->pme, false, s); break;
+            case 3: launch_pme_gather(c->nb, c->pme, s); break;
+            case 4: launch_integrate(c->nb, c->units, c->integ, s); break;
+            case 5: launch_list_build(c->nb, s); break;
+            case 6: launch_bonded(c->nb, c->bd, B200MD_TERM_ALL, false, s); break;
+            default: throw std::runtime_error("unknown phase");
+        }
+        CUDA_CHECK(cudaEventRecord(e1, s));
+        CUDA_CHECK(cudaEventSynchronize(e1));
+        float ms = 0; CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+        if (r >= 0) total += ms;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    *ms_mean = total/std::max(1, reps);
+    API_END(ctx)
+}
+
+// stand-alone FFT for parity tests of the bespoke transform
+static int fft_standalone(int device, int nx, int ny, int nz, const float* in, float* out, bool forward) {
+    try {
+        CUDA_CHECK(cudaSetDevice(device));
+        PmeDev p{}; p.nx = nx; p.ny = ny; p.nz = nz; p.nzc = nz/2 + 1;
+        DevBuf<float> grid; DevBuf<float2> cg; DevBuf<float2> tw[3];
+        grid.alloc((size_t) nx*ny*nz); cg.alloc((size_t) nx*ny*p.nzc);
+        p.grid = grid.p; p.cgrid = cg.p;
+        const int n[3] = {nx, ny, nz};
+        for (int d = 0; d < 3; d++) make_fft_plan(n[d], p.plan[d], tw[d]);
+        int maxSmem = 0;
+        cudaDeviceGetAttribute(&maxSmem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+        require(fft_plane_smem_bytes(ny, nz) <= (size_t) maxSmem && fft_line_smem_bytes(nx) <= (size_t) maxSmem, "grid too large for shared memory");
+        if (forward) {
+            CUDA_CHECK(cudaMemcpy(grid.p, in, sizeof(float)*grid.n, cudaMemcpyHostToDevice));
+            launch_fft3d_r2c(p, 0);
+            CUDA_CHECK(cudaDeviceSynchronize());
+            CUDA_CHECK(cudaMemcpy(out, cg.p, sizeof(float2)*cg.n, cudaMemcpyDeviceToHost));
+        }
+        else {
+            CUDA_CHECK(cudaMemcpy(cg.p, in, sizeof(float2)*cg.n, cudaMemcpyHostToDevice));
+            launch_fft3d_c2r(p, 0);
+            CUDA_CHECK(cudaDeviceSynchronize());
+            CUDA_CHECK(cudaMemcpy(out, grid.p, sizeof(float)*grid.n, cudaMemcpyDeviceToHost));
+        }
+        return 0;
+    } catch (std::exception& e) { g_create_error = e.what(); return -1; }
+}
+extern "C" int b200md_fft3d_r2c(int device, int nx, int ny, int nz, const float* in, float* out) { return fft_standalone(device, nx, ny, nz, in, out, true); }
+extern "C" int b200md_fft3d_c2r(int device, int nx, int ny, int nz, const float* in, float* out) { return fft_standalone(device, nx, ny, nz, in, out, false); }

@@ -1,0 +1,148 @@
+// engine.h -- internal declarations shared by the CUDA translation units of libb200md.so.
+// Public boundary: include/b200md.h.  Data layout and kernel inventory: DESIGN.md.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#define B200MD_TILE 32
+#define B200MD_PME_ORDER 5           // ReferenceLJCoulombIxn.cpp:243 (pme_init(..., 5, 1)); same on every reference platform
+#define B200MD_FORCE_SCALE 4294967296.0   // 2^32 fixed point, as the reference GPU platforms (nonbonded.cu:301-316)
+#define B200MD_ONE_4PI_EPS0 138.93545764438198    // SimTKOpenMMRealType.h:89
+#define B200MD_BOLTZ 0.00831446261815324  // kJ/mol/K, SimTKOpenMMRealType.h:76-80 (CODATA 2018)
+#define B200MD_MAX_RADIX 16
+#define B200MD_MAX_FFT_STAGES 8
+
+#define CUDA_CHECK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) throw std::runtime_error(std::string(#x) + ": " + cudaGetErrorString(e_)); } while (0)
+
+// Periodic box, reduced lower-triangular form (ContextImpl.cpp:267-275): a=(ax,0,0) b=(bx,by,0) c=(cx,cy,cz).
+struct BoxDev {
+    float ax, bx, by, cx, cy, cz;
+    float invAx, invBy, invCz;
+    int triclinic;
+    int periodic;
+    double recip[9];     // recipBoxVectors[i][j] at recip[3*i+j], as invert_box_vectors (ReferencePME.cpp:196-204)
+    double volume;
+};
+
+struct FftPlanDev {      // 1-D mixed-radix Stockham plan for one grid dimension
+    int n;
+    int nstages;
+    int radix[B200MD_MAX_FFT_STAGES];
+    const float2* tw;    // tw[k] = exp(-2 pi i k / n), k < n
+};
+
+// Everything the force kernels need, passed by value.
+struct NbDev {
+    BoxDev box;
+    int natoms, npad, nblocks;
+    int method;                  // B200MD_NB_*
+    int useSwitch;
+    float cutoff, cutoff2, paddedCutoff2, switchDist;
+    float alpha;                 // Ewald alpha
+    float krf, crf;              // reaction field
+    float dispDummy;
+    // user-order state
+    float4* posq;                // xyz + charge*sqrt(ONE_4PI_EPS0)
+    float4* velm;                // v + 1/mass
+    float2* sigeps;              // (sigma/2, 2 sqrt(eps))  (ReferenceKernels.cpp:1093-1097)
+    long long* force;            // [3][npad] fixed point, user order
+    double* energy;              // [B200MD_NUM_ENERGY] accumulators
+    // sorted (nonbonded) copies
+    float4* sposq;
+    float2* ssigeps;
+    float4* sshift;              // lattice shift applied to the atom when it was binned
+    int* sorig;                  // sorted slot -> user atom (-1 for padding)
+    int* sortedOf;               // user atom -> sorted slot
+    float4* refPos;              // user-order positions at the last list build
+    // binning
+    int ncell[3];
+    int ncells;
+    const int* cellRank;         // linear cell -> rank along the space filling curve
+    int* cellCount;              // [ncells+1] -> after scan: start offsets
+    int* cellFill;               // [ncells]
+    int* atomCell;               // [natoms] rank of the atom's cell
+    int* tmpSorted;              // [npad]
+    float4* atomShift;           // [natoms]
+    // blocks and tiles
+    float4* blockCenter;
+    float4* blockHalf;
+    int* tileI;                  // [maxTiles]
+    int* tileJ;                  // [maxTiles*32]
+    int* tileMask;               // [maxTiles] index into maskPool or -1
+    unsigned int* maskPool;      // [maxTiles*32]
+    int maxTiles;
+    int* counters;               // [0]=tiles [1]=mask tiles [2]=rebuild flag [3]=overflow [4]=list builds [5]=pairs(diag) [6]=nan flag
+    // exclusions, CSR in user order
+    const int* exclStart;
+    const int* exclList;
+    float halfPad2;              // (padding/2)^2
+    // multi-GPU sharding of the tile list / PME atoms
+    int rank, world;
+};
+
+enum { EN_NB = 0, EN_RECIP = 1, EN_BOND = 2, EN_ANGLE = 3, EN_TORSION = 4, EN_EXC = 5, EN_KE = 6, B200MD_NUM_ENERGY = 8 };
+
+struct PmeDev {
+    int nx, ny, nz, nzc;
+    float* grid;                 // real [nx][ny][nz]
+    float2* cgrid;               // complex [nx][ny][nzc]
+    float* eterm;                // [nx][ny][nzc] influence function (no ONE_4PI_EPS0: charges carry sqrt of it)
+    const double* moduli[3];
+    FftPlanDev plan[3];          // x, y, z
+    double alpha;
+};
+
+struct BondedDev {
+    int nbonds, nangles, ntorsions, nexc;
+    const int2* bondAtoms; const double2* bondParams;           // (r0, k)
+    const int4* angleAtoms; const double2* angleParams;         // (theta0, k)
+    const int4* torsionAtoms; const double4* torsionParams;     // (k, phase, n, 0)
+    const int2* excAtoms; const double4* excParams;             // (qq14*ONE_4PI_EPS0, sigma, 4 eps, 0)
+    int excPeriodic;
+};
+
+// One integration unit = a SETTLE water, a SHAKE cluster (centre + <=3 H) or a free atom.
+struct UnitDev {
+    int nunits;
+    const int4* unitAtoms;       // atoms (unused = -1); SETTLE: (O,H1,H2,-1)
+    const int* unitType;         // 0 free, 1 SETTLE, 2 SHAKE
+    const float4* unitParams;    // SETTLE: (dOH, dHH, 0, 0); SHAKE: (d1, d2, d3, 0)
+};
+
+struct IntegDev {
+    int kind;
+    float dt, vscale, fscale, noisescale;   // Langevin constants (ReferenceStochasticDynamics.cpp:94-99)
+    float kT;
+    float tol;
+    unsigned int seed;
+    unsigned long long stepIndex;            // not used on device when graphs are active: see stepCounter
+    unsigned long long* stepCounter;         // device counter, incremented by the integrate kernel
+};
+
+// ---- launchers (defined in the .cu files) ----
+void launch_check_displacement(const NbDev& nb, cudaStream_t s);
+void launch_list_build(const NbDev& nb, cudaStream_t s);          // all list kernels, each gated on counters[2]
+void launch_gather_sorted(const NbDev& nb, cudaStream_t s);
+void launch_pair(const NbDev& nb, bool energy, cudaStream_t s);
+void launch_count_pairs(const NbDev& nb, cudaStream_t s);
+int  list_build_launch_count();
+
+void launch_pme_eterm(const NbDev& nb, const PmeDev& pme, cudaStream_t s);
+void launch_pme_spread(const NbDev& nb, const PmeDev& pme, cudaStream_t s);
+void launch_pme_fft_conv(const NbDev& nb, const PmeDev& pme, bool energy, cudaStream_t s);
+void launch_pme_gather(const NbDev& nb, const PmeDev& pme, cudaStream_t s);
+void launch_fft3d_r2c(const PmeDev& pme, cudaStream_t s);         // grid -> cgrid
+void launch_fft3d_c2r(const PmeDev& pme, cudaStream_t s);         // cgrid -> grid
+size_t fft_plane_smem_bytes(int ny, int nz);
+size_t fft_line_smem_bytes(int nx);
+bool fft_make_radices(int n, int* radix, int* nstages);
+
+void launch_bonded(const NbDev& nb, const BondedDev& bd, int terms, bool energy, cudaStream_t s);
+
+void launch_integrate(const NbDev& nb, const UnitDev& units, const IntegDev& integ, cudaStream_t s);
+void launch_constrain_positions(const NbDev& nb, const UnitDev& units, float tol, cudaStream_t s);
+void launch_constrain_velocities(const NbDev& nb, const UnitDev& units, float tol, cudaStream_t s);
+void launch_kinetic_energy(const NbDev& nb, const UnitDev& units, const IntegDev& integ, float shiftDt, cudaStream_t s);
+void launch_remove_cm(const NbDev& nb, double* scratch, cudaStream_t s);

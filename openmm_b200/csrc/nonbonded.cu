@@ -1,0 +1,502 @@
+// nonbonded.cu -- neighbour-list construction and the direct-space 32x32 tile kernel (sm_100a).
+//
+// Replaces (reference, platforms/cuda): findBlockBounds/sortBoxData/findBlocksWithInteractions
+// (findInteractingBlocks.cu:7,54,180), CudaSort (sort.cu), the host-side Hilbert reorder
+// (ComputeContext.cpp:447-612) and computeNonbonded (nonbonded.cu:106-652) with body
+// coulombLennardJones.cc:1-116.  Arithmetic follows ReferenceLJCoulombIxn::calculateEwaldIxn
+// (ReferenceLJCoulombIxn.cpp:373-460) and calculateOneIxn for the cutoff / no-cutoff methods.
+//
+// Design (not the reference's): atoms are fully re-sorted on the device along a space-filling curve of
+// binning cells every time the list is rebuilt; the nonbonded kernels work on the sorted copy (sposq) while
+// integration/bonded code keeps the user's order.  Exclusion masks are generated on the fly while tiles are
+// emitted, so there is no static "exclusion tile" set and no host involvement.
+#include "engine.h"
+#include "../../include/b200md.h"
+
+#define FULL 0xffffffffu
+
+__device__ __forceinline__ float3 min_image(float3 d, const BoxDev& b) {
+    if (b.triclinic) {
+        float s = floorf(d.z*b.invCz + 0.5f);
+        d.x -= s*b.cx; d.y -= s*b.cy; d.z -= s*b.cz;
+        s = floorf(d.y*b.invBy + 0.5f);
+        d.x -= s*b.bx; d.y -= s*b.by;
+        s = floorf(d.x*b.invAx + 0.5f);
+        d.x -= s*b.ax;
+    }
+    else {
+        d.x -= b.ax*rintf(d.x*b.invAx);
+        d.y -= b.by*rintf(d.y*b.invBy);
+        d.z -= b.cz*rintf(d.z*b.invCz);
+    }
+    return d;
+}
+
+// squared distance from the (periodic image of the) point/box centre offset d to an axis-aligned box of half
+// extents h centred at the origin.  Orthorhombic: the per-axis nearest image minimises it.  Triclinic: the 3-step
+// reduction is not guaranteed to pick the image nearest to the BOX, so all 27 neighbouring images are tried
+// (list construction only; the pair kernel applies the reference's own 3-step minimum image per pair).
+__device__ __forceinline__ float box_dist2(float3 d, float hx, float hy, float hz, const BoxDev& b, bool periodic) {
+    if (periodic) d = min_image(d, b);
+    if (!periodic || !b.triclinic) {
+        const float dx = fmaxf(0.f, fabsf(d.x) - hx), dy = fmaxf(0.f, fabsf(d.y) - hy), dz = fmaxf(0.f, fabsf(d.z) - hz);
+        return dx*dx + dy*dy + dz*dz;
+    }
+    float best = 3e38f;
+    for (int sz = -1; sz <= 1; sz++)
+        for (int sy = -1; sy <= 1; sy++)
+            for (int sx = -1; sx <= 1; sx++) {
+                const float x = d.x + sx*b.ax + sy*b.bx + sz*b.cx;
+                const float y = d.y + sy*b.by + sz*b.cy;
+                const float z = d.z + sz*b.cz;
+                const float dx = fmaxf(0.f, fabsf(x) - hx), dy = fmaxf(0.f, fabsf(y) - hy), dz = fmaxf(0.f, fabsf(z) - hz);
+                best = fminf(best, dx*dx + dy*dy + dz*dz);
+            }
+    return best;
+}
+
+// ------------------------------------------------------------------------------------------------
+// 1. rebuild decision: any atom moved more than padding/2 since the last build (findInteractingBlocks.cu:67-76)
+__global__ void k_check_displacement(NbDev nb) {
+    int a = blockIdx.x*blockDim.x + threadIdx.x;
+    if (a >= nb.natoms) return;
+    float4 p = nb.posq[a];
+    float4 r = nb.refPos[a];
+    float dx = p.x-r.x, dy = p.y-r.y, dz = p.z-r.z;
+    float d2 = dx*dx + dy*dy + dz*dz;
+    if (!(d2 <= nb.halfPad2))       // also true for NaN
+        nb.counters[2] = 1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// 2. binning (periodic systems only; non-periodic systems keep the identity order)
+__global__ void k_bin_atoms(NbDev nb) {
+    if (nb.counters[2] == 0) return;
+    int a = blockIdx.x*blockDim.x + threadIdx.x;
+    if (a >= nb.natoms) return;
+    float4 p = nb.posq[a];
+    int key = 0;
+    float4 shift = make_float4(0, 0, 0, 0);
+    if (nb.box.periodic) {
+        const double* R = nb.box.recip;
+        double f[3];
+        f[0] = p.x*R[0] + p.y*R[3] + p.z*R[6];
+        f[1] = p.x*R[1] + p.y*R[4] + p.z*R[7];
+        f[2] = p.x*R[2] + p.y*R[5] + p.z*R[8];
+        int c[3];
+        float fl[3];
+        for (int d = 0; d < 3; d++) {
+            double w = floor(f[d]);
+            fl[d] = (float) w;
+            double fr = f[d] - w;
+            int ci = (int) (fr*nb.ncell[d]);
+            c[d] = min(max(ci, 0), nb.ncell[d]-1);
+        }
+        shift.x = -(fl[0]*nb.box.ax + fl[1]*nb.box.bx + fl[2]*nb.box.cx);
+        shift.y = -(fl[1]*nb.box.by + fl[2]*nb.box.cy);
+        shift.z = -(fl[2]*nb.box.cz);
+        key = nb.cellRank[(c[0]*nb.ncell[1] + c[1])*nb.ncell[2] + c[2]];
+    }
+    else
+        key = 0;
+    nb.atomCell[a] = key;
+    nb.atomShift[a] = shift;
+    atomicAdd(&nb.cellCount[key], 1);
+}
+
+// exclusive scan of cellCount[0..ncells) into cellCount (in place), single block
+__global__ void k_scan_cells(NbDev nb) {
+    if (nb.counters[2] == 0) return;
+    __shared__ int partial[1024];
+    int n = nb.ncells;
+    int per = (n + blockDim.x - 1)/blockDim.x;
+    int begin = threadIdx.x*per, end = min(begin+per, n);
+    int sum = 0;
+    for (int i = begin; i < end; i++) sum += nb.cellCount[i];
+    partial[threadIdx.x] = sum;
+    __syncthreads();
+    // Hillis-Steele inclusive scan over 1024 partials
+    for (int off = 1; off < blockDim.x; off <<= 1) {
+        int v = (threadIdx.x >= off) ? partial[threadIdx.x-off] : 0;
+        __syncthreads();
+        partial[threadIdx.x] += v;
+        __syncthreads();
+    }
+    int run = partial[threadIdx.x] - sum;
+    for (int i = begin; i < end; i++) {
+        int c = nb.cellCount[i];
+        nb.cellCount[i] = run;
+        run += c;
+    }
+    if (threadIdx.x == 0) nb.cellCount[n] = nb.natoms;
+}
+
+__global__ void k_fill_cells(NbDev nb) {
+    if (nb.counters[2] == 0) return;
+    int a = blockIdx.x*blockDim.x + threadIdx.x;
+    if (a >= nb.natoms) return;
+    int key = nb.atomCell[a];
+    int slot = nb.cellCount[key] + atomicAdd(&nb.cellFill[key], 1);
+    nb.tmpSorted[slot] = a;
+}
+
+// make the order inside a cell deterministic (ascending user index)
+__global__ void k_sort_cells(NbDev nb) {
+    if (nb.counters[2] == 0) return;
+    int c = blockIdx.x*blockDim.x + threadIdx.x;
+    if (c >= nb.ncells) return;
+    int begin = nb.cellCount[c], end = nb.cellCount[c+1];
+    if (!nb.box.periodic) return;     // single pseudo cell: handled by identity order below
+    for (int i = begin+1; i < end; i++) {
+        int v = nb.tmpSorted[i];
+        int j = i-1;
+        while (j >= begin && nb.tmpSorted[j] > v) { nb.tmpSorted[j+1] = nb.tmpSorted[j]; j--; }
+        nb.tmpSorted[j+1] = v;
+    }
+}
+
+__global__ void k_finalize_sort(NbDev nb) {
+    if (nb.counters[2] == 0) return;
+    int s = blockIdx.x*blockDim.x + threadIdx.x;
+    if (s >= nb.npad) return;
+    if (s < nb.natoms) {
+        int a = nb.box.periodic ? nb.tmpSorted[s] : s;
+        float4 p = nb.posq[a];
+        float4 sh = nb.atomShift[a];
+        nb.sorig[s] = a;
+        nb.sortedOf[a] = s;
+        nb.sshift[s] = sh;
+        nb.sposq[s] = make_float4(p.x+sh.x, p.y+sh.y, p.z+sh.z, p.w);
+        nb.ssigeps[s] = nb.sigeps[a];
+        nb.refPos[a] = p;
+    }
+    else {
+        nb.sorig[s] = -1;
+        nb.sshift[s] = make_float4(0, 0, 0, 0);
+        nb.ssigeps[s] = make_float2(0, 0);
+        // position is filled by k_block_bounds with a copy of a real atom of the same block
+    }
+}
+
+// one warp per block of 32 sorted atoms: axis-aligned bounding box (findBlockBounds, findInteractingBlocks.cu:7-52)
+__global__ void k_block_bounds(NbDev nb) {
+    if (nb.counters[2] == 0) return;
+    int warp = (blockIdx.x*blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (warp >= nb.nblocks) return;
+    int s = warp*32 + lane;
+    int sl = min(s, nb.natoms-1);
+    float4 p = nb.sposq[sl];
+    if (s >= nb.natoms) nb.sposq[s] = make_float4(p.x, p.y, p.z, 0.f);
+    float lox = p.x, hix = p.x, loy = p.y, hiy = p.y, loz = p.z, hiz = p.z;
+    for (int off = 16; off > 0; off >>= 1) {
+        lox = fminf(lox, __shfl_xor_sync(FULL, lox, off)); hix = fmaxf(hix, __shfl_xor_sync(FULL, hix, off));
+        loy = fminf(loy, __shfl_xor_sync(FULL, loy, off)); hiy = fmaxf(hiy, __shfl_xor_sync(FULL, hiy, off));
+        loz = fminf(loz, __shfl_xor_sync(FULL, loz, off)); hiz = fmaxf(hiz, __shfl_xor_sync(FULL, hiz, off));
+    }
+    if (lane == 0) {
+        nb.blockCenter[warp] = make_float4(0.5f*(lox+hix), 0.5f*(loy+hiy), 0.5f*(loz+hiz), 0);
+        nb.blockHalf[warp] = make_float4(0.5f*(hix-lox), 0.5f*(hiy-loy), 0.5f*(hiz-loz), 0);
+    }
+    if (warp == 0 && lane == 0) { nb.counters[0] = 0; nb.counters[1] = 0; }
+}
+
+// Emit one tile from the first `count` entries of buf (ascending sorted indices).
+__device__ void flush_tile(const NbDev& nb, int ib, const int* buf, int count, bool diagonal, int lane) {
+    int t = 0;
+    if (lane == 0) t = atomicAdd(&nb.counters[0], 1);
+    t = __shfl_sync(FULL, t, 0);
+    if (t >= nb.maxTiles) { if (lane == 0) nb.counters[3] = 1; return; }
+    int myj = (lane < count) ? buf[lane] : -1;
+    nb.tileJ[t*32 + lane] = myj;
+    unsigned int valid = (count >= 32) ? FULL : ((1u << count) - 1u);
+    unsigned int mask = valid;
+    bool need = (count < 32);
+    int si = ib*32 + lane;
+    if (diagonal) {            // own block against itself: keep j > i only
+        unsigned int le = (lane == 31) ? FULL : ((2u << lane) - 1u);
+        mask &= ~le;
+        need = true;
+    }
+    if (si >= nb.natoms) { mask = 0; need = true; }
+    else {
+        int a = nb.sorig[si];
+        int e0 = nb.exclStart[a], e1 = nb.exclStart[a+1];
+        int jlo = buf[0], jhi = buf[count-1];
+        for (int e = e0; e < e1; e++) {
+            int sj = nb.sortedOf[nb.exclList[e]];
+            if (sj < jlo || sj > jhi) continue;
+            int lo = 0, hi = count-1;          // binary search in the ascending tile
+            while (lo < hi) { int mid = (lo+hi) >> 1; if (buf[mid] < sj) lo = mid+1; else hi = mid; }
+            if (buf[lo] == sj) { mask &= ~(1u << lo); need = true; }
+        }
+    }
+    need = __any_sync(FULL, need);
+    int mi = -1;
+    if (need) {
+        if (lane == 0) mi = atomicAdd(&nb.counters[1], 1);
+        mi = __shfl_sync(FULL, mi, 0);
+        nb.maskPool[mi*32 + lane] = mask;     // capacity == maxTiles, and mask tiles <= tiles
+    }
+    if (lane == 0) { nb.tileI[t] = ib; nb.tileMask[t] = mi; }
+}
+
+// one warp per i-block: cull j-blocks by box distance, then j-atoms against the i-block box, compact into
+// tiles of 32 (findBlocksWithInteractions, findInteractingBlocks.cu:180-405 is the reference counterpart).
+__global__ void __launch_bounds__(128) k_build_tiles(NbDev nb) {
+    if (nb.counters[2] == 0) return;
+    __shared__ int sbuf[4][64];
+    int wib = threadIdx.x >> 5;
+    int lane = threadIdx.x & 31;
+    int ib = blockIdx.x*4 + wib;
+    if (ib >= nb.nblocks) return;
+    int* buf = sbuf[wib];
+    float4 ci = nb.blockCenter[ib];
+    float4 hi = nb.blockHalf[ib];
+    const bool periodic = nb.box.periodic != 0;
+    const bool allPairs = (nb.method == B200MD_NB_NOCUTOFF);
+    int nbuf = 0;
+    for (int jb0 = ib; jb0 < nb.nblocks; jb0 += 32) {
+        int jb = jb0 + lane;
+        bool cand = false;
+        if (jb < nb.nblocks) {
+            if (allPairs || jb == ib) cand = true;
+            else {
+                float4 cj = nb.blockCenter[jb];
+                float4 hj = nb.blockHalf[jb];
+                float3 d = make_float3(cj.x-ci.x, cj.y-ci.y, cj.z-ci.z);
+                cand = (box_dist2(d, hi.x+hj.x, hi.y+hj.y, hi.z+hj.z, nb.box, periodic) < nb.paddedCutoff2);
+            }
+        }
+        unsigned int bits = __ballot_sync(FULL, cand);
+        while (bits) {
+            int b = __ffs(bits) - 1;
+            bits &= bits - 1;
+            int jblk = jb0 + b;
+            int sj = jblk*32 + lane;
+            bool inc = false;
+            if (sj < nb.natoms) {
+                if (allPairs || jblk == ib) inc = true;
+                else {
+                    float4 pj = nb.sposq[sj];
+                    float3 d = make_float3(pj.x-ci.x, pj.y-ci.y, pj.z-ci.z);
+                    inc = (box_dist2(d, hi.x, hi.y, hi.z, nb.box, periodic) < nb.paddedCutoff2);
+                }
+            }
+            unsigned int m = __ballot_sync(FULL, inc);
+            int pos = nbuf + __popc(m & ((1u << lane) - 1u));
+            if (inc) buf[pos] = sj;
+            nbuf += __popc(m);
+            __syncwarp();
+            if (jblk == ib) {
+                // the diagonal tile is always emitted on its own so that its mask is the simple j>i triangle
+                flush_tile(nb, ib, buf, nbuf, true, lane);
+                nbuf = 0;
+                __syncwarp();
+            }
+            else if (nbuf >= 32) {
+                flush_tile(nb, ib, buf, 32, false, lane);
+                int v = (lane + 32 < nbuf) ? buf[lane+32] : 0;
+                __syncwarp();
+                buf[lane] = v;
+                nbuf -= 32;
+                __syncwarp();
+            }
+        }
+    }
+    if (nbuf > 0) flush_tile(nb, ib, buf, nbuf, false, lane);
+}
+
+__global__ void k_list_done(NbDev nb) {
+    if (nb.counters[2] == 0) return;
+    if (threadIdx.x == 0 && blockIdx.x == 0) { nb.counters[2] = 0; nb.counters[4] += 1; }
+}
+
+// every step: refresh the sorted copy of the positions
+__global__ void k_gather_sorted(NbDev nb) {
+    int s = blockIdx.x*blockDim.x + threadIdx.x;
+    if (s >= nb.npad) return;
+    int a = nb.sorig[s];
+    if (a < 0) a = nb.sorig[nb.natoms-1];
+    float4 p = nb.posq[a];
+    float4 sh = nb.sshift[min(s, nb.natoms-1)];
+    if (s >= nb.natoms) p.w = 0.f;
+    nb.sposq[s] = make_float4(p.x+sh.x, p.y+sh.y, p.z+sh.z, p.w);
+}
+
+void launch_check_displacement(const NbDev& nb, cudaStream_t s) {
+    k_check_displacement<<<(nb.natoms+255)/256, 256, 0, s>>>(nb);
+}
+
+int list_build_launch_count() { return 9; }
+
+void launch_list_build(const NbDev& nb, cudaStream_t s) {
+    // the two memsets are unconditional (cheap); every kernel returns immediately unless counters[2] is set
+    cudaMemsetAsync(nb.cellCount, 0, sizeof(int)*(nb.ncells+1), s);
+    cudaMemsetAsync(nb.cellFill, 0, sizeof(int)*nb.ncells, s);
+    int nbk = (nb.natoms+255)/256;
+    k_bin_atoms<<<nbk, 256, 0, s>>>(nb);
+    k_scan_cells<<<1, 1024, 0, s>>>(nb);
+    k_fill_cells<<<nbk, 256, 0, s>>>(nb);
+    k_sort_cells<<<(nb.ncells+127)/128, 128, 0, s>>>(nb);
+    k_finalize_sort<<<(nb.npad+255)/256, 256, 0, s>>>(nb);
+    k_block_bounds<<<(nb.nblocks*32+255)/256, 256, 0, s>>>(nb);
+    k_build_tiles<<<(nb.nblocks+3)/4, 128, 0, s>>>(nb);
+    k_list_done<<<1, 32, 0, s>>>(nb);
+}
+
+void launch_gather_sorted(const NbDev& nb, cudaStream_t s) {
+    k_gather_sorted<<<(nb.npad+255)/256, 256, 0, s>>>(nb);
+}
+
+// ------------------------------------------------------------------------------------------------
+// The direct-space kernel.  One warp per 32x32 tile; lane = i-atom; the 32 j-atoms rotate through the
+// lanes by shuffle so every lane sees every j once.  Forces leave the tile as 2^32 fixed point.
+//
+// Per pair (ReferenceLJCoulombIxn.cpp:388-447), with q pre-multiplied by sqrt(ONE_4PI_EPS0):
+//   PME:    dEdR = qi qj/r^3 (erfc(ar) + 2 ar exp(-a^2 r^2)/sqrt(pi)) + sw*eps(12 s^12 - 6 s^6)/r^2 [- E_lj sw'/r]
+//           E    = qi qj erfc(ar)/r + sw*eps (s^12 - s^6)
+//   cutoff: reaction field (ReferenceLJCoulombIxn.cpp:559-575): dEdR = qi qj (1/r^3 - 2 krf) ..., E = qi qj (1/r + krf r^2 - crf)
+template <bool ENERGY, int METHOD>
+__global__ void __launch_bounds__(256) k_pair(NbDev nb) {
+    const int lane = threadIdx.x & 31;
+    const int gwarp = (blockIdx.x*blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x*blockDim.x) >> 5;
+    const int ntiles = min(nb.counters[0], nb.maxTiles);
+    const bool periodic = nb.box.periodic != 0;
+    float energy = 0.f;
+    // tiles are dealt round-robin over (rank, warp): the multi-GPU force decomposition shards this loop
+    for (int t = nb.rank + nb.world*gwarp; t < ntiles; t += nb.world*nwarps) {
+        const int ib = nb.tileI[t];
+        const int si = ib*32 + lane;
+        const float4 pi = nb.sposq[si];
+        const float2 sei = nb.ssigeps[si];
+        const int jidx = nb.tileJ[t*32 + lane];
+        const int jj = max(jidx, 0);
+        float4 pj = nb.sposq[jj];
+        float2 sej = nb.ssigeps[jj];
+        const int mi = nb.tileMask[t];
+        const unsigned int mask = (mi < 0) ? FULL : nb.maskPool[mi*32 + lane];
+        float fix = 0.f, fiy = 0.f, fiz = 0.f, fjx = 0.f, fjy = 0.f, fjz = 0.f;
+        const int src = (lane + 1) & 31;
+#pragma unroll 4
+        for (int k = 0; k < 32; k++) {
+            const int slot = (lane + k) & 31;
+            float3 d = make_float3(pj.x-pi.x, pj.y-pi.y, pj.z-pi.z);
+            if (periodic) d = min_image(d, nb.box);
+            const float r2 = d.x*d.x + d.y*d.y + d.z*d.z;
+            if (((mask >> slot) & 1u) && r2 < nb.cutoff2) {
+                const float invR = rsqrtf(r2);
+                const float r = r2*invR;
+                const float invR2 = invR*invR;
+                const float qq = pi.w*pj.w;
+                float dEdR, e;
+                if (METHOD == B200MD_NB_PME) {
+                    const float ar = nb.alpha*r;
+                    const float ex = __expf(-ar*ar);
+                    // erfc: Abramowitz-Stegun 7.1.26, |err| < 1.5e-7 (same form as coulombLennardJones.cc:15-20)
+                    const float tt = __fdividef(1.0f, 1.0f + 0.3275911f*ar);
+                    const float erfcAr = (0.254829592f+(-0.284496736f+(1.421413741f+(-1.453152027f+1.061405429f*tt)*tt)*tt)*tt)*tt*ex;
+                    const float pref = qq*invR;
+                    dEdR = pref*invR2*(erfcAr + 1.1283791671f*ar*ex);
+                    e = pref*erfcAr;
+                }
+                else if (METHOD == B200MD_NB_NOCUTOFF) {
+                    const float pref = qq*invR;
+                    dEdR = pref*invR2;
+                    e = pref;
+                }
+                else {   // cutoff with reaction field
+                    dEdR = qq*(invR*invR2 - 2.0f*nb.krf);
+                    e = qq*(invR + nb.krf*r2 - nb.crf);
+                }
+                const float sig = sei.x + sej.x;
+                const float eps = sei.y*sej.y;
+                float s2 = sig*invR; s2 *= s2;
+                const float s6 = s2*s2*s2;
+                float ljF = eps*(12.0f*s6 - 6.0f)*s6*invR2;
+                float ljE = eps*(s6 - 1.0f)*s6;
+                if (nb.useSwitch && r > nb.switchDist) {
+                    const float w = nb.cutoff - nb.switchDist;
+                    const float x = (r - nb.switchDist)/w;
+                    const float sw = 1.0f + x*x*x*(-10.0f + x*(15.0f - x*6.0f));
+                    const float dsw = x*x*(-30.0f + x*(60.0f - x*30.0f))/w;
+                    ljF = sw*ljF - ljE*dsw*invR;
+                    ljE *= sw;
+                }
+                dEdR += ljF;
+                if (ENERGY) energy += e + ljE;
+                fix -= d.x*dEdR; fiy -= d.y*dEdR; fiz -= d.z*dEdR;
+                fjx += d.x*dEdR; fjy += d.y*dEdR; fjz += d.z*dEdR;
+            }
+            pj.x = __shfl_sync(FULL, pj.x, src); pj.y = __shfl_sync(FULL, pj.y, src);
+            pj.z = __shfl_sync(FULL, pj.z, src); pj.w = __shfl_sync(FULL, pj.w, src);
+            sej.x = __shfl_sync(FULL, sej.x, src); sej.y = __shfl_sync(FULL, sej.y, src);
+            fjx = __shfl_sync(FULL, fjx, src); fjy = __shfl_sync(FULL, fjy, src); fjz = __shfl_sync(FULL, fjz, src);
+        }
+        // after 32 rotations every lane holds its own j again
+        const int ai = nb.sorig[si];
+        if (ai >= 0) {
+            atomicAdd((unsigned long long*) &nb.force[ai], (unsigned long long) __float2ll_rn(fix*4294967296.0f));
+            atomicAdd((unsigned long long*) &nb.force[ai + nb.npad], (unsigned long long) __float2ll_rn(fiy*4294967296.0f));
+            atomicAdd((unsigned long long*) &nb.force[ai + 2*nb.npad], (unsigned long long) __float2ll_rn(fiz*4294967296.0f));
+        }
+        if (jidx >= 0) {
+            const int aj = nb.sorig[jidx];
+            atomicAdd((unsigned long long*) &nb.force[aj], (unsigned long long) __float2ll_rn(fjx*4294967296.0f));
+            atomicAdd((unsigned long long*) &nb.force[aj + nb.npad], (unsigned long long) __float2ll_rn(fjy*4294967296.0f));
+            atomicAdd((unsigned long long*) &nb.force[aj + 2*nb.npad], (unsigned long long) __float2ll_rn(fjz*4294967296.0f));
+        }
+    }
+    if (ENERGY) {
+        for (int off = 16; off > 0; off >>= 1) energy += __shfl_xor_sync(FULL, energy, off);
+        if (lane == 0 && energy != 0.f) atomicAdd(&nb.energy[EN_NB], (double) energy);
+    }
+}
+
+template <bool ENERGY>
+static void launch_pair_m(const NbDev& nb, cudaStream_t s) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    dim3 grid(sms*4), block(256);
+    switch (nb.method) {
+        case B200MD_NB_PME: k_pair<ENERGY, B200MD_NB_PME><<<grid, block, 0, s>>>(nb); break;
+        case B200MD_NB_NOCUTOFF: k_pair<ENERGY, B200MD_NB_NOCUTOFF><<<grid, block, 0, s>>>(nb); break;
+        default: k_pair<ENERGY, B200MD_NB_CUTOFF_PERIODIC><<<grid, block, 0, s>>>(nb); break;
+    }
+}
+
+void launch_pair(const NbDev& nb, bool energy, cudaStream_t s) {
+    if (energy) launch_pair_m<true>(nb, s); else launch_pair_m<false>(nb, s);
+}
+
+// diagnostic: number of pairs inside the true cutoff that the list evaluates (tile efficiency accounting)
+__global__ void k_count_pairs(NbDev nb) {
+    const int lane = threadIdx.x & 31;
+    const int gwarp = (blockIdx.x*blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x*blockDim.x) >> 5;
+    const int ntiles = min(nb.counters[0], nb.maxTiles);
+    int count = 0;
+    for (int t = gwarp; t < ntiles; t += nwarps) {
+        const int si = nb.tileI[t]*32 + lane;
+        const float4 pi = nb.sposq[si];
+        const int mi = nb.tileMask[t];
+        const unsigned int mask = (mi < 0) ? FULL : nb.maskPool[mi*32 + lane];
+        for (int k = 0; k < 32; k++) {
+            int jidx = nb.tileJ[t*32 + k];
+            if (jidx < 0 || !((mask >> k) & 1u)) continue;
+            float4 pj = nb.sposq[jidx];
+            float3 d = make_float3(pj.x-pi.x, pj.y-pi.y, pj.z-pi.z);
+            if (nb.box.periodic) d = min_image(d, nb.box);
+            if (d.x*d.x + d.y*d.y + d.z*d.z < nb.cutoff2) count++;
+        }
+    }
+    for (int off = 16; off > 0; off >>= 1) count += __shfl_xor_sync(FULL, count, off);
+    if (lane == 0 && count) atomicAdd(&nb.counters[5], count);
+}
+
+void launch_count_pairs(const NbDev& nb, cudaStream_t s) {
+    cudaMemsetAsync(&nb.counters[5], 0, sizeof(int), s);
+    k_count_pairs<<<148*4, 256, 0, s>>>(nb);
+}

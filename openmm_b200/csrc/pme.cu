@@ -1,0 +1,175 @@
+// pme.cu -- PME charge spreading, influence function and force interpolation (sm_100a).
+//
+// Restates pme_update_grid_index_and_fraction / pme_update_bsplines / pme_grid_spread_charge /
+// pme_grid_interpolate_force / pme_calculate_bsplines_moduli (ReferencePME.cpp:98-193, 206-405, 617-713);
+// replaces findAtomGridIndex / gridSpreadCharge / finishSpreadCharge / gridInterpolateForce of the
+// reference GPU platforms (platforms/common/src/kernels/pme.cc:1-161, 506-606).  Order-5 cardinal B-splines,
+// forward-only stencil with periodic wrap, charges carry sqrt(ONE_4PI_EPS0).
+#include "engine.h"
+
+#define ORDER B200MD_PME_ORDER
+
+// theta / dtheta for one axis, the recursion of pme_update_bsplines (ReferencePME.cpp:274-327)
+__device__ __forceinline__ void bspline(float dr, float* data, float* ddata) {
+    data[ORDER-1] = 0.f;
+    data[1] = dr;
+    data[0] = 1.f - dr;
+#pragma unroll
+    for (int k = 3; k < ORDER; k++) {
+        const float div = 1.f/(k - 1.f);
+        data[k-1] = div*dr*data[k-2];
+#pragma unroll
+        for (int l = 1; l < k-1; l++)
+            data[k-l-1] = div*((dr + l)*data[k-l-2] + (k - l - dr)*data[k-l-1]);
+        data[0] = div*(1.f - dr)*data[0];
+    }
+    ddata[0] = -data[0];
+#pragma unroll
+    for (int k = 1; k < ORDER; k++) ddata[k] = data[k-1] - data[k];
+    const float div = 1.f/(ORDER - 1);
+    data[ORDER-1] = div*dr*data[ORDER-2];
+#pragma unroll
+    for (int l = 1; l < ORDER-1; l++)
+        data[ORDER-l-1] = div*((dr + l)*data[ORDER-l-2] + (ORDER - l - dr)*data[ORDER-l-1]);
+    data[0] = div*(1.f - dr)*data[0];
+}
+
+// grid index and fraction (ReferencePME.cpp:206-266); the fractional coordinate is formed in double so that the
+// B-spline argument keeps full fp32 precision on 128-point grids
+// returns false for a non-finite coordinate (the atom is skipped; the NaN shows up in the integrator instead of
+// as an out-of-bounds grid access)
+__device__ __forceinline__ bool grid_index(const float4& p, const NbDev& nb, const PmeDev& pme, int* idx, float* frac) {
+    const double* R = nb.box.recip;
+    const int n[3] = {pme.nx, pme.ny, pme.nz};
+    bool ok = true;
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+        double t = p.x*R[d] + p.y*R[3+d] + p.z*R[6+d];
+        t = (t - floor(t))*n[d];
+        ok = ok && (t >= 0.0) && (t <= (double) n[d]);
+        int ti = (int) t;
+        frac[d] = (float) (t - ti);
+        idx[d] = (ti >= n[d]) ? ti - n[d] : ti;
+    }
+    return ok;
+}
+
+__global__ void __launch_bounds__(128) k_pme_spread(NbDev nb, PmeDev pme) {
+    // atoms are dealt to ranks in contiguous chunks of the sorted order (multi-GPU: each rank spreads its share)
+    const int per = (nb.natoms + nb.world - 1)/nb.world;
+    const int s = nb.rank*per + blockIdx.x*blockDim.x + threadIdx.x;
+    if (s >= min(nb.natoms, (nb.rank+1)*per)) return;
+    const float4 p = nb.sposq[s];
+    if (p.w == 0.f) return;
+    int idx[3];
+    float fr[3];
+    if (!grid_index(p, nb, pme, idx, fr)) return;
+    float tx[ORDER], ty[ORDER], tz[ORDER], dd[ORDER];
+    bspline(fr[0], tx, dd);
+    bspline(fr[1], ty, dd);
+    bspline(fr[2], tz, dd);
+#pragma unroll
+    for (int ix = 0; ix < ORDER; ix++) {
+        int xi = idx[0] + ix; if (xi >= pme.nx) xi -= pme.nx;
+        const float qx = p.w*tx[ix];
+#pragma unroll
+        for (int iy = 0; iy < ORDER; iy++) {
+            int yi = idx[1] + iy; if (yi >= pme.ny) yi -= pme.ny;
+            const float qxy = qx*ty[iy];
+            float* row = pme.grid + ((size_t) xi*pme.ny + yi)*pme.nz;
+#pragma unroll
+            for (int iz = 0; iz < ORDER; iz++) {
+                int zi = idx[2] + iz; if (zi >= pme.nz) zi -= pme.nz;
+                atomicAdd(row + zi, qxy*tz[iz]);
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128) k_pme_gather(NbDev nb, PmeDev pme) {
+    const int per = (nb.natoms + nb.world - 1)/nb.world;
+    const int s = nb.rank*per + blockIdx.x*blockDim.x + threadIdx.x;
+    if (s >= min(nb.natoms, (nb.rank+1)*per)) return;
+    const float4 p = nb.sposq[s];
+    if (p.w == 0.f) return;
+    int idx[3];
+    float fr[3];
+    if (!grid_index(p, nb, pme, idx, fr)) return;
+    float tx[ORDER], ty[ORDER], tz[ORDER], dx[ORDER], dy[ORDER], dz[ORDER];
+    bspline(fr[0], tx, dx);
+    bspline(fr[1], ty, dy);
+    bspline(fr[2], tz, dz);
+    float fx = 0.f, fy = 0.f, fz = 0.f;
+#pragma unroll
+    for (int ix = 0; ix < ORDER; ix++) {
+        int xi = idx[0] + ix; if (xi >= pme.nx) xi -= pme.nx;
+#pragma unroll
+        for (int iy = 0; iy < ORDER; iy++) {
+            int yi = idx[1] + iy; if (yi >= pme.ny) yi -= pme.ny;
+            const float* row = pme.grid + ((size_t) xi*pme.ny + yi)*pme.nz;
+            float sz = 0.f, sdz = 0.f;
+#pragma unroll
+            for (int iz = 0; iz < ORDER; iz++) {
+                int zi = idx[2] + iz; if (zi >= pme.nz) zi -= pme.nz;
+                const float g = __ldg(row + zi);
+                sz += tz[iz]*g;
+                sdz += dz[iz]*g;
+            }
+            fx += dx[ix]*ty[iy]*sz;
+            fy += tx[ix]*dy[iy]*sz;
+            fz += tx[ix]*ty[iy]*sdz;
+        }
+    }
+    // ReferencePME.cpp:708-711 (triclinic-aware)
+    const double* R = nb.box.recip;
+    const float q = p.w;
+    const float gx = fx*pme.nx, gy = fy*pme.ny, gz = fz*pme.nz;
+    const float Fx = -q*(gx*(float) R[0]);
+    const float Fy = -q*(gx*(float) R[3] + gy*(float) R[4]);
+    const float Fz = -q*(gx*(float) R[6] + gy*(float) R[7] + gz*(float) R[8]);
+    const int a = nb.sorig[s];
+    atomicAdd((unsigned long long*) &nb.force[a], (unsigned long long) __float2ll_rn(Fx*4294967296.0f));
+    atomicAdd((unsigned long long*) &nb.force[a + nb.npad], (unsigned long long) __float2ll_rn(Fy*4294967296.0f));
+    atomicAdd((unsigned long long*) &nb.force[a + 2*nb.npad], (unsigned long long) __float2ll_rn(Fz*4294967296.0f));
+}
+
+// influence function on the half-complex grid (pme_reciprocal_convolution, ReferencePME.cpp:409-514), computed in
+// double once per box change.  eterm = exp(-pi^2 m^2/alpha^2) / (pi V m^2 bx by bz); the (0,0,0) term is zero
+// (the reference skips it; its inverse transform is a constant and exerts no force).
+__global__ void k_pme_eterm(NbDev nb, PmeDev pme) {
+    const size_t total = (size_t) pme.nx*pme.ny*pme.nzc;
+    const size_t i = (size_t) blockIdx.x*blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int kz = (int) (i % pme.nzc);
+    const int ky = (int) ((i / pme.nzc) % pme.ny);
+    const int kx = (int) (i / ((size_t) pme.nzc*pme.ny));
+    if (kx == 0 && ky == 0 && kz == 0) { pme.eterm[i] = 0.f; return; }
+    const double* R = nb.box.recip;
+    const double mx = (kx < (pme.nx+1)/2) ? kx : kx - pme.nx;
+    const double my = (ky < (pme.ny+1)/2) ? ky : ky - pme.ny;
+    const double mz = (kz < (pme.nz+1)/2) ? kz : kz - pme.nz;
+    const double mhx = mx*R[0];
+    const double mhy = mx*R[3] + my*R[4];
+    const double mhz = mx*R[6] + my*R[7] + mz*R[8];
+    const double m2 = mhx*mhx + mhy*mhy + mhz*mhz;
+    const double pi = 3.14159265358979323846;
+    const double factor = pi*pi/(pme.alpha*pme.alpha);
+    const double denom = m2*pi*nb.box.volume*pme.moduli[0][kx]*pme.moduli[1][ky]*pme.moduli[2][kz];
+    pme.eterm[i] = (float) (exp(-factor*m2)/denom);
+}
+
+void launch_pme_eterm(const NbDev& nb, const PmeDev& pme, cudaStream_t s) {
+    size_t total = (size_t) pme.nx*pme.ny*pme.nzc;
+    k_pme_eterm<<<(unsigned) ((total + 255)/256), 256, 0, s>>>(nb, pme);
+}
+
+void launch_pme_spread(const NbDev& nb, const PmeDev& pme, cudaStream_t s) {
+    cudaMemsetAsync(pme.grid, 0, sizeof(float)*(size_t) pme.nx*pme.ny*pme.nz, s);
+    const int per = (nb.natoms + nb.world - 1)/nb.world;
+    k_pme_spread<<<(per + 127)/128, 128, 0, s>>>(nb, pme);
+}
+
+void launch_pme_gather(const NbDev& nb, const PmeDev& pme, cudaStream_t s) {
+    const int per = (nb.natoms + nb.world - 1)/nb.world;
+    k_pme_gather<<<(per + 127)/128, 128, 0, s>>>(nb, pme);
+}

@@ -1,0 +1,283 @@
+"""GPU parity tests (pytest -m gpu): the CUDA hot path, called through the C-ABI, against
+ (a) the reference itself (oracle/_ref: the unmodified Reference platform, double precision) on identical inputs,
+ (b) the committed golden fixtures (Gromacs known answers held by the reference's own tests),
+ (c) the plain-C oracle (oracle/md_oracle.c),
+ (d) size-independent properties at the benchmark size (momentum conservation, constraint satisfaction, energy/force
+     consistency by finite differences, determinism).
+Tolerance: 1e-4 relative in the reference's own ASSERT_EQUAL_VEC form (BASELINE.json north_star)."""
+import json
+import os
+import numpy as np
+import pytest
+from conftest import relative_force_error, GOLDEN
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def mods():
+    from openmm_b200 import systems, Engine, engine
+    from oracle import omm, port
+    return systems, Engine, engine, omm, port
+
+
+def _compare(mods, desc, pme=None, tol=TOL, etol=TOL):
+    systems, Engine, engine, omm, port = mods
+    eng = Engine(desc)
+    e = eng.compute()
+    f = eng.get_forces()
+    if pme is None and desc.method == systems.NB_PME:
+        pme = desc.pme_parameters()
+    sim = omm.Simulation(desc, "Reference", pme=pme)
+    fr, er = sim.forces_energy()
+    assert relative_force_error(f, fr) < tol
+    assert abs(e - er)/max(1.0, abs(er)) < etol
+    assert eng.stats()["overflow"] == 0
+    return eng, sim
+
+
+# ---- the bespoke FFT against numpy (template: platforms/cuda/tests/TestCudaFFT3D.cpp:52-135, same odd sizes) ----
+@pytest.mark.parametrize("shape", [(28, 25, 30), (28, 25, 25), (25, 28, 25), (25, 25, 28), (21, 25, 27), (56, 56, 56), (88, 88, 88), (90, 90, 90), (128, 128, 128), (6, 6, 6)])
+def test_fft3d_matches_numpy(mods, shape):
+    _, _, engine, _, _ = mods
+    rng = np.random.default_rng(sum(shape))
+    x = rng.standard_normal(shape).astype(np.float32)
+    ref = np.fft.rfftn(x.astype(np.float64))
+    out = engine.fft3d_r2c(x)
+    assert np.abs(out - ref).max()/np.abs(ref).max() < 2e-6
+    back = engine.fft3d_c2r(ref.astype(np.complex64), shape[2])
+    assert np.abs(back/np.prod(shape) - x).max() < 1e-5        # unnormalised round trip scales by N (fftpack.h:80-92)
+
+
+def test_fft_rejects_unsupported_size(mods):
+    _, _, engine, _, _ = mods
+    with pytest.raises(engine.EngineError):
+        engine.fft3d_r2c(np.zeros((34, 8, 8), np.float32))      # 17 is not a supported radix
+
+
+# ---- golden vectors held by the reference's own tests ----
+def test_gromacs_triclinic_golden(mods):
+    systems, Engine, *_ = mods
+    g = json.load(open(os.path.join(GOLDEN, "ewald_triclinic_gromacs.json")))
+    d = systems.SystemDesc(masses=np.ones(8), charges=np.array(g["charges"]), sigmas=np.array(g["sigmas"]), epsilons=np.array(g["epsilons"]),
+                           positions=np.array(g["positions"]), box=np.array(g["box"]), method=systems.NB_PME, cutoff=g["cutoff"],
+                           pme_alpha=g["alpha"], pme_grid=tuple(g["grid"]), use_dispersion=False)
+    eng = Engine(d)
+    e = eng.compute()
+    assert relative_force_error(eng.get_forces(), np.array(g["expected_forces"])) < g["tolerance"]     # TestEwald.h:268
+    assert abs(e - g["expected_energy"])/abs(g["expected_energy"]) < g["tolerance"]
+
+
+def test_nacl_amorph_fixture(mods):
+    systems, Engine, *_ = mods
+    z = np.load(os.path.join(GOLDEN, "nacl_amorph.npz"))
+    n, L = 894, float(z["box"])
+    pme = z["pme"]
+    d = systems.SystemDesc(masses=np.ones(n), charges=z["charges"], sigmas=np.ones(n), epsilons=np.zeros(n), positions=z["positions"],
+                           box=np.diag([L, L, L]), method=systems.NB_PME, cutoff=float(z["cutoff"]),
+                           pme_alpha=float(pme[0]), pme_grid=(int(pme[1]), int(pme[2]), int(pme[3])))
+    eng = Engine(d)
+    e = eng.compute()
+    assert relative_force_error(eng.get_forces(), z["reference_forces"]) < TOL
+    assert abs(e - float(z["reference_energy"]))/abs(e) < 1e-5           # TestEwald.h:147-149 asks 1e-5 on the energy
+    assert abs(e - float(z["gromacs_energy"]))/abs(e) < 1e-5
+
+
+def test_water5_fixture_and_c_oracle(mods):
+    systems, Engine, _, _, port = mods
+    z = np.load(os.path.join(GOLDEN, "water5_reference.npz"))
+    d = systems.water_box(5, cutoff=0.75).rounded()
+    eng = Engine(d)
+    e = eng.compute()
+    f = eng.get_forces()
+    assert relative_force_error(f, z["reference_forces"]) < TOL
+    assert abs(e - float(z["reference_energy"]))/abs(e) < TOL
+    fp, ep, _ = port.forces_energy(d)
+    assert relative_force_error(f, fp) < TOL and abs(e - ep)/abs(ep) < TOL
+
+
+# ---- against the reference itself on identical (fp32-representable) inputs ----
+def test_nocutoff_cluster(mods):
+    _compare(mods, mods[0].cluster(70).rounded())
+
+
+def test_cutoff_nonperiodic(mods):
+    _compare(mods, mods[0].cluster(500, method=mods[0].NB_CUTOFF_NONPERIODIC).rounded())
+
+
+def test_cutoff_periodic_lj_and_reaction_field(mods):
+    systems = mods[0]
+    _compare(mods, systems.lj_fluid(8, cutoff=1.0).rounded())
+    _compare(mods, systems.lj_fluid(8, cutoff=1.0, charged=True).rounded())
+
+
+def test_switching_function_and_dispersion(mods):
+    systems = mods[0]
+    d = systems.lj_fluid(8, cutoff=1.0).rounded()
+    d.use_switch, d.switch_distance = True, 0.8
+    _compare(mods, d)
+
+
+def test_pme_water_rigid_and_flexible(mods):
+    systems = mods[0]
+    _compare(mods, systems.water_box(7, cutoff=0.9).rounded())
+    _compare(mods, systems.water_box(7, cutoff=0.9, rigid=False).rounded())
+
+
+def test_pme_ions_cubic_and_triclinic(mods):
+    systems = mods[0]
+    _compare(mods, systems.random_ions(894, 3.0, cutoff=1.0).rounded())
+    _compare(mods, systems.random_ions(894, 3.0, cutoff=1.0, triclinic=True).rounded())
+
+
+def test_pme_grid_with_radix_11(mods):
+    systems = mods[0]
+    d = systems.water_box(7, cutoff=0.9).rounded()
+    d.pme_alpha, d.pme_grid = d.pme_parameters()[0], (22, 22, 22)
+    _compare(mods, d)
+
+
+def test_exceptions_14_and_torsions(mods):
+    systems = mods[0]
+    rng = np.random.default_rng(5)
+    d = systems.water_box(5, cutoff=0.75, rigid=False).rounded()
+    n = d.natoms
+    # a handful of artificial 1-4 exceptions with their own parameters + torsions over consecutive atoms
+    o = 3*np.arange(20, dtype=np.int32)
+    d.exc_i = np.concatenate([d.exc_i, o]); d.exc_j = np.concatenate([d.exc_j, o+3])
+    d.exc_qq = np.concatenate([d.exc_qq, np.full(20, 0.2)]); d.exc_sigma = np.concatenate([d.exc_sigma, np.full(20, 0.3)])
+    d.exc_eps = np.concatenate([d.exc_eps, np.full(20, 0.5)])
+    d.tor_i, d.tor_j, d.tor_k, d.tor_l = o, o+1, o+3, o+4
+    d.tor_n = rng.integers(1, 4, 20).astype(np.int32); d.tor_phase = rng.random(20)*3; d.tor_kk = rng.random(20)*10
+    assert n > 70
+    _compare(mods, d)
+
+
+def test_benchmark_size_water_parity(mods):
+    """S1 of SURVEY.md 8(d): 24,000 atoms, 56^3 grid -- parity at the size bench.py runs."""
+    eng, sim = _compare(mods, mods[0].water_box(20, cutoff=0.9).rounded())
+    st = eng.stats()
+    assert st["num_tiles"] > 0 and st["pairs_in_cutoff"] > 3e6
+
+
+# ---- integrators and constraints ----
+@pytest.mark.parametrize("kind", [0, 1, 2])
+def test_deterministic_integration_matches_reference(mods, kind):
+    """Verlet, and Langevin / LangevinMiddle at T = 0 (no noise term, ReferenceStochasticDynamics.cpp:99-100) are
+    deterministic: 10 steps must follow the Reference trajectory."""
+    systems, Engine, _, omm, _ = mods
+    d = systems.water_box(6, cutoff=0.9).rounded()
+    v = np.random.default_rng(3).standard_normal((d.natoms, 3))*0.3
+    eng = Engine(d)
+    eng.set_integrator(kind, 0.001, 0.0, 1.0, 7)
+    sim = omm.Simulation(d, "Reference", integrator=(kind, 0.0, 1.0, 0.001), pme=d.pme_parameters())
+    eng.set_velocities(v); sim.set_velocities(v)
+    eng.apply_velocity_constraints()
+    eng.step(10); sim.step(10)
+    ref = sim.state(positions=True, velocities=True, energy=True)
+    assert np.abs(eng.get_positions() - ref["positions"]).max() < 5e-6
+    assert np.abs(eng.get_velocities() - ref["velocities"]).max() < 1e-3      # fp32 positions: dx/dt noise ~1e-7/1e-3
+    eng.compute()
+    assert abs(eng.kinetic_energy() - ref["kinetic"])/ref["kinetic"] < 1e-3
+
+
+def test_settle_constraints_hold_over_langevin_run(mods):
+    """tests/TestSettle.h:45-98: constraint lengths within 1e-5 (relative to fp32 positions here: 2e-6 nm)."""
+    systems, Engine, *_ = mods
+    d = systems.water_box(8, cutoff=0.9).rounded()
+    eng = Engine(d)
+    eng.set_integrator(systems.INT_LANGEVIN, 0.002, 300.0, 2.0, 11)
+    eng.step(500)
+    x = eng.get_positions()
+    for i, j, dist in zip(d.con_i[::7], d.con_j[::7], d.con_d[::7]):
+        assert abs(np.linalg.norm(x[i]-x[j]) - dist) < 1e-5
+    assert np.isfinite(x).all()
+
+
+def test_langevin_temperature(mods):
+    """tests/TestLangevinIntegrator.h:92 (statistical): the thermostat reaches the target temperature."""
+    systems, Engine, *_ = mods
+    d = systems.water_box(8, cutoff=0.9).rounded()
+    eng = Engine(d)
+    eng.set_integrator(systems.INT_LANGEVIN_MIDDLE, 0.002, 300.0, 5.0, 3)
+    eng.step(1500)
+    ke = []
+    for _ in range(20):
+        eng.step(50)
+        eng.compute(energy=False)
+        ke.append(eng.kinetic_energy())
+    dof = 3*d.natoms - len(d.con_i)
+    T = 2*np.mean(ke)/(dof*0.00831446261815324)
+    assert abs(T - 300.0) < 12.0
+
+
+def test_random_seed_reproducibility(mods):
+    """tests/TestLangevinIntegrator.h:205: equal seeds give identical trajectories, different seeds do not."""
+    systems, Engine, *_ = mods
+    d = systems.water_box(5, cutoff=0.75).rounded()
+    out = []
+    for seed in (5, 5, 6):
+        eng = Engine(d)
+        eng.set_integrator(systems.INT_LANGEVIN, 0.002, 300.0, 1.0, seed)
+        eng.step(25)
+        out.append(eng.get_positions())
+    assert np.array_equal(out[0], out[1])
+    assert np.abs(out[0] - out[2]).max() > 1e-4
+
+
+def test_energy_force_consistency_finite_difference(mods):
+    """tests/TestEwald.h:160-178: E(x + h n) - E(x - h n) = -2h |F| along the force direction."""
+    systems, Engine, *_ = mods
+    d = systems.random_ions(300, 2.2, cutoff=1.0, seed=4).rounded()
+    eng = Engine(d)
+    eng.compute()
+    f = eng.get_forces()
+    norm = np.sqrt((f**2).sum())
+    h = 1e-3
+    x0 = d.positions
+    eng.set_positions(x0 + 0.5*h*f/norm)
+    e1 = eng.compute()
+    eng.set_positions(x0 - 0.5*h*f/norm)
+    e2 = eng.compute()
+    assert abs((e2 - e1)/h - norm)/norm < 2e-2
+
+
+def test_momentum_conservation_and_determinism_at_benchmark_size(mods):
+    systems, Engine, *_ = mods
+    d = systems.water_box(20, cutoff=0.9).rounded()
+    eng = Engine(d)
+    eng.compute()
+    f1 = eng.get_forces()
+    assert np.abs(f1.sum(axis=0)).max() < 0.5           # sum of ~1e7 kJ/mol/nm of |F|: direct space cancels exactly (fixed point), PME to ~1e-7
+    eng.compute()
+    assert np.array_equal(f1, eng.get_forces()) or np.abs(f1 - eng.get_forces()).max() < 1e-3   # float atomics in the spread only
+
+
+def test_checkpoint_roundtrip(mods):
+    systems, Engine, *_ = mods
+    d = systems.water_box(5, cutoff=0.75).rounded()
+    eng = Engine(d)
+    eng.set_integrator(systems.INT_LANGEVIN, 0.002, 300.0, 1.0, 5)
+    eng.step(10)
+    blob = eng.checkpoint()
+    eng.step(10)
+    xa = eng.get_positions()
+    eng.load_checkpoint(blob)
+    eng.step(10)
+    assert np.array_equal(xa, eng.get_positions())
+
+
+def test_box_too_small_is_an_error(mods):
+    systems, Engine, engine, *_ = mods
+    d = systems.water_box(5, cutoff=0.9)       # box 1.55 nm < 2*0.9
+    with pytest.raises(engine.EngineError):
+        Engine(d)
+
+
+def test_unsupported_constraint_topology_is_an_error(mods):
+    systems, Engine, engine, *_ = mods
+    d = systems.lj_fluid(4, cutoff=0.7)
+    d.con_i = np.array([0, 1, 2], dtype=np.int32); d.con_j = np.array([1, 2, 3], dtype=np.int32); d.con_d = np.full(3, 0.38)
+    with pytest.raises(engine.EngineError):
+        Engine(d)
