@@ -88,12 +88,18 @@ int b200md_set_torsions(b200md_ctx* ctx, int n, const int* p1, const int* p2, co
 int b200md_set_constraints(b200md_ctx* ctx, int n, const int* p1, const int* p2, const double* distance);
 /* RemoveCMMotionKernel (kernels.h:1464-1483); frequency <= 0 disables.                               */
 int b200md_set_cm_remover(b200md_ctx* ctx, int frequency);
+/* RemoveCMMotionKernel::execute (kernels.h:1483): subtract the centre-of-mass velocity now.          */
+int b200md_remove_cm_motion(b200md_ctx* ctx);
 /* Build exclusion lists, constraint clusters, PME plans; allocate the device state.                  */
 int b200md_finalize(b200md_ctx* ctx);
 /* CalcNonbondedForceKernel::copyParametersToContext (kernels.h:595), after finalize.                 */
 int b200md_update_nonbonded_params(b200md_ctx* ctx, const double* charge, const double* sigma, const double* epsilon,
                                    int nexc, const double* exc_charge_prod, const double* exc_sigma, const double* exc_epsilon,
                                    double dispersion_coefficient);
+
+/* Calc{HarmonicBond,HarmonicAngle,PeriodicTorsion}ForceKernel::copyParametersToContext (kernels.h:305,375,445):
+ * same topology, new parameters. kind 0 bonds (a=length,b=k), 1 angles (a=angle,b=k), 2 torsions (a=phase,b=k).  */
+int b200md_update_bonded_params(b200md_ctx* ctx, int kind, int n, const double* a, const double* b, const int* periodicity);
 
 /* ---------------------------------------------------------------------------------------------------
  * UpdateStateDataKernel (kernels.h:125-214).                                                         */

@@ -35,9 +35,11 @@ __global__ void __launch_bounds__(128) k_bonded(NbDev nb, BondedDev bd, int term
     const int nB = (terms & B200MD_TERM_BONDS) ? bd.nbonds : 0;
     const int nA = (terms & B200MD_TERM_ANGLES) ? bd.nangles : 0;
     const int nT = (terms & B200MD_TERM_TORSIONS) ? bd.ntorsions : 0;
+    // both the 1-4 pairs and the Ewald exclusion correction belong to the DIRECT-space group: the reference evaluates
+    // the exclusion loop after `if (!includeDirect) return;` (ReferenceLJCoulombIxn.cpp:373-374, 462-523)
     const bool doDirect = (terms & B200MD_TERM_NB_DIRECT) != 0;
-    const bool doRecip = (terms & B200MD_TERM_NB_RECIP) != 0 && nb.method == B200MD_NB_PME;
-    const int nE = (doDirect || doRecip) ? bd.nexc : 0;
+    const bool doRecip = doDirect && nb.method == B200MD_NB_PME;
+    const int nE = doDirect ? bd.nexc : 0;
     // the bonded work is sharded over ranks in the multi-GPU force decomposition
     const int gid = nb.rank + nb.world*(blockIdx.x*blockDim.x + threadIdx.x);
     double eB = 0, eA = 0, eT = 0, eE = 0;
@@ -163,7 +165,7 @@ void launch_bonded(const NbDev& nb, const BondedDev& bd, int terms, bool energy,
     if (terms & B200MD_TERM_BONDS) n += bd.nbonds;
     if (terms & B200MD_TERM_ANGLES) n += bd.nangles;
     if (terms & B200MD_TERM_TORSIONS) n += bd.ntorsions;
-    if (terms & (B200MD_TERM_NB_DIRECT | B200MD_TERM_NB_RECIP)) n += bd.nexc;
+    if (terms & B200MD_TERM_NB_DIRECT) n += bd.nexc;
     if (n == 0) return;
     int per = (n + nb.world - 1)/nb.world;
     k_bonded<<<(per + 127)/128, 128, 0, s>>>(nb, bd, terms, energy ? 1 : 0);

@@ -77,6 +77,7 @@ struct b200md_ctx {
     DevBuf<unsigned int> maskPool;
     DevBuf<unsigned long long> stepCounter;
     DevBuf<float> grid, eterm;
+    DevBuf<long long> gridFixed;
     DevBuf<float2> cgrid;
     DevBuf<float2> tw[3];
     DevBuf<double> moduli[3];
@@ -207,6 +208,14 @@ extern "C" int b200md_set_cm_remover(b200md_ctx* ctx, int freq) {
     if (!ctx) return -1;
     ctx->cmFreq = freq;
     return 0;
+}
+
+extern "C" int b200md_remove_cm_motion(b200md_ctx* ctx) {
+    API_BEGIN(ctx)
+    require(ctx->finalized, "remove_cm_motion before finalize");
+    launch_remove_cm(ctx->nb, ctx->cmScratch.p, ctx->stream);
+    ctx->kernelLaunches += 2;
+    API_END(ctx)
 }
 
 // ---------------------------------------------------------------- Hilbert curve over the binning cells
@@ -449,6 +458,8 @@ static void setup_pme(b200md_ctx* c, int nx, int ny, int nz, double alpha) {
     if (fft_plane_smem_bytes(ny, nz) > (size_t) maxSmem || fft_line_smem_bytes(nx) > (size_t) maxSmem)
         throw std::runtime_error("B200 platform: PME grid plane does not fit in shared memory (max about 160x160 per slab)");
     c->grid.alloc((size_t) nx*ny*nz);
+    c->gridFixed.alloc((size_t) nx*ny*nz);
+    p.gridFixed = c->gridFixed.p;
     c->cgrid.alloc((size_t) nx*ny*p.nzc);
     c->eterm.alloc((size_t) nx*ny*p.nzc);
     p.grid = c->grid.p; p.cgrid = c->cgrid.p; p.eterm = c->eterm.p;
@@ -575,6 +586,31 @@ extern "C" int b200md_update_nonbonded_params(b200md_ctx* ctx, const double* q, 
     API_END(ctx)
 }
 
+// Calc{HarmonicBond,HarmonicAngle,PeriodicTorsion}ForceKernel::copyParametersToContext (kernels.h:305,375,445):
+// same topology, new parameters.  kind: 0 bonds (a=length,b=k), 1 angles (a=angle,b=k), 2 torsions (a=phase,b=k,per)
+extern "C" int b200md_update_bonded_params(b200md_ctx* ctx, int kind, int n, const double* a, const double* b, const int* periodicity) {
+    API_BEGIN(ctx)
+    require(ctx->finalized, "update_bonded_params before finalize");
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    if (kind == 0) {
+        require(n == ctx->bd.nbonds, "the number of bonds cannot change");
+        std::vector<double2> p(n); for (int i = 0; i < n; i++) p[i] = make_double2(a[i], b[i]);
+        ctx->bondParams.upload(p);
+    }
+    else if (kind == 1) {
+        require(n == ctx->bd.nangles, "the number of angles cannot change");
+        std::vector<double2> p(n); for (int i = 0; i < n; i++) p[i] = make_double2(a[i], b[i]);
+        ctx->angleParams.upload(p);
+    }
+    else if (kind == 2) {
+        require(n == ctx->bd.ntorsions, "the number of torsions cannot change");
+        std::vector<double4> p(n); for (int i = 0; i < n; i++) p[i] = make_double4(b[i], a[i], (double) periodicity[i], 0);
+        ctx->torsionParams.upload(p);
+    }
+    else throw std::runtime_error("unknown bonded kind");
+    API_END(ctx)
+}
+
 // ---------------------------------------------------------------- state
 extern "C" int b200md_set_positions(b200md_ctx* ctx, const double* x) {
     API_BEGIN(ctx)
@@ -695,14 +731,14 @@ static int enqueue_forces(b200md_ctx* c, int terms, bool energy) {
     if (recip) {
         launch_pme_spread(c->nb, c->pme, s); launches++;
         if (c->world > 1 && c->comm) {
-            int rc = g_nccl.AllReduce(c->grid.p, c->grid.p, (size_t) c->pme.nx*c->pme.ny*c->pme.nz, NCCL_FLOAT32, NCCL_SUM, c->comm, s);
+            int rc = g_nccl.AllReduce(c->gridFixed.p, c->gridFixed.p, (size_t) c->pme.nx*c->pme.ny*c->pme.nz, NCCL_INT64, NCCL_SUM, c->comm, s);
             if (rc != 0) throw std::runtime_error("ncclAllReduce(grid) failed");
         }
         launch_pme_fft_conv(c->nb, c->pme, energy && c->rank == 0, s); launches += 3;
         launch_pme_gather(c->nb, c->pme, s); launches++;
     }
     int bterms = terms & (B200MD_TERM_BONDS | B200MD_TERM_ANGLES | B200MD_TERM_TORSIONS);
-    if (c->haveNb) bterms |= terms & (B200MD_TERM_NB_DIRECT | B200MD_TERM_NB_RECIP);
+    if (c->haveNb) bterms |= terms & B200MD_TERM_NB_DIRECT;
     const int nbonded = c->bd.nbonds + c->bd.nangles + c->bd.ntorsions + c->bd.nexc;
     if (bterms && nbonded > 0) { launch_bonded(c->nb, c->bd, bterms, energy, s); launches++; }
     if (c->world > 1 && c->comm) {
@@ -740,9 +776,8 @@ extern "C" int b200md_compute(b200md_ctx* ctx, int terms, int want_forces, doubl
         if (terms & B200MD_TERM_ANGLES) e += h[EN_ANGLE];
         if (terms & B200MD_TERM_TORSIONS) e += h[EN_TORSION];
         if (ctx->haveNb) {
-            if (terms & (B200MD_TERM_NB_DIRECT | B200MD_TERM_NB_RECIP)) e += h[EN_EXC];
             if (terms & B200MD_TERM_NB_DIRECT) {
-                e += h[EN_NB];
+                e += h[EN_NB] + h[EN_EXC];
                 const int m = ctx->nb.method;
                 if (m == B200MD_NB_CUTOFF_PERIODIC || m == B200MD_NB_PME)      // ReferenceKernels.cpp:1008-1011
                     e += ctx->dispersionCoefficient/ctx->nb.box.volume;
@@ -891,9 +926,22 @@ extern "C" int b200md_time_phase(b200md_ctx* ctx, int phase, int reps, double* m
     CUDA_CHECK(cudaEventCreate(&e0)); CUDA_CHECK(cudaEventCreate(&e1));
     const int one = 1;
     double total = 0;
+    // the integrate phase mutates the state: snapshot it and restore it after every repetition
+    DevBuf<float4> savePos, saveVel; unsigned long long saveStep = 0;
+    if (phase == 4) {
+        require(c->haveIntegrator, "time_phase(integrate) before set_integrator");
+        savePos.alloc(c->npad); saveVel.alloc(c->npad);
+        CUDA_CHECK(cudaMemcpyAsync(savePos.p, c->posq.p, sizeof(float4)*c->npad, cudaMemcpyDeviceToDevice, s));
+        CUDA_CHECK(cudaMemcpyAsync(saveVel.p, c->velm.p, sizeof(float4)*c->npad, cudaMemcpyDeviceToDevice, s));
+        CUDA_CHECK(cudaMemcpyAsync(&saveStep, c->stepCounter.p, sizeof(saveStep), cudaMemcpyDeviceToHost, s));
+        CUDA_CHECK(cudaStreamSynchronize(s));
+    }
     for (int r = -2; r < reps; r++) {
+        if (phase == 4) {
+            CUDA_CHECK(cudaMemcpyAsync(c->posq.p, savePos.p, sizeof(float4)*c->npad, cudaMemcpyDeviceToDevice, s));
+            CUDA_CHECK(cudaMemcpyAsync(c->velm.p, saveVel.p, sizeof(float4)*c->npad, cudaMemcpyDeviceToDevice, s));
+        }
         if (phase == 5) CUDA_CHECK(cudaMemcpyAsync(&c->counters.p[2], &one, sizeof(int), cudaMemcpyHostToDevice, s));
-        if (phase == 1) CUDA_CHECK(cudaMemsetAsync(c->grid.p, 0, sizeof(float)*c->grid.n, s));
         CUDA_CHECK(cudaEventRecord(e0, s));
         switch (phase) {
             case 0: launch_pair(c->nb, false, s); break;
@@ -909,6 +957,12 @@ extern "C" int b200md_time_phase(b200md_ctx* ctx, int phase, int reps, double* m
         CUDA_CHECK(cudaEventSynchronize(e1));
         float ms = 0; CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
         if (r >= 0) total += ms;
+    }
+    if (phase == 4) {
+        CUDA_CHECK(cudaMemcpyAsync(c->posq.p, savePos.p, sizeof(float4)*c->npad, cudaMemcpyDeviceToDevice, s));
+        CUDA_CHECK(cudaMemcpyAsync(c->velm.p, saveVel.p, sizeof(float4)*c->npad, cudaMemcpyDeviceToDevice, s));
+        CUDA_CHECK(cudaMemcpyAsync(c->stepCounter.p, &saveStep, sizeof(saveStep), cudaMemcpyHostToDevice, s));
+        CUDA_CHECK(cudaStreamSynchronize(s));
     }
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     *ms_mean = total/std::max(1, reps);

@@ -86,7 +86,8 @@ enum { EN_NB = 0, EN_RECIP = 1, EN_BOND = 2, EN_ANGLE = 3, EN_TORSION = 4, EN_EX
 
 struct PmeDev {
     int nx, ny, nz, nzc;
-    float* grid;                 // real [nx][ny][nz]
+    float* grid;                 // real [nx][ny][nz] (output of the inverse transform, input of the gather)
+    long long* gridFixed;        // real [nx][ny][nz], 2^32 fixed point: deterministic charge spreading (pme.cc:78-89 option)
     float2* cgrid;               // complex [nx][ny][nzc]
     float* eterm;                // [nx][ny][nzc] influence function (no ONE_4PI_EPS0: charges carry sqrt of it)
     const double* moduli[3];

@@ -5,90 +5,110 @@
 // pme_reciprocal_convolution (ReferencePME.cpp:409-514, 793-799): unnormalised transforms in both directions,
 // forward = exp(-2 pi i jk/n).
 //
-// Slab decomposition, three launches for forward + convolution + inverse:
-//   A  k_fft_zy_fwd  one CTA per x-slab: the (y,z) plane lives in shared memory, real-to-complex along z
-//                    (two real rows packed in one complex line), complex along y, written once as [x][ky][kz]
-//   B  k_fft_x_conv  one CTA per batch of (ky,kz) lines: forward along x, multiply by the influence function,
-//                    accumulate the reciprocal energy, inverse along x -- the k-space grid never leaves smem
-//   C  k_fft_yz_inv  one CTA per x-slab: inverse along y, complex-to-real along z
-// Every grid point is read and written exactly once per launch: 3 x (8H + 8H) + the 4G real read / write.
+// Five launches for forward + convolution + inverse; every launch is a batch of independent 1-D lines that live in
+// shared memory for the whole transform, so the grid is read and written exactly once per pass and stays in L2:
+//   1  k_fft_z_fwd   real-to-complex along z; two real rows are packed into one complex line (half the work)
+//   2  k_fft_y       complex along y, 16 adjacent kz columns per CTA (128-byte coalesced segments)
+//   3  k_fft_x_conv  forward along x, multiply by the influence function, accumulate the reciprocal energy,
+//                    inverse along x -- the k-space grid never leaves shared memory between the three
+//   4  k_fft_y       inverse along y
+//   5  k_fft_z_inv   complex-to-real along z (Hermitian unpacking, two rows per complex line)
+// Round 1 v1 used one CTA per x-slab (3 launches); profiles/r01_launches_bench_nograph.csv showed 56 under-filled
+// CTAs taking 27 us each -- the line-batched layout below gives 100-200 CTAs per pass.
 //
-// 1-D transforms are Stockham autosort, mixed radix with generic radices 2..16 (any n whose factors are <= 16,
-// so 56 = 8*7, 88 = 8*11, 90 = 10*9, 128 = 16*8 ...), out of place between two shared-memory buffers.
+// 1-D transforms are Stockham autosort, mixed radix with generic radices 2..16 (any n whose prime factors are
+// <= 13: 56 = 8*7, 88 = 8*11, 90 = 6*5*3, 128 = 8*4*4 ...), out of place between two shared-memory buffers, twiddles
+// staged in shared memory.
 #include "engine.h"
 #include <math.h>
 
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) { return make_float2(a.x*b.x - a.y*b.y, a.x*b.y + a.y*b.x); }
 
-// one Stockham stage of radix R over `nlines` lines of length n.
-// element (line, i) lives at base[line*lineStride + i*elemStride].
+// one Stockham stage of radix R over `nlines` contiguous lines of length n (line l at base + l*n).
+// tw: exp(-2 pi i k/n) in shared memory.
 template <int R>
-__device__ void fft_stage(const float2* __restrict__ in, float2* __restrict__ out, int n, int nlines, int elemStride, int lineStride,
-                          int Ns, const float2* __restrict__ tw, bool inverse) {
+__device__ __forceinline__ void fft_stage(const float2* __restrict__ in, float2* __restrict__ out, int n, int nlines,
+                                          int Ns, const float2* __restrict__ tw, bool inverse) {
     const int nb = n/R;                 // butterflies per line
     const int twStep = n/(Ns*R);
-    float2 root[R];
-#pragma unroll
-    for (int m = 0; m < R; m++) {
-        float2 w = __ldg(&tw[m*nb]);
-        root[m] = inverse ? make_float2(w.x, -w.y) : w;
-    }
     const int total = nlines*nb;
     for (int w = threadIdx.x; w < total; w += blockDim.x) {
         const int line = w/nb;
         const int j = w - line*nb;
         const int k = j % Ns;
-        const float2* src = in + line*lineStride;
+        const float2* src = in + line*n;
         float2 v[R];
 #pragma unroll
         for (int t = 0; t < R; t++) {
-            float2 x = src[(j + t*nb)*elemStride];
+            float2 x = src[j + t*nb];
             if (t > 0 && k > 0) {
-                float2 wv = __ldg(&tw[t*k*twStep]);
+                float2 wv = tw[t*k*twStep];
                 if (inverse) wv.y = -wv.y;
                 x = cmul(x, wv);
             }
             v[t] = x;
         }
-        float2* dst = out + line*lineStride;
+        float2* dst = out + line*n;
         const int j0 = (j/Ns)*Ns*R + k;
+        if (R == 2) {
+            dst[j0] = make_float2(v[0].x + v[1].x, v[0].y + v[1].y);
+            dst[j0 + Ns] = make_float2(v[0].x - v[1].x, v[0].y - v[1].y);
+        }
+        else if (R == 4) {
+            // radix-4 butterfly with trivial twiddles (-i forward, +i inverse)
+            const float2 a = make_float2(v[0].x + v[2].x, v[0].y + v[2].y), b = make_float2(v[0].x - v[2].x, v[0].y - v[2].y);
+            const float2 c = make_float2(v[1].x + v[3].x, v[1].y + v[3].y), d = make_float2(v[1].x - v[3].x, v[1].y - v[3].y);
+            const float2 id = inverse ? make_float2(-d.y, d.x) : make_float2(d.y, -d.x);     // (-+)i * d
+            dst[j0] = make_float2(a.x + c.x, a.y + c.y);
+            dst[j0 + Ns] = make_float2(b.x + id.x, b.y + id.y);
+            dst[j0 + 2*Ns] = make_float2(a.x - c.x, a.y - c.y);
+            dst[j0 + 3*Ns] = make_float2(b.x - id.x, b.y - id.y);
+        }
+        else {
+            float2 root[R];
 #pragma unroll
-        for (int q = 0; q < R; q++) {
-            float2 acc = v[0];
-#pragma unroll
-            for (int t = 1; t < R; t++) {
-                const float2 r = root[(q*t) % R];
-                acc.x += v[t].x*r.x - v[t].y*r.y;
-                acc.y += v[t].x*r.y + v[t].y*r.x;
+            for (int m = 0; m < R; m++) {
+                const float2 wv = tw[m*nb];
+                root[m] = inverse ? make_float2(wv.x, -wv.y) : wv;
             }
-            dst[(j0 + q*Ns)*elemStride] = acc;
+#pragma unroll
+            for (int q = 0; q < R; q++) {
+                float2 acc = v[0];
+#pragma unroll
+                for (int t = 1; t < R; t++) {
+                    const float2 r = root[(q*t) % R];
+                    acc.x += v[t].x*r.x - v[t].y*r.y;
+                    acc.y += v[t].x*r.y + v[t].y*r.x;
+                }
+                dst[j0 + q*Ns] = acc;
+            }
         }
     }
 }
 
-// full 1-D transform of all lines; returns the buffer holding the result. Block-wide; ends with __syncthreads.
-__device__ float2* fft_lines(float2* a, float2* b, const FftPlanDev& plan, int nlines, int elemStride, int lineStride, bool inverse) {
+// full 1-D transform of `nlines` contiguous lines; returns the buffer holding the result. Block-wide.
+__device__ float2* fft_lines(float2* a, float2* b, const FftPlanDev& plan, int nlines, const float2* tw, bool inverse) {
     int Ns = 1;
     float2* in = a;
     float2* out = b;
     for (int s = 0; s < plan.nstages; s++) {
         const int R = plan.radix[s];
         switch (R) {
-            case 2: fft_stage<2>(in, out, plan.n, nlines, elemStride, lineStride, Ns, plan.tw, inverse); break;
-            case 3: fft_stage<3>(in, out, plan.n, nlines, elemStride, lineStride, Ns, plan.tw, inverse); break;
-            case 4: fft_stage<4>(in, out, plan.n, nlines, elemStride, lineStride, Ns, plan.tw, inverse); break;
-            case 5: fft_stage<5>(in, out, plan.n, nlines, elemStride, lineStride, Ns, plan.tw, inverse); break;
-            case 6: fft_stage<6>(in, out, plan.n, nlines, elemStride, lineStride, Ns, plan.tw, inverse); break;
-            case 7: fft_stage<7>(in, out, plan.n, nlines, elemStride, lineStride, Ns, plan.tw, inverse); break;
-            case 8: fft_stage<8>(in, out, plan.n, nlines, elemStride, lineStride, Ns, plan.tw, inverse); break;
-            case 9: fft_stage<9>(in, out, plan.n, nlines, elemStride, lineStride, Ns, plan.tw, inverse); break;
-            case 10: fft_stage<10>(in, out, plan.n, nlines, elemStride, lineStride, Ns, plan.tw, inverse); break;
-            case 11: fft_stage<11>(in, out, plan.n, nlines, elemStride, lineStride, Ns, plan.tw, inverse); break;
-            case 12: fft_stage<12>(in, out, plan.n, nlines, elemStride, lineStride, Ns, plan.tw, inverse); break;
-            case 13: fft_stage<13>(in, out, plan.n, nlines, elemStride, lineStride, Ns, plan.tw, inverse); break;
-            case 14: fft_stage<14>(in, out, plan.n, nlines, elemStride, lineStride, Ns, plan.tw, inverse); break;
-            case 15: fft_stage<15>(in, out, plan.n, nlines, elemStride, lineStride, Ns, plan.tw, inverse); break;
-            case 16: fft_stage<16>(in, out, plan.n, nlines, elemStride, lineStride, Ns, plan.tw, inverse); break;
+            case 2: fft_stage<2>(in, out, plan.n, nlines, Ns, tw, inverse); break;
+            case 3: fft_stage<3>(in, out, plan.n, nlines, Ns, tw, inverse); break;
+            case 4: fft_stage<4>(in, out, plan.n, nlines, Ns, tw, inverse); break;
+            case 5: fft_stage<5>(in, out, plan.n, nlines, Ns, tw, inverse); break;
+            case 6: fft_stage<6>(in, out, plan.n, nlines, Ns, tw, inverse); break;
+            case 7: fft_stage<7>(in, out, plan.n, nlines, Ns, tw, inverse); break;
+            case 8: fft_stage<8>(in, out, plan.n, nlines, Ns, tw, inverse); break;
+            case 9: fft_stage<9>(in, out, plan.n, nlines, Ns, tw, inverse); break;
+            case 10: fft_stage<10>(in, out, plan.n, nlines, Ns, tw, inverse); break;
+            case 11: fft_stage<11>(in, out, plan.n, nlines, Ns, tw, inverse); break;
+            case 12: fft_stage<12>(in, out, plan.n, nlines, Ns, tw, inverse); break;
+            case 13: fft_stage<13>(in, out, plan.n, nlines, Ns, tw, inverse); break;
+            case 14: fft_stage<14>(in, out, plan.n, nlines, Ns, tw, inverse); break;
+            case 15: fft_stage<15>(in, out, plan.n, nlines, Ns, tw, inverse); break;
+            case 16: fft_stage<16>(in, out, plan.n, nlines, Ns, tw, inverse); break;
             default: break;   // n == 1
         }
         __syncthreads();
@@ -98,139 +118,191 @@ __device__ float2* fft_lines(float2* a, float2* b, const FftPlanDev& plan, int n
     return in;
 }
 
-// greedy factorisation into radices <= 16, largest first so the stage count is minimal
-bool fft_make_radices(int n, int* radix, int* nstages) {
-    int ns = 0;
-    int rem = n;
-    while (rem > 1) {
-        int best = 0;
-        // prefer a split that leaves a remainder also factorable; greedy largest divisor <= 16 works for all
-        // numbers whose prime factors are <= 13
-        for (int r = B200MD_MAX_RADIX; r >= 2; r--)
-            if (rem % r == 0) { best = r; break; }
-        if (best == 0 || ns >= B200MD_MAX_FFT_STAGES) return false;
-        radix[ns++] = best;
-        rem /= best;
+// factorisation into radices <= 16 minimising sum(R + 4): R complex MACs per point per generic stage plus a
+// synchronisation cost per stage (exhaustive search, n is small)
+static int best_cost(int n, int* radix, int depth) {
+    if (n == 1) return 0;
+    if (depth >= B200MD_MAX_FFT_STAGES) return 1 << 28;
+    int best = 1 << 28, sub[B200MD_MAX_FFT_STAGES];
+    for (int r = 2; r <= B200MD_MAX_RADIX && r <= n; r++) {
+        if (n % r) continue;
+        const int stageCost = (r == 2 ? 2 : (r == 4 ? 3 : r)) + 4;
+        int c = stageCost + best_cost(n/r, sub, depth+1);
+        if (c < best) {
+            best = c;
+            radix[0] = r;
+            for (int k = 0; k + depth + 1 < B200MD_MAX_FFT_STAGES && k < B200MD_MAX_FFT_STAGES-1; k++) radix[k+1] = sub[k];
+        }
     }
+    return best;
+}
+
+bool fft_make_radices(int n, int* radix, int* nstages) {
+    int r[B200MD_MAX_FFT_STAGES+1] = {0};
+    if (n < 1) return false;
+    if (best_cost(n, r, 0) >= (1 << 28)) return false;
+    int ns = 0, rem = n;
+    while (rem > 1 && ns < B200MD_MAX_FFT_STAGES) { radix[ns] = r[ns]; rem /= r[ns]; ns++; }
+    if (rem != 1) return false;
+    // larger radices first: the early stages have the poorest write locality, keep them few
+    for (int a = 0; a < ns; a++) for (int b = a+1; b < ns; b++) if (radix[b] > radix[a]) { int t = radix[a]; radix[a] = radix[b]; radix[b] = t; }
     *nstages = ns;
     return true;
 }
 
-size_t fft_plane_smem_bytes(int ny, int nz) {
-    int nzc = nz/2 + 1;
-    int np = (ny + 1)/2;
-    size_t elems = (size_t) ny*nzc;
-    if ((size_t) np*nz > elems) elems = (size_t) np*nz;
-    return 2*elems*sizeof(float2);
+#define ZROWS 16          // real rows per CTA in the z passes (8 packed complex lines)
+#define LINE_BATCH 16     // lines per CTA in the y and x passes
+#define FFT_THREADS 128
+
+size_t fft_plane_smem_bytes(int ny, int nz) {       // kept for the engine's capacity check: largest per-CTA need
+    size_t z = (2*(size_t) (ZROWS/2)*nz + nz)*sizeof(float2);
+    size_t y = (2*(size_t) LINE_BATCH*ny + ny)*sizeof(float2);
+    return z > y ? z : y;
+}
+size_t fft_line_smem_bytes(int nx) { return (2*(size_t) LINE_BATCH*nx + nx)*sizeof(float2); }
+
+__device__ __forceinline__ void stage_twiddles(float2* tws, const FftPlanDev& plan) {
+    for (int i = threadIdx.x; i < plan.n; i += blockDim.x) tws[i] = plan.tw[i];
 }
 
-#define FFT_LINE_BATCH 16
-size_t fft_line_smem_bytes(int nx) { return 2*(size_t) FFT_LINE_BATCH*nx*sizeof(float2); }
-
-// ---- A: forward z (R2C, two rows per complex line) then y, one x-slab per CTA ----
-__global__ void __launch_bounds__(512) k_fft_zy_fwd(PmeDev pme) {
+// ---- 1: forward z, real to complex, two rows per complex line ----
+__global__ void __launch_bounds__(FFT_THREADS) k_fft_z_fwd(PmeDev pme) {
     extern __shared__ float2 smem[];
-    const int ny = pme.ny, nz = pme.nz, nzc = pme.nzc;
-    const int np = (ny + 1)/2;
-    size_t elems = (size_t) ny*nzc;
-    if ((size_t) np*nz > elems) elems = (size_t) np*nz;
+    const int nz = pme.nz, nzc = pme.nzc;
+    const int nrowsTotal = pme.nx*pme.ny;
+    const int row0 = blockIdx.x*ZROWS;
+    const int nrows = min(ZROWS, nrowsTotal - row0);
+    const int np = (nrows + 1)/2;
     float2* A = smem;
-    float2* B = smem + elems;
-    const int x = blockIdx.x;
-    const float* plane = pme.grid + (size_t) x*ny*nz;
-    for (int i = threadIdx.x; i < np*nz; i += blockDim.x) {
-        int p = i/nz, z = i - p*nz;
-        float re = plane[(2*p)*nz + z];
-        float im = (2*p+1 < ny) ? plane[(2*p+1)*nz + z] : 0.f;
-        A[i] = make_float2(re, im);
+    float2* B = A + (ZROWS/2)*nz;
+    float2* tws = B + (ZROWS/2)*nz;
+    stage_twiddles(tws, pme.plan[2]);
+    if (pme.gridFixed != nullptr) {
+        const long long* base = pme.gridFixed + (size_t) row0*nz;
+        const float sc = 1.0f/4294967296.0f;
+        for (int i = threadIdx.x; i < np*nz; i += blockDim.x) {
+            const int p = i/nz, z = i - p*nz;
+            const float re = (float) base[(size_t) (2*p)*nz + z]*sc;
+            const float im = (2*p+1 < nrows) ? (float) base[(size_t) (2*p+1)*nz + z]*sc : 0.f;
+            A[i] = make_float2(re, im);
+        }
+    }
+    else {
+        const float* base = pme.grid + (size_t) row0*nz;
+        for (int i = threadIdx.x; i < np*nz; i += blockDim.x) {
+            const int p = i/nz, z = i - p*nz;
+            const float re = base[(size_t) (2*p)*nz + z];
+            const float im = (2*p+1 < nrows) ? base[(size_t) (2*p+1)*nz + z] : 0.f;
+            A[i] = make_float2(re, im);
+        }
     }
     __syncthreads();
-    float2* R = fft_lines(A, B, pme.plan[2], np, 1, nz, false);
-    float2* O = (R == A) ? B : A;
-    // unpack the two interleaved real transforms
+    const float2* R = fft_lines(A, B, pme.plan[2], np, tws, false);
+    // unpack the two interleaved real transforms straight to global memory
+    float2* dst = pme.cgrid + (size_t) row0*nzc;
     for (int i = threadIdx.x; i < np*nzc; i += blockDim.x) {
-        int p = i/nzc, k = i - p*nzc;
-        float2 Z = R[p*nz + k];
+        const int p = i/nzc, k = i - p*nzc;
+        const float2 Z = R[p*nz + k];
         float2 Zc = R[p*nz + ((nz - k) % nz)];
         Zc.y = -Zc.y;
-        float2 a = make_float2(0.5f*(Z.x + Zc.x), 0.5f*(Z.y + Zc.y));
-        float2 d = make_float2(0.5f*(Z.x - Zc.x), 0.5f*(Z.y - Zc.y));
-        O[(2*p)*nzc + k] = a;
-        if (2*p+1 < ny) O[(2*p+1)*nzc + k] = make_float2(d.y, -d.x);     // -i*d
+        dst[(size_t) (2*p)*nzc + k] = make_float2(0.5f*(Z.x + Zc.x), 0.5f*(Z.y + Zc.y));
+        if (2*p+1 < nrows) {
+            const float2 d = make_float2(0.5f*(Z.x - Zc.x), 0.5f*(Z.y - Zc.y));
+            dst[(size_t) (2*p+1)*nzc + k] = make_float2(d.y, -d.x);     // -i*d
+        }
     }
-    __syncthreads();
-    float2* other = (O == A) ? B : A;
-    float2* Y = fft_lines(O, other, pme.plan[1], nzc, nzc, 1, false);
-    float2* dst = pme.cgrid + (size_t) x*ny*nzc;
-    for (int i = threadIdx.x; i < ny*nzc; i += blockDim.x) dst[i] = Y[i];
 }
 
-// ---- C: inverse y then z (C2R), one x-slab per CTA ----
-__global__ void __launch_bounds__(512) k_fft_yz_inv(PmeDev pme) {
+// ---- 5: inverse z, complex to real ----
+__global__ void __launch_bounds__(FFT_THREADS) k_fft_z_inv(PmeDev pme) {
     extern __shared__ float2 smem[];
-    const int ny = pme.ny, nz = pme.nz, nzc = pme.nzc;
-    const int np = (ny + 1)/2;
-    size_t elems = (size_t) ny*nzc;
-    if ((size_t) np*nz > elems) elems = (size_t) np*nz;
+    const int nz = pme.nz, nzc = pme.nzc;
+    const int nrowsTotal = pme.nx*pme.ny;
+    const int row0 = blockIdx.x*ZROWS;
+    const int nrows = min(ZROWS, nrowsTotal - row0);
+    const int np = (nrows + 1)/2;
     float2* A = smem;
-    float2* B = smem + elems;
-    const int x = blockIdx.x;
-    const float2* src = pme.cgrid + (size_t) x*ny*nzc;
-    for (int i = threadIdx.x; i < ny*nzc; i += blockDim.x) A[i] = src[i];
-    __syncthreads();
-    float2* Y = fft_lines(A, B, pme.plan[1], nzc, nzc, 1, true);
-    float2* O = (Y == A) ? B : A;
+    float2* B = A + (ZROWS/2)*nz;
+    float2* tws = B + (ZROWS/2)*nz;
+    stage_twiddles(tws, pme.plan[2]);
+    const float2* src = pme.cgrid + (size_t) row0*nzc;
     // pack rows (2p, 2p+1) into one complex line using the Hermitian symmetry along z
     for (int i = threadIdx.x; i < np*nz; i += blockDim.x) {
-        int p = i/nz, k = i - p*nz;
-        int kk = (k < nzc) ? k : nz - k;
-        float2 a = Y[(2*p)*nzc + kk];
-        float2 b = (2*p+1 < ny) ? Y[(2*p+1)*nzc + kk] : make_float2(0.f, 0.f);
+        const int p = i/nz, k = i - p*nz;
+        const int kk = (k < nzc) ? k : nz - k;
+        float2 a = src[(size_t) (2*p)*nzc + kk];
+        float2 b = (2*p+1 < nrows) ? src[(size_t) (2*p+1)*nzc + kk] : make_float2(0.f, 0.f);
         if (k >= nzc) { a.y = -a.y; b.y = -b.y; }
-        O[i] = make_float2(a.x - b.y, a.y + b.x);       // a + i b
+        A[i] = make_float2(a.x - b.y, a.y + b.x);       // a + i b
     }
     __syncthreads();
-    float2* other = (O == A) ? B : A;
-    float2* Z = fft_lines(O, other, pme.plan[2], np, 1, nz, true);
-    float* plane = pme.grid + (size_t) x*ny*nz;
+    const float2* Z = fft_lines(A, B, pme.plan[2], np, tws, true);
+    float* dst = pme.grid + (size_t) row0*nz;
     for (int i = threadIdx.x; i < np*nz; i += blockDim.x) {
-        int p = i/nz, z = i - p*nz;
-        float2 v = Z[i];
-        plane[(2*p)*nz + z] = v.x;
-        if (2*p+1 < ny) plane[(2*p+1)*nz + z] = v.y;
+        const int p = i/nz, z = i - p*nz;
+        const float2 v = Z[i];
+        dst[(size_t) (2*p)*nz + z] = v.x;
+        if (2*p+1 < nrows) dst[(size_t) (2*p+1)*nz + z] = v.y;
     }
 }
 
-// ---- B: forward x, convolution + energy, inverse x; one batch of (ky,kz) lines per CTA ----
+// ---- 2 / 4: along y, LINE_BATCH adjacent kz columns of one x per CTA ----
+__global__ void __launch_bounds__(FFT_THREADS) k_fft_y(PmeDev pme, int inverse) {
+    extern __shared__ float2 smem[];
+    const int ny = pme.ny, nzc = pme.nzc;
+    const int nbz = (nzc + LINE_BATCH - 1)/LINE_BATCH;
+    const int x = blockIdx.x/nbz, bz = blockIdx.x - x*nbz;
+    const int kz0 = bz*LINE_BATCH;
+    const int nk = min(LINE_BATCH, nzc - kz0);
+    float2* A = smem;
+    float2* B = A + LINE_BATCH*ny;
+    float2* tws = B + LINE_BATCH*ny;
+    stage_twiddles(tws, pme.plan[1]);
+    float2* base = pme.cgrid + (size_t) x*ny*nzc + kz0;
+    for (int i = threadIdx.x; i < ny*LINE_BATCH; i += blockDim.x) {
+        const int y = i/LINE_BATCH, l = i - y*LINE_BATCH;
+        if (l < nk) A[l*ny + y] = base[(size_t) y*nzc + l];
+    }
+    __syncthreads();
+    const float2* R = fft_lines(A, B, pme.plan[1], nk, tws, inverse != 0);
+    for (int i = threadIdx.x; i < ny*LINE_BATCH; i += blockDim.x) {
+        const int y = i/LINE_BATCH, l = i - y*LINE_BATCH;
+        if (l < nk) base[(size_t) y*nzc + l] = R[l*ny + y];
+    }
+}
+
+// ---- 3: forward x, convolution + energy, inverse x; one batch of (ky,kz) lines per CTA ----
 // mode 0: forward + convolution + inverse (PME); mode 1: forward only; mode 2: inverse only (stand-alone FFT)
 template <bool ENERGY>
-__global__ void __launch_bounds__(256) k_fft_x_conv(PmeDev pme, double* energyOut, int mode) {
+__global__ void __launch_bounds__(FFT_THREADS) k_fft_x_conv(PmeDev pme, double* energyOut, int mode) {
     extern __shared__ float2 smem[];
     const int nx = pme.nx;
     const int plane = pme.ny*pme.nzc;
     float2* A = smem;
-    float2* B = smem + FFT_LINE_BATCH*nx;
-    const int m0 = blockIdx.x*FFT_LINE_BATCH;
-    const int nl = min(FFT_LINE_BATCH, plane - m0);
-    for (int i = threadIdx.x; i < nx*FFT_LINE_BATCH; i += blockDim.x) {
-        int x = i/FFT_LINE_BATCH, l = i - x*FFT_LINE_BATCH;
-        A[l*nx + x] = (l < nl) ? pme.cgrid[(size_t) x*plane + m0 + l] : make_float2(0.f, 0.f);
+    float2* B = A + LINE_BATCH*nx;
+    float2* tws = B + LINE_BATCH*nx;
+    stage_twiddles(tws, pme.plan[0]);
+    const int m0 = blockIdx.x*LINE_BATCH;
+    const int nl = min(LINE_BATCH, plane - m0);
+    for (int i = threadIdx.x; i < nx*LINE_BATCH; i += blockDim.x) {
+        const int x = i/LINE_BATCH, l = i - x*LINE_BATCH;
+        if (l < nl) A[l*nx + x] = pme.cgrid[(size_t) x*plane + m0 + l];
     }
     __syncthreads();
     float2* R = A;
     float2* other = B;
     if (mode != 2) {
-        R = fft_lines(A, B, pme.plan[0], FFT_LINE_BATCH, 1, nx, false);
+        R = fft_lines(A, B, pme.plan[0], nl, tws, false);
         other = (R == A) ? B : A;
     }
     if (mode == 0) {
         float esum = 0.f;
-        for (int i = threadIdx.x; i < nx*FFT_LINE_BATCH; i += blockDim.x) {
-            int x = i/FFT_LINE_BATCH, l = i - x*FFT_LINE_BATCH;
+        for (int i = threadIdx.x; i < nx*LINE_BATCH; i += blockDim.x) {
+            const int x = i/LINE_BATCH, l = i - x*LINE_BATCH;
             if (l < nl) {
                 const int m = m0 + l;
                 const float et = pme.eterm[(size_t) x*plane + m];
-                float2 v = R[l*nx + x];
+                const float2 v = R[l*nx + x];
                 if (ENERGY) {
                     const int kz = m % pme.nzc;
                     const float wgt = (kz == 0 || (2*kz == pme.nz)) ? 1.f : 2.f;    // Hermitian mirror counted here
@@ -240,22 +312,22 @@ __global__ void __launch_bounds__(256) k_fft_x_conv(PmeDev pme, double* energyOu
             }
         }
         if (ENERGY) {
-            __shared__ float red[8];
+            __shared__ float red[FFT_THREADS/32];
             for (int off = 16; off > 0; off >>= 1) esum += __shfl_xor_sync(0xffffffffu, esum, off);
             if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = esum;
             __syncthreads();
             if (threadIdx.x == 0) {
                 float tot = 0.f;
-                for (int w = 0; w < (blockDim.x >> 5); w++) tot += red[w];
+                for (int w = 0; w < FFT_THREADS/32; w++) tot += red[w];
                 atomicAdd(energyOut, 0.5*(double) tot);
             }
         }
         __syncthreads();
     }
     if (mode != 1)
-        R = fft_lines(R, other, pme.plan[0], FFT_LINE_BATCH, 1, nx, true);
-    for (int i = threadIdx.x; i < nx*FFT_LINE_BATCH; i += blockDim.x) {
-        int x = i/FFT_LINE_BATCH, l = i - x*FFT_LINE_BATCH;
+        R = fft_lines(R, other, pme.plan[0], nl, tws, true);
+    for (int i = threadIdx.x; i < nx*LINE_BATCH; i += blockDim.x) {
+        const int x = i/LINE_BATCH, l = i - x*LINE_BATCH;
         if (l < nl) pme.cgrid[(size_t) x*plane + m0 + l] = R[l*nx + x];
     }
 }
@@ -264,36 +336,44 @@ static void set_smem(const void* f, size_t bytes) {
     if (bytes > 48*1024) cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
 }
 
+struct FftLaunch {
+    size_t zs, ys, xs;
+    int zb, yb, xb;
+    FftLaunch(const PmeDev& p) {
+        zs = (2*(size_t) (ZROWS/2)*p.nz + p.nz)*sizeof(float2);
+        ys = (2*(size_t) LINE_BATCH*p.ny + p.ny)*sizeof(float2);
+        xs = (2*(size_t) LINE_BATCH*p.nx + p.nx)*sizeof(float2);
+        zb = (p.nx*p.ny + ZROWS - 1)/ZROWS;
+        yb = p.nx*((p.nzc + LINE_BATCH - 1)/LINE_BATCH);
+        xb = (p.ny*p.nzc + LINE_BATCH - 1)/LINE_BATCH;
+        set_smem((const void*) k_fft_z_fwd, zs);
+        set_smem((const void*) k_fft_z_inv, zs);
+        set_smem((const void*) k_fft_y, ys);
+        set_smem((const void*) k_fft_x_conv<true>, xs);
+        set_smem((const void*) k_fft_x_conv<false>, xs);
+    }
+};
+
 void launch_pme_fft_conv(const NbDev& nb, const PmeDev& pme, bool energy, cudaStream_t s) {
-    size_t ps = fft_plane_smem_bytes(pme.ny, pme.nz);
-    size_t ls = fft_line_smem_bytes(pme.nx);
-    set_smem((const void*) k_fft_zy_fwd, ps);
-    set_smem((const void*) k_fft_yz_inv, ps);
-    set_smem((const void*) k_fft_x_conv<true>, ls);
-    set_smem((const void*) k_fft_x_conv<false>, ls);
-    int nbatch = (pme.ny*pme.nzc + FFT_LINE_BATCH - 1)/FFT_LINE_BATCH;
-    k_fft_zy_fwd<<<pme.nx, 512, ps, s>>>(pme);
-    if (energy) k_fft_x_conv<true><<<nbatch, 256, ls, s>>>(pme, nb.energy + EN_RECIP, 0);
-    else k_fft_x_conv<false><<<nbatch, 256, ls, s>>>(pme, nb.energy + EN_RECIP, 0);
-    k_fft_yz_inv<<<pme.nx, 512, ps, s>>>(pme);
+    FftLaunch L(pme);
+    k_fft_z_fwd<<<L.zb, FFT_THREADS, L.zs, s>>>(pme);
+    k_fft_y<<<L.yb, FFT_THREADS, L.ys, s>>>(pme, 0);
+    if (energy) k_fft_x_conv<true><<<L.xb, FFT_THREADS, L.xs, s>>>(pme, nb.energy + EN_RECIP, 0);
+    else k_fft_x_conv<false><<<L.xb, FFT_THREADS, L.xs, s>>>(pme, nb.energy + EN_RECIP, 0);
+    k_fft_y<<<L.yb, FFT_THREADS, L.ys, s>>>(pme, 1);
+    k_fft_z_inv<<<L.zb, FFT_THREADS, L.zs, s>>>(pme);
 }
 
 void launch_fft3d_r2c(const PmeDev& pme, cudaStream_t s) {
-    size_t ps = fft_plane_smem_bytes(pme.ny, pme.nz);
-    size_t ls = fft_line_smem_bytes(pme.nx);
-    set_smem((const void*) k_fft_zy_fwd, ps);
-    set_smem((const void*) k_fft_x_conv<false>, ls);
-    int nbatch = (pme.ny*pme.nzc + FFT_LINE_BATCH - 1)/FFT_LINE_BATCH;
-    k_fft_zy_fwd<<<pme.nx, 512, ps, s>>>(pme);
-    k_fft_x_conv<false><<<nbatch, 256, ls, s>>>(pme, nullptr, 1);
+    FftLaunch L(pme);
+    k_fft_z_fwd<<<L.zb, FFT_THREADS, L.zs, s>>>(pme);
+    k_fft_y<<<L.yb, FFT_THREADS, L.ys, s>>>(pme, 0);
+    k_fft_x_conv<false><<<L.xb, FFT_THREADS, L.xs, s>>>(pme, nullptr, 1);
 }
 
 void launch_fft3d_c2r(const PmeDev& pme, cudaStream_t s) {
-    size_t ps = fft_plane_smem_bytes(pme.ny, pme.nz);
-    size_t ls = fft_line_smem_bytes(pme.nx);
-    set_smem((const void*) k_fft_yz_inv, ps);
-    set_smem((const void*) k_fft_x_conv<false>, ls);
-    int nbatch = (pme.ny*pme.nzc + FFT_LINE_BATCH - 1)/FFT_LINE_BATCH;
-    k_fft_x_conv<false><<<nbatch, 256, ls, s>>>(pme, nullptr, 2);
-    k_fft_yz_inv<<<pme.nx, 512, ps, s>>>(pme);
+    FftLaunch L(pme);
+    k_fft_x_conv<false><<<L.xb, FFT_THREADS, L.xs, s>>>(pme, nullptr, 2);
+    k_fft_y<<<L.yb, FFT_THREADS, L.ys, s>>>(pme, 1);
+    k_fft_z_inv<<<L.zb, FFT_THREADS, L.zs, s>>>(pme);
 }

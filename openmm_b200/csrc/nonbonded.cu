@@ -169,6 +169,7 @@ __global__ void k_finalize_sort(NbDev nb) {
         nb.sposq[s] = make_float4(p.x+sh.x, p.y+sh.y, p.z+sh.z, p.w);
         nb.ssigeps[s] = nb.sigeps[a];
         nb.refPos[a] = p;
+        if (s == 0) nb.counters[7] = 0;        // max block half extent, filled by k_block_bounds
     }
     else {
         nb.sorig[s] = -1;
@@ -197,6 +198,8 @@ __global__ void k_block_bounds(NbDev nb) {
     if (lane == 0) {
         nb.blockCenter[warp] = make_float4(0.5f*(lox+hix), 0.5f*(loy+hiy), 0.5f*(loz+hiz), 0);
         nb.blockHalf[warp] = make_float4(0.5f*(hix-lox), 0.5f*(hiy-loy), 0.5f*(hiz-loz), 0);
+        const float h = 0.5f*fmaxf(hix-lox, fmaxf(hiy-loy, hiz-loz));
+        atomicMax(&nb.counters[7], __float_as_int(h));       // non-negative floats order like ints
     }
     if (warp == 0 && lane == 0) { nb.counters[0] = 0; nb.counters[1] = 0; }
 }
@@ -357,19 +360,38 @@ void launch_gather_sorted(const NbDev& nb, cudaStream_t s) {
 //   PME:    dEdR = qi qj/r^3 (erfc(ar) + 2 ar exp(-a^2 r^2)/sqrt(pi)) + sw*eps(12 s^12 - 6 s^6)/r^2 [- E_lj sw'/r]
 //           E    = qi qj erfc(ar)/r + sw*eps (s^12 - s^6)
 //   cutoff: reaction field (ReferenceLJCoulombIxn.cpp:559-575): dEdR = qi qj (1/r^3 - 2 krf) ..., E = qi qj (1/r + krf r^2 - crf)
-template <bool ENERGY, int METHOD>
-__global__ void __launch_bounds__(256) k_pair(NbDev nb) {
+//
+// B200 notes (profiles/r01_k_pair_v1_details.csv): the v1 loop was bound by the XU pipe (MUFU + FRND: rsqrt, ex2,
+// rcp and three rintf of the per-pair minimum image = 6 XU ops per pair slot, ~5 clk/SM each).  v2:
+//  * SHIFT mode: when every block satisfies halfExtent <= L/2 - cutoff - padding (checked on the device at list
+//    build) the j atoms of a tile are moved ONCE to the periodic image nearest the i-block centre, and the per-pair
+//    minimum image (3 FRND) disappears; pairs whose true image would differ are beyond the cutoff either way.
+//  * forces without energy use the identity erfc(z) + 2z exp(-z^2)/sqrt(pi) = 1 - z^3 g(z^2) with a (5,5) rational
+//    minimax fit of g(w) = (erf(z) - 2z exp(-z^2)/sqrt(pi))/z^3 on w = z^2 in [0,14] (|err| < 1.2e-7 evaluated in
+//    fp32): one MUFU.RCP instead of EX2 + RCP + the 5-term erfc polynomial.  The energy path keeps erfc (A&S 7.1.26).
+//  * the loop body is branch-free (select instead of a divergent branch) so unrolled iterations interleave.
+#define PME_G_WMAX 14.0f
+
+__device__ __forceinline__ float ewald_g(float w) {
+    const float p = 0.7522528288f + w*(-0.01832553619f + w*(0.01676110697f + w*(0.0002032837893f + w*(3.445905357e-05f + w*(-3.521083106e-07f)))));
+    const float q = 1.0f + w*(0.5756407144f + w*(0.1533710339f + w*(0.02451798422f + w*(0.002480551583f + w*0.0001580620439f))));
+    return __fdividef(p, q);
+}
+
+template <bool ENERGY, int METHOD, bool SHIFT, bool RATIONAL>
+__device__ __forceinline__ void pair_tiles(const NbDev& nb, float& energy) {
     const int lane = threadIdx.x & 31;
     const int gwarp = (blockIdx.x*blockDim.x + threadIdx.x) >> 5;
     const int nwarps = (gridDim.x*blockDim.x) >> 5;
     const int ntiles = min(nb.counters[0], nb.maxTiles);
     const bool periodic = nb.box.periodic != 0;
-    float energy = 0.f;
+    const float alpha2 = nb.alpha*nb.alpha, alpha3 = alpha2*nb.alpha;
+    const int src = (lane + 1) & 31;
     // tiles are dealt round-robin over (rank, warp): the multi-GPU force decomposition shards this loop
     for (int t = nb.rank + nb.world*gwarp; t < ntiles; t += nb.world*nwarps) {
         const int ib = nb.tileI[t];
         const int si = ib*32 + lane;
-        const float4 pi = nb.sposq[si];
+        float4 pi = nb.sposq[si];
         const float2 sei = nb.ssigeps[si];
         const int jidx = nb.tileJ[t*32 + lane];
         const int jj = max(jidx, 0);
@@ -377,21 +399,31 @@ __global__ void __launch_bounds__(256) k_pair(NbDev nb) {
         float2 sej = nb.ssigeps[jj];
         const int mi = nb.tileMask[t];
         const unsigned int mask = (mi < 0) ? FULL : nb.maskPool[mi*32 + lane];
+        if (SHIFT) {
+            const float4 c = nb.blockCenter[ib];
+            pi.x -= c.x; pi.y -= c.y; pi.z -= c.z;
+            pj.x -= c.x; pj.y -= c.y; pj.z -= c.z;
+            pi.x -= nb.box.ax*rintf(pi.x*nb.box.invAx); pi.y -= nb.box.by*rintf(pi.y*nb.box.invBy); pi.z -= nb.box.cz*rintf(pi.z*nb.box.invCz);
+            pj.x -= nb.box.ax*rintf(pj.x*nb.box.invAx); pj.y -= nb.box.by*rintf(pj.y*nb.box.invBy); pj.z -= nb.box.cz*rintf(pj.z*nb.box.invCz);
+        }
         float fix = 0.f, fiy = 0.f, fiz = 0.f, fjx = 0.f, fjy = 0.f, fjz = 0.f;
-        const int src = (lane + 1) & 31;
 #pragma unroll 4
         for (int k = 0; k < 32; k++) {
             const int slot = (lane + k) & 31;
             float3 d = make_float3(pj.x-pi.x, pj.y-pi.y, pj.z-pi.z);
-            if (periodic) d = min_image(d, nb.box);
-            const float r2 = d.x*d.x + d.y*d.y + d.z*d.z;
-            if (((mask >> slot) & 1u) && r2 < nb.cutoff2) {
-                const float invR = rsqrtf(r2);
-                const float r = r2*invR;
-                const float invR2 = invR*invR;
-                const float qq = pi.w*pj.w;
-                float dEdR, e;
-                if (METHOD == B200MD_NB_PME) {
+            if (!SHIFT && periodic) d = min_image(d, nb.box);
+            const float r2raw = d.x*d.x + d.y*d.y + d.z*d.z;
+            const bool valid = ((mask >> slot) & 1u) && r2raw < nb.cutoff2;
+            const float r2 = valid ? r2raw : 1.0f;
+            const float invR = rsqrtf(r2);
+            const float invR2 = invR*invR;
+            const float qq = pi.w*pj.w;
+            float dEdR, e = 0.f;
+            if (METHOD == B200MD_NB_PME) {
+                if (RATIONAL && !ENERGY)
+                    dEdR = qq*(invR*invR2 - alpha3*ewald_g(alpha2*r2));
+                else {
+                    const float r = r2*invR;
                     const float ar = nb.alpha*r;
                     const float ex = __expf(-ar*ar);
                     // erfc: Abramowitz-Stegun 7.1.26, |err| < 1.5e-7 (same form as coulombLennardJones.cc:15-20)
@@ -401,34 +433,37 @@ __global__ void __launch_bounds__(256) k_pair(NbDev nb) {
                     dEdR = pref*invR2*(erfcAr + 1.1283791671f*ar*ex);
                     e = pref*erfcAr;
                 }
-                else if (METHOD == B200MD_NB_NOCUTOFF) {
-                    const float pref = qq*invR;
-                    dEdR = pref*invR2;
-                    e = pref;
-                }
-                else {   // cutoff with reaction field
-                    dEdR = qq*(invR*invR2 - 2.0f*nb.krf);
-                    e = qq*(invR + nb.krf*r2 - nb.crf);
-                }
-                const float sig = sei.x + sej.x;
-                const float eps = sei.y*sej.y;
-                float s2 = sig*invR; s2 *= s2;
-                const float s6 = s2*s2*s2;
-                float ljF = eps*(12.0f*s6 - 6.0f)*s6*invR2;
-                float ljE = eps*(s6 - 1.0f)*s6;
-                if (nb.useSwitch && r > nb.switchDist) {
-                    const float w = nb.cutoff - nb.switchDist;
-                    const float x = (r - nb.switchDist)/w;
+            }
+            else if (METHOD == B200MD_NB_NOCUTOFF) {
+                const float pref = qq*invR;
+                dEdR = pref*invR2;
+                e = pref;
+            }
+            else {   // cutoff with reaction field
+                dEdR = qq*(invR*invR2 - 2.0f*nb.krf);
+                e = qq*(invR + nb.krf*r2 - nb.crf);
+            }
+            const float sig = sei.x + sej.x;
+            const float eps = sei.y*sej.y;
+            float s2 = sig*invR; s2 *= s2;
+            const float s6 = s2*s2*s2;
+            float ljF = eps*(12.0f*s6 - 6.0f)*s6*invR2;
+            float ljE = eps*(s6 - 1.0f)*s6;
+            if (nb.useSwitch) {
+                const float r = r2*invR;
+                if (r > nb.switchDist) {
+                    const float w = __fdividef(1.0f, nb.cutoff - nb.switchDist);
+                    const float x = (r - nb.switchDist)*w;
                     const float sw = 1.0f + x*x*x*(-10.0f + x*(15.0f - x*6.0f));
-                    const float dsw = x*x*(-30.0f + x*(60.0f - x*30.0f))/w;
+                    const float dsw = x*x*(-30.0f + x*(60.0f - x*30.0f))*w;
                     ljF = sw*ljF - ljE*dsw*invR;
                     ljE *= sw;
                 }
-                dEdR += ljF;
-                if (ENERGY) energy += e + ljE;
-                fix -= d.x*dEdR; fiy -= d.y*dEdR; fiz -= d.z*dEdR;
-                fjx += d.x*dEdR; fjy += d.y*dEdR; fjz += d.z*dEdR;
             }
+            dEdR = valid ? dEdR + ljF : 0.f;
+            if (ENERGY) energy += valid ? e + ljE : 0.f;
+            fix -= d.x*dEdR; fiy -= d.y*dEdR; fiz -= d.z*dEdR;
+            fjx += d.x*dEdR; fjy += d.y*dEdR; fjz += d.z*dEdR;
             pj.x = __shfl_sync(FULL, pj.x, src); pj.y = __shfl_sync(FULL, pj.y, src);
             pj.z = __shfl_sync(FULL, pj.z, src); pj.w = __shfl_sync(FULL, pj.w, src);
             sej.x = __shfl_sync(FULL, sej.x, src); sej.y = __shfl_sync(FULL, sej.y, src);
@@ -448,9 +483,28 @@ __global__ void __launch_bounds__(256) k_pair(NbDev nb) {
             atomicAdd((unsigned long long*) &nb.force[aj + 2*nb.npad], (unsigned long long) __float2ll_rn(fjz*4294967296.0f));
         }
     }
+}
+
+template <bool ENERGY, int METHOD>
+__global__ void __launch_bounds__(256) k_pair(NbDev nb) {
+    float energy = 0.f;
+    // counters[7]: max block half extent (float bits) recorded at list build
+    const float maxHalf = __int_as_float(nb.counters[7]);
+    const BoxDev& b = nb.box;
+    const float minL = fminf(b.ax, fminf(b.by, b.cz));
+    const bool shiftOK = b.periodic && !b.triclinic && (0.5f*minL - nb.cutoff - 2.0f*sqrtf(nb.halfPad2) >= maxHalf);
+    const bool rational = (METHOD == B200MD_NB_PME) && (nb.alpha*nb.alpha*nb.cutoff2 < PME_G_WMAX);
+    if (shiftOK) {
+        if (rational) pair_tiles<ENERGY, METHOD, true, true>(nb, energy);
+        else pair_tiles<ENERGY, METHOD, true, false>(nb, energy);
+    }
+    else {
+        if (rational) pair_tiles<ENERGY, METHOD, false, true>(nb, energy);
+        else pair_tiles<ENERGY, METHOD, false, false>(nb, energy);
+    }
     if (ENERGY) {
         for (int off = 16; off > 0; off >>= 1) energy += __shfl_xor_sync(FULL, energy, off);
-        if (lane == 0 && energy != 0.f) atomicAdd(&nb.energy[EN_NB], (double) energy);
+        if ((threadIdx.x & 31) == 0 && energy != 0.f) atomicAdd(&nb.energy[EN_NB], (double) energy);
     }
 }
 

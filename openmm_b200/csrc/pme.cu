@@ -76,11 +76,12 @@ __global__ void __launch_bounds__(128) k_pme_spread(NbDev nb, PmeDev pme) {
         for (int iy = 0; iy < ORDER; iy++) {
             int yi = idx[1] + iy; if (yi >= pme.ny) yi -= pme.ny;
             const float qxy = qx*ty[iy];
-            float* row = pme.grid + ((size_t) xi*pme.ny + yi)*pme.nz;
+            long long* row = pme.gridFixed + ((size_t) xi*pme.ny + yi)*pme.nz;
 #pragma unroll
             for (int iz = 0; iz < ORDER; iz++) {
                 int zi = idx[2] + iz; if (zi >= pme.nz) zi -= pme.nz;
-                atomicAdd(row + zi, qxy*tz[iz]);
+                // integer accumulation: the grid (hence every force) is independent of the order of the atomics
+                atomicAdd((unsigned long long*) (row + zi), (unsigned long long) __float2ll_rn(qxy*tz[iz]*4294967296.0f));
             }
         }
     }
@@ -164,7 +165,7 @@ void launch_pme_eterm(const NbDev& nb, const PmeDev& pme, cudaStream_t s) {
 }
 
 void launch_pme_spread(const NbDev& nb, const PmeDev& pme, cudaStream_t s) {
-    cudaMemsetAsync(pme.grid, 0, sizeof(float)*(size_t) pme.nx*pme.ny*pme.nz, s);
+    cudaMemsetAsync(pme.gridFixed, 0, sizeof(long long)*(size_t) pme.nx*pme.ny*pme.nz, s);
     const int per = (nb.natoms + nb.world - 1)/nb.world;
     k_pme_spread<<<(per + 127)/128, 128, 0, s>>>(nb, pme);
 }

@@ -1,0 +1,112 @@
+"""GPU tests of the drop-in boundary proper: the B200 Platform plugin (plugin/libOpenMMB200.so) loaded into the
+UNMODIFIED reference OpenMM (oracle/_ref/libOpenMM.so) through Platform::loadPluginLibrary, driven through the
+reference's public API (System / NonbondedForce / Context / LangevinIntegrator), compared with the Reference platform
+in the same process -- plus the reference's own test bodies (tests/Test<X>.h) built against the B200 platform."""
+import os
+import subprocess
+import numpy as np
+import pytest
+from conftest import relative_force_error, ROOT
+
+pytestmark = pytest.mark.gpu
+PLUGIN = os.path.join(ROOT, "plugin", "libOpenMMB200.so")
+REFTESTS = os.path.join(ROOT, "oracle", "_ref", "tests")
+
+
+@pytest.fixture(scope="module")
+def omm():
+    from oracle import omm
+    if not omm.available() or not os.path.exists(PLUGIN):
+        pytest.fail("oracle/_ref or the plugin is not built: run __graft_entry__.build() where /root/reference exists")
+    omm.load_plugin(PLUGIN)
+    assert "B200" in omm.platforms()
+    return omm
+
+
+def test_plugin_forces_energy_match_reference_platform(omm):
+    from openmm_b200 import systems
+    for d in (systems.water_box(7, cutoff=0.9).rounded(), systems.water_box(7, cutoff=0.9, rigid=False).rounded(),
+              systems.random_ions(894, 3.0, cutoff=1.0, triclinic=True).rounded(), systems.cluster(70).rounded()):
+        pme = d.pme_parameters() if d.method == systems.NB_PME else None
+        a = omm.Simulation(d, "B200", pme=pme)
+        b = omm.Simulation(d, "Reference", pme=pme)
+        assert a.platform() == "B200"
+        fa, ea = a.forces_energy()
+        fb, eb = b.forces_energy()
+        assert relative_force_error(fa, fb) < 1e-4
+        assert abs(ea - eb)/max(1.0, abs(eb)) < 1e-4
+        if pme is not None:
+            assert a.pme_parameters()[1:] == tuple(pme[1:])
+
+
+def test_plugin_force_groups_direct_vs_reciprocal(omm):
+    from openmm_b200 import systems
+    d = systems.water_box(7, cutoff=0.9).rounded()
+    pme = d.pme_parameters()
+    a = omm.Simulation(d, "B200", pme=pme, recip_group=1)
+    b = omm.Simulation(d, "Reference", pme=pme, recip_group=1)
+    ftot = b.forces_energy(3)[0]
+    scale = np.maximum(1.0, np.linalg.norm(ftot, axis=1))[:, None]
+    for groups in (1, 2, 3):
+        fa, ea = a.forces_energy(groups)
+        fb, eb = b.forces_energy(groups)
+        # each group against the reference's SAME group; the error is measured on the scale of the TOTAL force of
+        # the atom (the reciprocal part alone is a small difference of large fp32 grid terms)
+        assert np.abs((fa - fb)/scale).max() < 1e-4 and abs(ea - eb)/max(1.0, abs(eb)) < 1e-4
+
+
+def test_plugin_langevin_dynamics_and_constraints(omm):
+    from openmm_b200 import systems
+    d = systems.water_box(8, cutoff=0.9).rounded()
+    sim = omm.Simulation(d, "B200", integrator=(systems.INT_LANGEVIN, 300.0, 2.0, 0.002), pme=d.pme_parameters())
+    sim.set_velocities_to_temperature(300.0, 3)
+    sim.step(400)
+    st = sim.state(positions=True, energy=True)
+    x = st["positions"]
+    for i, j, dist in zip(d.con_i[::5], d.con_j[::5], d.con_d[::5]):
+        assert abs(np.linalg.norm(x[i]-x[j]) - dist) < 1e-5
+    dof = 3*d.natoms - len(d.con_i)
+    T = 2*st["kinetic"]/(dof*0.00831446261815324)
+    assert 250 < T < 350
+    assert abs(sim.L.omm_context_get_time(sim.ctx) - 0.8) < 1e-9
+
+
+def test_plugin_deterministic_verlet_follows_reference(omm):
+    from openmm_b200 import systems
+    d = systems.water_box(6, cutoff=0.9).rounded()
+    v = np.random.default_rng(3).standard_normal((d.natoms, 3))*0.3
+    a = omm.Simulation(d, "B200", integrator=(systems.INT_VERLET, 0, 0, 0.001), pme=d.pme_parameters())
+    b = omm.Simulation(d, "Reference", integrator=(systems.INT_VERLET, 0, 0, 0.001), pme=d.pme_parameters())
+    for s in (a, b):
+        s.set_velocities(v)
+        s.step(10)
+    sa, sb = a.state(positions=True, energy=True), b.state(positions=True, energy=True)
+    assert np.abs(sa["positions"] - sb["positions"]).max() < 5e-6
+    assert abs(sa["potential"] - sb["potential"])/abs(sb["potential"]) < 1e-4
+    assert abs(sa["kinetic"] - sb["kinetic"])/sb["kinetic"] < 1e-3
+
+
+def test_plugin_checkpoint(omm):
+    from openmm_b200 import systems
+    d = systems.water_box(5, cutoff=0.75).rounded()
+    sim = omm.Simulation(d, "B200", integrator=(systems.INT_LANGEVIN, 300.0, 1.0, 0.002), pme=d.pme_parameters())
+    sim.step(5)
+    sim.checkpoint_roundtrip()
+    sim.step(5)
+    assert np.isfinite(sim.state(positions=True)["positions"]).all()
+
+
+REFERENCE_TEST_BINARIES = ["TestB200NonbondedForce", "TestB200Ewald", "TestB200Settle", "TestB200LangevinIntegrator", "TestB200LangevinMiddleIntegrator",
+                           "TestB200VerletIntegrator", "TestB200HarmonicBondForce", "TestB200HarmonicAngleForce", "TestB200PeriodicTorsionForce",
+                           "TestB200CMMotionRemover"]
+
+
+@pytest.mark.parametrize("name", REFERENCE_TEST_BINARIES)
+def test_reference_own_test_bodies_pass_on_b200_platform(name):
+    """tests/Test<X>.h of the reference compiled against our platform (plugin/tests/shim.cpp lists which functions)."""
+    exe = os.path.join(REFTESTS, name)
+    if not os.path.exists(exe):
+        pytest.fail("%s not built (make -C plugin reftests where /root/reference exists)" % exe)
+    env = dict(os.environ, B200_PLUGIN=PLUGIN)
+    p = subprocess.run([exe], capture_output=True, text=True, timeout=600, env=env)
+    assert p.returncode == 0 and "Done" in p.stdout, p.stdout[-2000:] + p.stderr[-2000:]
