@@ -6,9 +6,10 @@
 
 One bench "step" = `--md-steps` MD steps (default 500 = 1 ps at 2 fs) of the workload: force evaluation (tile list
 check/rebuild, direct-space tile kernel, PME spread + bespoke FFT/convolution + gather, exclusion corrections) and the
-fused Langevin+SETTLE update.  Default workload `water24k` = S1 of SURVEY.md 8(d): the DHFR-sized explicit-solvent
-PME system (24,000 atoms vs DHFR's 23,558; same 56^3 grid, 0.9 nm cutoff, rigid water, Langevin 2 fs).  `dhfr` /
-`apoa1` use the real benchmark systems when their fixtures exist under data/.
+fused Langevin+SETTLE/SHAKE update.  Default workload `dhfr` = BASELINE.json configs[1]: the real DHFR benchmark system
+(23,558 atoms, amber99sb + tip3p, PME 0.9 nm, 56^3 grid, HBonds + rigid water, Langevin 2 fs) from data/dhfr.npz, which
+tools/make_benchmark_systems.py builds with the reference's own forcefield.py.  Others: `apoa1` (92,224 atoms, 88^3),
+`water24k` (S1 of SURVEY.md 8d), `water1m` (S4).
 N > 1 (torchrun, one process per GPU): the SAME system on N GPUs by force decomposition -> "scaling": "strong".
 """
 import argparse
@@ -114,7 +115,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default=os.environ.get("B200MD_WORKLOAD", "water24k"))
+    ap.add_argument("--workload", default=os.environ.get("B200MD_WORKLOAD", "dhfr"))
     ap.add_argument("--md-steps", type=int, default=500)
     ap.add_argument("--ref-md-steps", type=int, default=10)
     ap.add_argument("--dt", type=float, default=0.002)
@@ -220,7 +221,7 @@ def main():
     flops = T*1024*60.0
     line = {"metric": "ns/day", "value": nsday, "unit": "ns/day", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms/args.steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": args.workload, "atoms": d.natoms, "md_steps_per_step": md, "dt_fs": args.dt*1e3, "integrator": "Langevin 300K 1/ps + SETTLE",
+            "config": {"workload": args.workload, "atoms": d.natoms, "md_steps_per_step": md, "dt_fs": args.dt*1e3, "integrator": "Langevin 300K 1/ps + SETTLE/SHAKE (HBonds)",
                        "cutoff_nm": d.cutoff, "pme_grid": st["pme_grid"], "parallelism": "force-decomposition x%d" % world if world > 1 else "single GPU",
                        "l2": "256 MiB buffer written between timed iterations (inside the timed region)", "us_per_md_step": 1e3*ms/(args.steps*md)},
             "clocks": sampler.summary(),

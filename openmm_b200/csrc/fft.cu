@@ -24,65 +24,38 @@
 
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) { return make_float2(a.x*b.x - a.y*b.y, a.x*b.y + a.y*b.x); }
 
-// one Stockham stage of radix R over `nlines` contiguous lines of length n (line l at base + l*n).
-// tw: exp(-2 pi i k/n) in shared memory.
-template <int R>
-__device__ __forceinline__ void fft_stage(const float2* __restrict__ in, float2* __restrict__ out, int n, int nlines,
+// One Stockham stage of radix R over `nlines` contiguous lines of length n (line l at base + l*n), ONE OUTPUT ELEMENT
+// PER THREAD: output q of butterfly j is sum_t x[j + t n/R] * w^(t (k twStep + q n/R)) -- the stage twiddle and the
+// radix-R DFT root collapse into a single table lookup whose index advances by a constant e (mod n).  The loop is
+// rolled: the whole stage is ~40 instructions of code for every radix, and every grid point is an independent work
+// item (profiles/r01: the fully unrolled one-butterfly-per-thread version ran at 7 % issue utilisation, stalled on
+// instruction fetch and with 4 warps per SM).
+__device__ __forceinline__ void fft_stage(const float2* __restrict__ in, float2* __restrict__ out, int n, int nlines, int R,
                                           int Ns, const float2* __restrict__ tw, bool inverse) {
     const int nb = n/R;                 // butterflies per line
     const int twStep = n/(Ns*R);
-    const int total = nlines*nb;
+    const int total = nlines*n;
     for (int w = threadIdx.x; w < total; w += blockDim.x) {
-        const int line = w/nb;
-        const int j = w - line*nb;
+        const int line = w/n;
+        const int rem = w - line*n;
+        const int j = rem/R;
+        const int q = rem - j*R;
         const int k = j % Ns;
-        const float2* src = in + line*n;
-        float2 v[R];
-#pragma unroll
-        for (int t = 0; t < R; t++) {
-            float2 x = src[j + t*nb];
-            if (t > 0 && k > 0) {
-                float2 wv = tw[t*k*twStep];
-                if (inverse) wv.y = -wv.y;
-                x = cmul(x, wv);
-            }
-            v[t] = x;
+        int e = k*twStep + q*nb;
+        if (e >= n) e -= n*(e/n);
+        const float2* src = in + line*n + j;
+        float2 acc = src[0];
+        int idx = e;
+        for (int t = 1; t < R; t++) {
+            const float2 x = src[t*nb];
+            float2 wv = tw[idx];
+            if (inverse) wv.y = -wv.y;
+            acc.x += x.x*wv.x - x.y*wv.y;
+            acc.y += x.x*wv.y + x.y*wv.x;
+            idx += e;
+            if (idx >= n) idx -= n;
         }
-        float2* dst = out + line*n;
-        const int j0 = (j/Ns)*Ns*R + k;
-        if (R == 2) {
-            dst[j0] = make_float2(v[0].x + v[1].x, v[0].y + v[1].y);
-            dst[j0 + Ns] = make_float2(v[0].x - v[1].x, v[0].y - v[1].y);
-        }
-        else if (R == 4) {
-            // radix-4 butterfly with trivial twiddles (-i forward, +i inverse)
-            const float2 a = make_float2(v[0].x + v[2].x, v[0].y + v[2].y), b = make_float2(v[0].x - v[2].x, v[0].y - v[2].y);
-            const float2 c = make_float2(v[1].x + v[3].x, v[1].y + v[3].y), d = make_float2(v[1].x - v[3].x, v[1].y - v[3].y);
-            const float2 id = inverse ? make_float2(-d.y, d.x) : make_float2(d.y, -d.x);     // (-+)i * d
-            dst[j0] = make_float2(a.x + c.x, a.y + c.y);
-            dst[j0 + Ns] = make_float2(b.x + id.x, b.y + id.y);
-            dst[j0 + 2*Ns] = make_float2(a.x - c.x, a.y - c.y);
-            dst[j0 + 3*Ns] = make_float2(b.x - id.x, b.y - id.y);
-        }
-        else {
-            float2 root[R];
-#pragma unroll
-            for (int m = 0; m < R; m++) {
-                const float2 wv = tw[m*nb];
-                root[m] = inverse ? make_float2(wv.x, -wv.y) : wv;
-            }
-#pragma unroll
-            for (int q = 0; q < R; q++) {
-                float2 acc = v[0];
-#pragma unroll
-                for (int t = 1; t < R; t++) {
-                    const float2 r = root[(q*t) % R];
-                    acc.x += v[t].x*r.x - v[t].y*r.y;
-                    acc.y += v[t].x*r.y + v[t].y*r.x;
-                }
-                dst[j0 + q*Ns] = acc;
-            }
-        }
+        out[line*n + (j/Ns)*Ns*R + k + q*Ns] = acc;
     }
 }
 
@@ -93,24 +66,7 @@ __device__ float2* fft_lines(float2* a, float2* b, const FftPlanDev& plan, int n
     float2* out = b;
     for (int s = 0; s < plan.nstages; s++) {
         const int R = plan.radix[s];
-        switch (R) {
-            case 2: fft_stage<2>(in, out, plan.n, nlines, Ns, tw, inverse); break;
-            case 3: fft_stage<3>(in, out, plan.n, nlines, Ns, tw, inverse); break;
-            case 4: fft_stage<4>(in, out, plan.n, nlines, Ns, tw, inverse); break;
-            case 5: fft_stage<5>(in, out, plan.n, nlines, Ns, tw, inverse); break;
-            case 6: fft_stage<6>(in, out, plan.n, nlines, Ns, tw, inverse); break;
-            case 7: fft_stage<7>(in, out, plan.n, nlines, Ns, tw, inverse); break;
-            case 8: fft_stage<8>(in, out, plan.n, nlines, Ns, tw, inverse); break;
-            case 9: fft_stage<9>(in, out, plan.n, nlines, Ns, tw, inverse); break;
-            case 10: fft_stage<10>(in, out, plan.n, nlines, Ns, tw, inverse); break;
-            case 11: fft_stage<11>(in, out, plan.n, nlines, Ns, tw, inverse); break;
-            case 12: fft_stage<12>(in, out, plan.n, nlines, Ns, tw, inverse); break;
-            case 13: fft_stage<13>(in, out, plan.n, nlines, Ns, tw, inverse); break;
-            case 14: fft_stage<14>(in, out, plan.n, nlines, Ns, tw, inverse); break;
-            case 15: fft_stage<15>(in, out, plan.n, nlines, Ns, tw, inverse); break;
-            case 16: fft_stage<16>(in, out, plan.n, nlines, Ns, tw, inverse); break;
-            default: break;   // n == 1
-        }
+        fft_stage(in, out, plan.n, nlines, R, Ns, tw, inverse);
         __syncthreads();
         Ns *= R;
         float2* t = in; in = out; out = t;
@@ -126,7 +82,7 @@ static int best_cost(int n, int* radix, int depth) {
     int best = 1 << 28, sub[B200MD_MAX_FFT_STAGES];
     for (int r = 2; r <= B200MD_MAX_RADIX && r <= n; r++) {
         if (n % r) continue;
-        const int stageCost = (r == 2 ? 2 : (r == 4 ? 3 : r)) + 4;
+        const int stageCost = r + 4;
         int c = stageCost + best_cost(n/r, sub, depth+1);
         if (c < best) {
             best = c;
@@ -152,7 +108,7 @@ bool fft_make_radices(int n, int* radix, int* nstages) {
 
 #define ZROWS 16          // real rows per CTA in the z passes (8 packed complex lines)
 #define LINE_BATCH 16     // lines per CTA in the y and x passes
-#define FFT_THREADS 128
+#define FFT_THREADS 256
 
 size_t fft_plane_smem_bytes(int ny, int nz) {       // kept for the engine's capacity check: largest per-CTA need
     size_t z = (2*(size_t) (ZROWS/2)*nz + nz)*sizeof(float2);

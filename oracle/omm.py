@@ -32,6 +32,9 @@ def lib():
             "omm_system_add_constraints": (None, [P, C.c_int, I, I, D]), "omm_system_add_force": (C.c_int, [P, P]),
             "omm_system_serialize": (C.c_int, [P, C.c_char_p]),
             "omm_nonbonded_create": (P, [C.c_int, D, D, D]), "omm_nonbonded_add_exceptions": (None, [P, C.c_int, I, I, D, D, D]),
+            "omm_nonbonded_create_exceptions_from_bonds": (None, [P, C.c_int, I, I, C.c_double, C.c_double]),
+            "omm_nonbonded_num_exceptions": (C.c_int, [P]), "omm_nonbonded_get_exceptions": (None, [P, I, I, D, D, D]),
+            "omm_force_destroy": (None, [P]),
             "omm_nonbonded_set_method": (None, [P, C.c_int, C.c_double, C.c_double]), "omm_nonbonded_set_pme": (None, [P, C.c_double, C.c_int, C.c_int, C.c_int]),
             "omm_nonbonded_set_switch": (None, [P, C.c_int, C.c_double]), "omm_nonbonded_set_dispersion": (None, [P, C.c_int]),
             "omm_nonbonded_set_rf_dielectric": (None, [P, C.c_double]), "omm_nonbonded_set_recip_group": (None, [P, C.c_int]),
@@ -84,6 +87,21 @@ def load_plugin(path):
 def platforms():
     L = lib()
     return [L.omm_platform_name(i).decode() for i in range(L.omm_num_platforms())]
+
+
+def exceptions_from_bonds(charges, sigmas, epsilons, bond_i, bond_j, coulomb14, lj14):
+    """NonbondedForce::createExceptionsFromBonds of the reference itself (NonbondedForce.cpp:207-248)."""
+    L = lib()
+    n = len(charges)
+    nb = L.omm_nonbonded_create(n, _dp(_f64(charges)), _dp(_f64(sigmas)), _dp(_f64(epsilons)))
+    bi, bj = _i32(bond_i), _i32(bond_j)
+    L.omm_nonbonded_create_exceptions_from_bonds(nb, len(bi), _ip(bi), _ip(bj), coulomb14, lj14)
+    ne = L.omm_nonbonded_num_exceptions(nb)
+    i, j = np.zeros(ne, np.int32), np.zeros(ne, np.int32)
+    qq, sg, ep = np.zeros(ne), np.zeros(ne), np.zeros(ne)
+    L.omm_nonbonded_get_exceptions(nb, _ip(i), _ip(j), _dp(qq), _dp(sg), _dp(ep))
+    L.omm_force_destroy(nb)
+    return i, j, qq, sg, ep
 
 
 class Simulation:

@@ -71,6 +71,18 @@ void* omm_nonbonded_create(int n, const double* q, const double* sigma, const do
 void omm_nonbonded_add_exceptions(void* f, int n, const int* i, const int* j, const double* qq, const double* sigma, const double* eps) {
     for (int k = 0; k < n; k++) ((NonbondedForce*) f)->addException(i[k], j[k], qq[k], sigma[k], eps[k]);
 }
+// NonbondedForce::createExceptionsFromBonds (NonbondedForce.cpp:207-248) on the real reference object, then read back
+void omm_nonbonded_create_exceptions_from_bonds(void* f, int n, const int* i, const int* j, double coulomb14, double lj14) {
+    std::vector<std::pair<int, int> > bonds(n);
+    for (int k = 0; k < n; k++) bonds[k] = std::make_pair(i[k], j[k]);
+    ((NonbondedForce*) f)->createExceptionsFromBonds(bonds, coulomb14, lj14);
+}
+int omm_nonbonded_num_exceptions(void* f) { return ((NonbondedForce*) f)->getNumExceptions(); }
+void omm_nonbonded_get_exceptions(void* f, int* i, int* j, double* qq, double* sigma, double* eps) {
+    NonbondedForce* nb = (NonbondedForce*) f;
+    for (int k = 0; k < nb->getNumExceptions(); k++) nb->getExceptionParameters(k, i[k], j[k], qq[k], sigma[k], eps[k]);
+}
+void omm_force_destroy(void* f) { delete (Force*) f; }
 void omm_nonbonded_set_method(void* f, int method, double cutoff, double ewaldTol) {
     NonbondedForce* nb = (NonbondedForce*) f;
     nb->setNonbondedMethod((NonbondedForce::NonbondedMethod) method);
