@@ -67,6 +67,7 @@ struct b200md_ctx {
     int cmFreq = 0;
     double boxA[3] = {0, 0, 0}, boxB[3] = {0, 0, 0}, boxC[3] = {0, 0, 0};
     bool haveBox = false;
+    bool haveOrigin = false;
     double padFrac = 0.10;
     // ---- device state ----
     DevBuf<float4> posq, velm, sposq, sshift, refPos, atomShift, blockCenter, blockHalf;
@@ -76,10 +77,10 @@ struct b200md_ctx {
     DevBuf<int> sorig, sortedOf, cellRank, cellCount, cellFill, atomCell, tmpSorted, tileI, tileJ, tileMask, counters, exclStart, exclList;
     DevBuf<unsigned int> maskPool;
     DevBuf<unsigned long long> stepCounter;
-    DevBuf<float> grid, eterm;
+    DevBuf<double> grid, eterm;
     DevBuf<long long> gridFixed;
-    DevBuf<float2> cgrid;
-    DevBuf<float2> tw[3];
+    DevBuf<double2> cgrid;
+    DevBuf<double2> tw[3];
     DevBuf<double> moduli[3];
     DevBuf<int2> bondAtoms, excAtoms; DevBuf<double2> bondParams, angleParams;
     DevBuf<int4> angleAtoms, torsionAtoms, unitAtoms; DevBuf<double4> torsionParams, excParams;
@@ -97,9 +98,11 @@ struct b200md_ctx {
     // ---- stats ----
     int64_t forceEvals = 0, kernelLaunches = 0;
     // ---- graph ----
-    cudaGraphExec_t stepGraph = nullptr;
+    cudaGraphExec_t stepGraph = nullptr;      // one MD step
+    cudaGraphExec_t multiGraph = nullptr;     // graphSteps MD steps in one launch (host launch cost amortised)
     bool graphValid = false;
     bool useGraph = true;
+    int graphSteps = 8;
     int stepLaunches = 0;
     // ---- multi-GPU ----
     void* comm = nullptr;
@@ -137,6 +140,8 @@ extern "C" int b200md_create(b200md_ctx** out, int device, int natoms) {
         if (pf) c->padFrac = atof(pf);
         const char* ug = getenv("B200MD_USE_GRAPH");
         if (ug) c->useGraph = atoi(ug) != 0;
+        const char* gs = getenv("B200MD_GRAPH_STEPS");
+        if (gs) c->graphSteps = std::max(1, atoi(gs));
         *out = c;
         return 0;
     } catch (std::exception& e) { g_create_error = e.what(); return -1; }
@@ -147,6 +152,7 @@ extern "C" void b200md_destroy(b200md_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     if (ctx->stepGraph) cudaGraphExecDestroy(ctx->stepGraph);
+    if (ctx->multiGraph) cudaGraphExecDestroy(ctx->multiGraph);
     if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -439,12 +445,12 @@ static std::vector<double> bspline_moduli(int n) {
     return mod;
 }
 
-static void make_fft_plan(int n, FftPlanDev& plan, DevBuf<float2>& tw) {
+static void make_fft_plan(int n, FftPlanDev& plan, DevBuf<double2>& tw) {
     plan.n = n;
     if (!fft_make_radices(n, plan.radix, &plan.nstages))
         throw std::runtime_error("B200 platform: PME grid dimension " + std::to_string(n) + " has a prime factor > 13; choose a dimension that factors into radices <= 16");
-    std::vector<float2> t(n);
-    for (int k = 0; k < n; k++) { double a = -2.0*M_PI*k/n; t[k] = make_float2((float) std::cos(a), (float) std::sin(a)); }
+    std::vector<double2> t(n);
+    for (int k = 0; k < n; k++) { double a = -2.0*M_PI*k/n; t[k] = make_double2(std::cos(a), std::sin(a)); }
     tw.upload(t);
     plan.tw = tw.p;
 }
@@ -620,6 +626,15 @@ extern "C" int b200md_set_positions(b200md_ctx* ctx, const double* x) {
     ctx->hbuf4.resize(ctx->npad);
     for (int i = 0; i < N; i++) ctx->hbuf4[i] = make_float4((float) x[3*i], (float) x[3*i+1], (float) x[3*i+2], (float) (ctx->charge[i]*sk));
     for (int i = N; i < ctx->npad; i++) ctx->hbuf4[i] = make_float4(0, 0, 0, 0);
+    if (!ctx->haveOrigin) {
+        // primary-cell origin = lower corner of the structure (first call only; later calls keep it so that the step
+        // graph's kernel parameters stay valid)
+        double lo[3] = {1e300, 1e300, 1e300};
+        for (int i = 0; i < N; i++) for (int k = 0; k < 3; k++) lo[k] = std::min(lo[k], x[3*i+k]);
+        for (int k = 0; k < 3; k++) ctx->nb.origin[k] = std::isfinite(lo[k]) ? lo[k] : 0.0;
+        ctx->haveOrigin = true;
+        invalidate_graph(ctx);
+    }
     CUDA_CHECK(cudaMemcpyAsync(ctx->posq.p, ctx->hbuf4.data(), sizeof(float4)*ctx->npad, cudaMemcpyHostToDevice, ctx->stream));
     const int one = 1;
     CUDA_CHECK(cudaMemcpyAsync(&ctx->counters.p[2], &one, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
@@ -809,7 +824,9 @@ extern "C" int b200md_set_integrator(b200md_ctx* ctx, int kind, double dt, doubl
 }
 
 static int enqueue_step(b200md_ctx* c) {
-    int launches = enqueue_forces(c, B200MD_TERM_ALL, false);
+    int launches = 0;
+    if (c->cmFreq == 1) { launch_remove_cm(c->nb, c->cmScratch.p, c->stream); launches += 2; }   // every step: part of the graph
+    launches += enqueue_forces(c, B200MD_TERM_ALL, false);
     launch_integrate(c->nb, c->units, c->integ, c->stream); launches += 2;
     return launches;
 }
@@ -824,33 +841,51 @@ extern "C" int b200md_integrate_only(b200md_ctx* ctx) {
     API_END(ctx)
 }
 
+static cudaGraphExec_t capture_steps(b200md_ctx* c, int nsteps, int* launches) {
+    cudaGraph_t g;
+    cudaGraphExec_t exec = nullptr;
+    CUDA_CHECK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+    int l = 0;
+    try { for (int k = 0; k < nsteps; k++) l += enqueue_step(c); } catch (...) { cudaStreamEndCapture(c->stream, &g); throw; }
+    CUDA_CHECK(cudaStreamEndCapture(c->stream, &g));
+    CUDA_CHECK(cudaGraphInstantiate(&exec, g, 0));
+    cudaGraphDestroy(g);
+    *launches = l;
+    return exec;
+}
+
 extern "C" int b200md_step(b200md_ctx* ctx, int nsteps) {
     API_BEGIN(ctx)
     require(ctx->finalized && ctx->haveIntegrator, "step before finalize / set_integrator");
     b200md_ctx* c = ctx;
-    for (int i = 0; i < nsteps; i++) {
-        if (c->cmFreq > 0 && c->stepCount % c->cmFreq == 0) { launch_remove_cm(c->nb, c->cmScratch.p, c->stream); c->kernelLaunches += 2; }
+    int remaining = nsteps;
+    while (remaining > 0) {
+        if (c->cmFreq > 1 && c->stepCount % c->cmFreq == 0) { launch_remove_cm(c->nb, c->cmScratch.p, c->stream); c->kernelLaunches += 2; }
+        int done = 1;
         if (c->useGraph) {
             if (!c->graphValid) {
                 if (c->stepGraph) { cudaGraphExecDestroy(c->stepGraph); c->stepGraph = nullptr; }
-                cudaGraph_t g;
-                CUDA_CHECK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
-                int l = 0;
-                try { l = enqueue_step(c); } catch (...) { cudaStreamEndCapture(c->stream, &g); throw; }
-                CUDA_CHECK(cudaStreamEndCapture(c->stream, &g));
-                CUDA_CHECK(cudaGraphInstantiate(&c->stepGraph, g, 0));
-                cudaGraphDestroy(g);
-                c->stepLaunches = l;
+                if (c->multiGraph) { cudaGraphExecDestroy(c->multiGraph); c->multiGraph = nullptr; }
+                c->stepGraph = capture_steps(c, 1, &c->stepLaunches);
+                if (c->graphSteps > 1) { int l; c->multiGraph = capture_steps(c, c->graphSteps, &l); }
                 c->graphValid = true;
             }
-            CUDA_CHECK(cudaGraphLaunch(c->stepGraph, c->stream));
-            c->kernelLaunches += c->stepLaunches;
+            // the multi-step graph may not straddle a centre-of-mass removal that lives outside the graph
+            int untilCm = (c->cmFreq > 1) ? (int) (c->cmFreq - c->stepCount % c->cmFreq) : remaining;
+            if (c->multiGraph && remaining >= c->graphSteps && untilCm >= c->graphSteps) {
+                CUDA_CHECK(cudaGraphLaunch(c->multiGraph, c->stream));
+                done = c->graphSteps;
+            }
+            else
+                CUDA_CHECK(cudaGraphLaunch(c->stepGraph, c->stream));
+            c->kernelLaunches += (int64_t) c->stepLaunches*done;
         }
         else
             c->kernelLaunches += enqueue_step(c);
-        c->forceEvals++;
-        c->stepCount++;
-        c->time += c->dt;
+        c->forceEvals += done;
+        c->stepCount += done;
+        c->time += c->dt*done;
+        remaining -= done;
     }
     CUDA_CHECK(cudaGetLastError());
     API_END(ctx)
@@ -974,7 +1009,7 @@ static int fft_standalone(int device, int nx, int ny, int nz, const float* in, f
     try {
         CUDA_CHECK(cudaSetDevice(device));
         PmeDev p{}; p.nx = nx; p.ny = ny; p.nz = nz; p.nzc = nz/2 + 1;
-        DevBuf<float> grid; DevBuf<float2> cg; DevBuf<float2> tw[3];
+        DevBuf<double> grid; DevBuf<double2> cg; DevBuf<double2> tw[3];
         grid.alloc((size_t) nx*ny*nz); cg.alloc((size_t) nx*ny*p.nzc);
         p.grid = grid.p; p.cgrid = cg.p;
         const int n[3] = {nx, ny, nz};
@@ -982,17 +1017,26 @@ static int fft_standalone(int device, int nx, int ny, int nz, const float* in, f
         int maxSmem = 0;
         cudaDeviceGetAttribute(&maxSmem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
         require(fft_plane_smem_bytes(ny, nz) <= (size_t) maxSmem && fft_line_smem_bytes(nx) <= (size_t) maxSmem, "grid too large for shared memory");
+        // host API is fp32 (TestCudaFFT3D-style checks); the device transform is double
         if (forward) {
-            CUDA_CHECK(cudaMemcpy(grid.p, in, sizeof(float)*grid.n, cudaMemcpyHostToDevice));
+            std::vector<double> h(grid.n);
+            for (size_t i = 0; i < grid.n; i++) h[i] = in[i];
+            CUDA_CHECK(cudaMemcpy(grid.p, h.data(), sizeof(double)*grid.n, cudaMemcpyHostToDevice));
             launch_fft3d_r2c(p, 0);
             CUDA_CHECK(cudaDeviceSynchronize());
-            CUDA_CHECK(cudaMemcpy(out, cg.p, sizeof(float2)*cg.n, cudaMemcpyDeviceToHost));
+            std::vector<double> o(2*cg.n);
+            CUDA_CHECK(cudaMemcpy(o.data(), cg.p, sizeof(double2)*cg.n, cudaMemcpyDeviceToHost));
+            for (size_t i = 0; i < 2*cg.n; i++) out[i] = (float) o[i];
         }
         else {
-            CUDA_CHECK(cudaMemcpy(cg.p, in, sizeof(float2)*cg.n, cudaMemcpyHostToDevice));
+            std::vector<double> h(2*cg.n);
+            for (size_t i = 0; i < 2*cg.n; i++) h[i] = in[i];
+            CUDA_CHECK(cudaMemcpy(cg.p, h.data(), sizeof(double2)*cg.n, cudaMemcpyHostToDevice));
             launch_fft3d_c2r(p, 0);
             CUDA_CHECK(cudaDeviceSynchronize());
-            CUDA_CHECK(cudaMemcpy(out, grid.p, sizeof(float)*grid.n, cudaMemcpyDeviceToHost));
+            std::vector<double> o(grid.n);
+            CUDA_CHECK(cudaMemcpy(o.data(), grid.p, sizeof(double)*grid.n, cudaMemcpyDeviceToHost));
+            for (size_t i = 0; i < grid.n; i++) out[i] = (float) o[i];
         }
         return 0;
     } catch (std::exception& e) { g_create_error = e.what(); return -1; }

@@ -30,7 +30,7 @@ struct FftPlanDev {      // 1-D mixed-radix Stockham plan for one grid dimension
     int n;
     int nstages;
     int radix[B200MD_MAX_FFT_STAGES];
-    const float2* tw;    // tw[k] = exp(-2 pi i k / n), k < n
+    const double2* tw;   // tw[k] = exp(-2 pi i k / n), k < n
 };
 
 // Everything the force kernels need, passed by value.
@@ -80,16 +80,19 @@ struct NbDev {
     float halfPad2;              // (padding/2)^2
     // multi-GPU sharding of the tile list / PME atoms
     int rank, world;
+    // origin of the primary periodic cell used for binning (chosen at set_positions so that a structure centred anywhere,
+    // e.g. a PDB centred on 0, is binned WITHOUT lattice shifts: a shift costs one fp32 rounding of the coordinate)
+    double origin[3];
 };
 
 enum { EN_NB = 0, EN_RECIP = 1, EN_BOND = 2, EN_ANGLE = 3, EN_TORSION = 4, EN_EXC = 5, EN_KE = 6, B200MD_NUM_ENERGY = 8 };
 
 struct PmeDev {
     int nx, ny, nz, nzc;
-    float* grid;                 // real [nx][ny][nz] (output of the inverse transform, input of the gather)
+    double* grid;                // real [nx][ny][nz] (output of the inverse transform, input of the gather)
     long long* gridFixed;        // real [nx][ny][nz], 2^32 fixed point: deterministic charge spreading (pme.cc:78-89 option)
-    float2* cgrid;               // complex [nx][ny][nzc]
-    float* eterm;                // [nx][ny][nzc] influence function (no ONE_4PI_EPS0: charges carry sqrt of it)
+    double2* cgrid;              // complex [nx][ny][nzc]
+    double* eterm;               // [nx][ny][nzc] influence function (no ONE_4PI_EPS0: charges carry sqrt of it)
     const double* moduli[3];
     FftPlanDev plan[3];          // x, y, z
     double alpha;

@@ -333,7 +333,7 @@ void launch_kinetic_energy(const NbDev& nb, const UnitDev& units, const IntegDev
 }
 
 // CMMotionRemover (ReferenceKernels.cpp RemoveCMMotion): subtract the centre-of-mass velocity.
-__global__ void k_cm_sum(NbDev nb, double* scratch) {
+__global__ void __launch_bounds__(256) k_cm_sum(NbDev nb, double* scratch) {
     const int a = blockIdx.x*blockDim.x + threadIdx.x;
     double px = 0, py = 0, pz = 0, m = 0;
     if (a < nb.natoms) {
@@ -344,8 +344,13 @@ __global__ void k_cm_sum(NbDev nb, double* scratch) {
         px += __shfl_xor_sync(0xffffffffu, px, off); py += __shfl_xor_sync(0xffffffffu, py, off);
         pz += __shfl_xor_sync(0xffffffffu, pz, off); m += __shfl_xor_sync(0xffffffffu, m, off);
     }
-    if ((threadIdx.x & 31) == 0 && m != 0.0) {
-        atomicAdd(&scratch[0], px); atomicAdd(&scratch[1], py); atomicAdd(&scratch[2], pz); atomicAdd(&scratch[3], m);
+    __shared__ double red[8][4];
+    if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5][0] = px; red[threadIdx.x >> 5][1] = py; red[threadIdx.x >> 5][2] = pz; red[threadIdx.x >> 5][3] = m; }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        double t = 0;
+        for (int w = 0; w < 8; w++) t += red[w][threadIdx.x];
+        atomicAdd(&scratch[threadIdx.x], t);
     }
 }
 __global__ void k_cm_apply(NbDev nb, double* scratch) {

@@ -80,9 +80,10 @@ __global__ void k_bin_atoms(NbDev nb) {
     if (nb.box.periodic) {
         const double* R = nb.box.recip;
         double f[3];
-        f[0] = p.x*R[0] + p.y*R[3] + p.z*R[6];
-        f[1] = p.x*R[1] + p.y*R[4] + p.z*R[7];
-        f[2] = p.x*R[2] + p.y*R[5] + p.z*R[8];
+        const double px = p.x - nb.origin[0], py = p.y - nb.origin[1], pz = p.z - nb.origin[2];
+        f[0] = px*R[0] + py*R[3] + pz*R[6];
+        f[1] = px*R[1] + py*R[4] + pz*R[7];
+        f[2] = px*R[2] + py*R[5] + pz*R[8];
         int c[3];
         float fl[3];
         for (int d = 0; d < 3; d++) {
@@ -415,7 +416,8 @@ __device__ __forceinline__ void pair_tiles(const NbDev& nb, float& energy) {
             const float r2raw = d.x*d.x + d.y*d.y + d.z*d.z;
             const bool valid = ((mask >> slot) & 1u) && r2raw < nb.cutoff2;
             const float r2 = valid ? r2raw : 1.0f;
-            const float invR = rsqrtf(r2);
+            float invR = rsqrtf(r2);
+            invR = invR*(1.5f - 0.5f*r2*invR*invR);      // one Newton step: MUFU.RSQ is ~2 ulp, and F ~ invR^3
             const float invR2 = invR*invR;
             const float qq = pi.w*pj.w;
             float dEdR, e = 0.f;

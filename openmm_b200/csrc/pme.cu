@@ -59,7 +59,9 @@ __global__ void __launch_bounds__(128) k_pme_spread(NbDev nb, PmeDev pme) {
     const int per = (nb.natoms + nb.world - 1)/nb.world;
     const int s = nb.rank*per + blockIdx.x*blockDim.x + threadIdx.x;
     if (s >= min(nb.natoms, (nb.rank+1)*per)) return;
-    const float4 p = nb.sposq[s];
+    // the user-order (never lattice-shifted) coordinate: the fractional position is formed in double, so the grid
+    // index/fraction is exact for fp32 inputs wherever the atom sits relative to the primary cell
+    const float4 p = nb.posq[nb.sorig[s]];
     if (p.w == 0.f) return;
     int idx[3];
     float fr[3];
@@ -91,7 +93,7 @@ __global__ void __launch_bounds__(128) k_pme_gather(NbDev nb, PmeDev pme) {
     const int per = (nb.natoms + nb.world - 1)/nb.world;
     const int s = nb.rank*per + blockIdx.x*blockDim.x + threadIdx.x;
     if (s >= min(nb.natoms, (nb.rank+1)*per)) return;
-    const float4 p = nb.sposq[s];
+    const float4 p = nb.posq[nb.sorig[s]];
     if (p.w == 0.f) return;
     int idx[3];
     float fr[3];
@@ -100,19 +102,19 @@ __global__ void __launch_bounds__(128) k_pme_gather(NbDev nb, PmeDev pme) {
     bspline(fr[0], tx, dx);
     bspline(fr[1], ty, dy);
     bspline(fr[2], tz, dz);
-    float fx = 0.f, fy = 0.f, fz = 0.f;
+    double fx = 0.0, fy = 0.0, fz = 0.0;
 #pragma unroll
     for (int ix = 0; ix < ORDER; ix++) {
         int xi = idx[0] + ix; if (xi >= pme.nx) xi -= pme.nx;
 #pragma unroll
         for (int iy = 0; iy < ORDER; iy++) {
             int yi = idx[1] + iy; if (yi >= pme.ny) yi -= pme.ny;
-            const float* row = pme.grid + ((size_t) xi*pme.ny + yi)*pme.nz;
-            float sz = 0.f, sdz = 0.f;
+            const double* row = pme.grid + ((size_t) xi*pme.ny + yi)*pme.nz;
+            double sz = 0.0, sdz = 0.0;
 #pragma unroll
             for (int iz = 0; iz < ORDER; iz++) {
                 int zi = idx[2] + iz; if (zi >= pme.nz) zi -= pme.nz;
-                const float g = __ldg(row + zi);
+                const double g = __ldg(row + zi);
                 sz += tz[iz]*g;
                 sdz += dz[iz]*g;
             }
@@ -123,15 +125,15 @@ __global__ void __launch_bounds__(128) k_pme_gather(NbDev nb, PmeDev pme) {
     }
     // ReferencePME.cpp:708-711 (triclinic-aware)
     const double* R = nb.box.recip;
-    const float q = p.w;
-    const float gx = fx*pme.nx, gy = fy*pme.ny, gz = fz*pme.nz;
-    const float Fx = -q*(gx*(float) R[0]);
-    const float Fy = -q*(gx*(float) R[3] + gy*(float) R[4]);
-    const float Fz = -q*(gx*(float) R[6] + gy*(float) R[7] + gz*(float) R[8]);
+    const double q = p.w;
+    const double gx = fx*pme.nx, gy = fy*pme.ny, gz = fz*pme.nz;
+    const double Fx = -q*(gx*R[0]);
+    const double Fy = -q*(gx*R[3] + gy*R[4]);
+    const double Fz = -q*(gx*R[6] + gy*R[7] + gz*R[8]);
     const int a = nb.sorig[s];
-    atomicAdd((unsigned long long*) &nb.force[a], (unsigned long long) __float2ll_rn(Fx*4294967296.0f));
-    atomicAdd((unsigned long long*) &nb.force[a + nb.npad], (unsigned long long) __float2ll_rn(Fy*4294967296.0f));
-    atomicAdd((unsigned long long*) &nb.force[a + 2*nb.npad], (unsigned long long) __float2ll_rn(Fz*4294967296.0f));
+    atomicAdd((unsigned long long*) &nb.force[a], (unsigned long long) __double2ll_rn(Fx*B200MD_FORCE_SCALE));
+    atomicAdd((unsigned long long*) &nb.force[a + nb.npad], (unsigned long long) __double2ll_rn(Fy*B200MD_FORCE_SCALE));
+    atomicAdd((unsigned long long*) &nb.force[a + 2*nb.npad], (unsigned long long) __double2ll_rn(Fz*B200MD_FORCE_SCALE));
 }
 
 // influence function on the half-complex grid (pme_reciprocal_convolution, ReferencePME.cpp:409-514), computed in
@@ -144,7 +146,7 @@ __global__ void k_pme_eterm(NbDev nb, PmeDev pme) {
     const int kz = (int) (i % pme.nzc);
     const int ky = (int) ((i / pme.nzc) % pme.ny);
     const int kx = (int) (i / ((size_t) pme.nzc*pme.ny));
-    if (kx == 0 && ky == 0 && kz == 0) { pme.eterm[i] = 0.f; return; }
+    if (kx == 0 && ky == 0 && kz == 0) { pme.eterm[i] = 0.0; return; }
     const double* R = nb.box.recip;
     const double mx = (kx < (pme.nx+1)/2) ? kx : kx - pme.nx;
     const double my = (ky < (pme.ny+1)/2) ? ky : ky - pme.ny;
@@ -156,7 +158,7 @@ __global__ void k_pme_eterm(NbDev nb, PmeDev pme) {
     const double pi = 3.14159265358979323846;
     const double factor = pi*pi/(pme.alpha*pme.alpha);
     const double denom = m2*pi*nb.box.volume*pme.moduli[0][kx]*pme.moduli[1][ky]*pme.moduli[2][kz];
-    pme.eterm[i] = (float) (exp(-factor*m2)/denom);
+    pme.eterm[i] = exp(-factor*m2)/denom;
 }
 
 void launch_pme_eterm(const NbDev& nb, const PmeDev& pme, cudaStream_t s) {
