@@ -55,6 +55,8 @@ struct b200md_ctx {
     bool finalized = false;
     std::string err;
     cudaStream_t stream = nullptr;
+    cudaStream_t stream2 = nullptr;     // body capture of conditional graph nodes
+    bool useCond = true;
     // ---- host copy of the system definition ----
     std::vector<double> mass, charge, sigma, epsilon;
     b200md_nonbonded_desc nbdesc{};
@@ -77,10 +79,10 @@ struct b200md_ctx {
     DevBuf<int> sorig, sortedOf, cellRank, cellCount, cellFill, atomCell, tmpSorted, tileI, tileJ, tileMask, counters, exclStart, exclList;
     DevBuf<unsigned int> maskPool;
     DevBuf<unsigned long long> stepCounter;
-    DevBuf<double> grid, eterm;
+    DevBuf<real> grid, eterm;
     DevBuf<long long> gridFixed;
-    DevBuf<double2> cgrid;
-    DevBuf<double2> tw[3];
+    DevBuf<real2> cgrid;
+    DevBuf<real2> tw[3];
     DevBuf<double> moduli[3];
     DevBuf<int2> bondAtoms, excAtoms; DevBuf<double2> bondParams, angleParams;
     DevBuf<int4> angleAtoms, torsionAtoms, unitAtoms; DevBuf<double4> torsionParams, excParams;
@@ -134,6 +136,8 @@ extern "C" int b200md_create(b200md_ctx** out, int device, int natoms) {
         c->npad = ((natoms + 31)/32)*32;
         c->nblocks = c->npad/32;
         CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+        if (getenv("B200MD_NO_COND")) c->useCond = false;
         c->mass.assign(natoms, 1.0);
         c->charge.assign(natoms, 0.0); c->sigma.assign(natoms, 1.0); c->epsilon.assign(natoms, 0.0);
         const char* pf = getenv("B200MD_PAD_FRACTION");
@@ -155,6 +159,7 @@ extern "C" void b200md_destroy(b200md_ctx* ctx) {
     if (ctx->multiGraph) cudaGraphExecDestroy(ctx->multiGraph);
     if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
     delete ctx;
 }
 
@@ -445,12 +450,12 @@ static std::vector<double> bspline_moduli(int n) {
     return mod;
 }
 
-static void make_fft_plan(int n, FftPlanDev& plan, DevBuf<double2>& tw) {
+static void make_fft_plan(int n, FftPlanDev& plan, DevBuf<real2>& tw) {
     plan.n = n;
     if (!fft_make_radices(n, plan.radix, &plan.nstages))
         throw std::runtime_error("B200 platform: PME grid dimension " + std::to_string(n) + " has a prime factor > 13; choose a dimension that factors into radices <= 16");
-    std::vector<double2> t(n);
-    for (int k = 0; k < n; k++) { double a = -2.0*M_PI*k/n; t[k] = make_double2(std::cos(a), std::sin(a)); }
+    std::vector<real2> t(n);
+    for (int k = 0; k < n; k++) { double a = -2.0*M_PI*k/n; t[k].x = (real) std::cos(a); t[k].y = (real) std::sin(a); }
     tw.upload(t);
     plan.tw = tw.p;
 }
@@ -738,9 +743,39 @@ static int enqueue_forces(b200md_ctx* c, int terms, bool energy) {
     const bool direct = (terms & B200MD_TERM_NB_DIRECT) && c->haveNb;
     const bool recip = (terms & B200MD_TERM_NB_RECIP) && c->haveNb && c->nb.method == B200MD_NB_PME;
     if (direct || recip) {
-        launch_check_displacement(c->nb, s); launches++;
-        launch_list_build(c->nb, s); launches += list_build_launch_count();
-        launch_gather_sorted(c->nb, s); launches++;
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        cudaGraph_t graph = nullptr;
+        const cudaGraphNode_t* deps = nullptr;
+        size_t ndeps = 0;
+        CUDA_CHECK(cudaStreamGetCaptureInfo_v2(s, &cap, nullptr, &graph, &deps, &ndeps));
+        if (cap == cudaStreamCaptureStatusActive && c->useCond) {
+            // the rebuild kernels live in an IF node of the step graph: zero launches on the (usual) steps without a rebuild
+            cudaGraphConditionalHandle h;
+            CUDA_CHECK(cudaGraphConditionalHandleCreate(&h, graph, 0, cudaGraphCondAssignDefault));
+            c->nb.condHandle = (unsigned long long) h;
+            launch_check_displacement(c->nb, s); launches++;
+            CUDA_CHECK(cudaStreamGetCaptureInfo_v2(s, &cap, nullptr, &graph, &deps, &ndeps));
+            cudaGraphNodeParams np = {cudaGraphNodeTypeConditional};
+            np.type = cudaGraphNodeTypeConditional;
+            np.conditional.handle = h;
+            np.conditional.type = cudaGraphCondTypeIf;
+            np.conditional.size = 1;
+            cudaGraphNode_t node;
+            CUDA_CHECK(cudaGraphAddNode(&node, graph, deps, ndeps, &np));
+            cudaGraph_t body = np.conditional.phGraph_out[0];
+            NbDev nbBody = c->nb;
+            CUDA_CHECK(cudaStreamBeginCaptureToGraph(c->stream2, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
+            launch_list_build(nbBody, c->stream2);
+            cudaGraph_t tmp;
+            CUDA_CHECK(cudaStreamEndCapture(c->stream2, &tmp));
+            CUDA_CHECK(cudaStreamUpdateCaptureDependencies(s, &node, 1, cudaStreamSetCaptureDependencies));
+            c->nb.condHandle = 0ull;
+        }
+        else {
+            c->nb.condHandle = 0ull;
+            launch_check_displacement(c->nb, s); launches++;
+            launch_list_build(c->nb, s); launches += list_build_launch_count();
+        }
     }
     if (direct) { launch_pair(c->nb, energy, s); launches++; }
     if (recip) {
@@ -749,7 +784,7 @@ static int enqueue_forces(b200md_ctx* c, int terms, bool energy) {
             int rc = g_nccl.AllReduce(c->gridFixed.p, c->gridFixed.p, (size_t) c->pme.nx*c->pme.ny*c->pme.nz, NCCL_INT64, NCCL_SUM, c->comm, s);
             if (rc != 0) throw std::runtime_error("ncclAllReduce(grid) failed");
         }
-        launch_pme_fft_conv(c->nb, c->pme, energy && c->rank == 0, s); launches += 3;
+        launch_pme_fft_conv(c->nb, c->pme, energy && c->rank == 0, s); launches += pme_fft_launch_count(c->pme);
         launch_pme_gather(c->nb, c->pme, s); launches++;
     }
     int bterms = terms & (B200MD_TERM_BONDS | B200MD_TERM_ANGLES | B200MD_TERM_TORSIONS);
@@ -932,6 +967,12 @@ extern "C" int b200md_comm_init(b200md_ctx* ctx, int rank, int world, const void
     int rc = g_nccl.CommInitRank(&ctx->comm, world, uid, rank);
     if (rc != 0) throw std::runtime_error(std::string("ncclCommInitRank failed: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?"));
     ctx->rank = rank; ctx->world = world;
+    // one eager collective: NCCL sets its transports up lazily on the first call, which must not happen inside a
+    // CUDA-graph capture (the step graph contains the force all-reduce)
+    DevBuf<long long> warm; warm.alloc(64); warm.zero();
+    rc = g_nccl.AllReduce(warm.p, warm.p, 64, NCCL_INT64, NCCL_SUM, ctx->comm, ctx->stream);
+    if (rc != 0) throw std::runtime_error("ncclAllReduce warm-up failed");
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     API_END(ctx)
 }
 
@@ -1009,7 +1050,7 @@ static int fft_standalone(int device, int nx, int ny, int nz, const float* in, f
     try {
         CUDA_CHECK(cudaSetDevice(device));
         PmeDev p{}; p.nx = nx; p.ny = ny; p.nz = nz; p.nzc = nz/2 + 1;
-        DevBuf<double> grid; DevBuf<double2> cg; DevBuf<double2> tw[3];
+        DevBuf<real> grid; DevBuf<real2> cg; DevBuf<real2> tw[3];
         grid.alloc((size_t) nx*ny*nz); cg.alloc((size_t) nx*ny*p.nzc);
         p.grid = grid.p; p.cgrid = cg.p;
         const int n[3] = {nx, ny, nz};
@@ -1019,23 +1060,23 @@ static int fft_standalone(int device, int nx, int ny, int nz, const float* in, f
         require(fft_plane_smem_bytes(ny, nz) <= (size_t) maxSmem && fft_line_smem_bytes(nx) <= (size_t) maxSmem, "grid too large for shared memory");
         // host API is fp32 (TestCudaFFT3D-style checks); the device transform is double
         if (forward) {
-            std::vector<double> h(grid.n);
-            for (size_t i = 0; i < grid.n; i++) h[i] = in[i];
-            CUDA_CHECK(cudaMemcpy(grid.p, h.data(), sizeof(double)*grid.n, cudaMemcpyHostToDevice));
+            std::vector<real> h(grid.n);
+            for (size_t i = 0; i < grid.n; i++) h[i] = (real) in[i];
+            CUDA_CHECK(cudaMemcpy(grid.p, h.data(), sizeof(real)*grid.n, cudaMemcpyHostToDevice));
             launch_fft3d_r2c(p, 0);
             CUDA_CHECK(cudaDeviceSynchronize());
-            std::vector<double> o(2*cg.n);
-            CUDA_CHECK(cudaMemcpy(o.data(), cg.p, sizeof(double2)*cg.n, cudaMemcpyDeviceToHost));
+            std::vector<real> o(2*cg.n);
+            CUDA_CHECK(cudaMemcpy(o.data(), cg.p, sizeof(real2)*cg.n, cudaMemcpyDeviceToHost));
             for (size_t i = 0; i < 2*cg.n; i++) out[i] = (float) o[i];
         }
         else {
-            std::vector<double> h(2*cg.n);
-            for (size_t i = 0; i < 2*cg.n; i++) h[i] = in[i];
-            CUDA_CHECK(cudaMemcpy(cg.p, h.data(), sizeof(double2)*cg.n, cudaMemcpyHostToDevice));
+            std::vector<real> h(2*cg.n);
+            for (size_t i = 0; i < 2*cg.n; i++) h[i] = (real) in[i];
+            CUDA_CHECK(cudaMemcpy(cg.p, h.data(), sizeof(real2)*cg.n, cudaMemcpyHostToDevice));
             launch_fft3d_c2r(p, 0);
             CUDA_CHECK(cudaDeviceSynchronize());
-            std::vector<double> o(grid.n);
-            CUDA_CHECK(cudaMemcpy(o.data(), grid.p, sizeof(double)*grid.n, cudaMemcpyDeviceToHost));
+            std::vector<real> o(grid.n);
+            CUDA_CHECK(cudaMemcpy(o.data(), grid.p, sizeof(real)*grid.n, cudaMemcpyDeviceToHost));
             for (size_t i = 0; i < grid.n; i++) out[i] = (float) o[i];
         }
         return 0;

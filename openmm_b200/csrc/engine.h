@@ -26,11 +26,17 @@ struct BoxDev {
     double volume;
 };
 
+// precision of the spectral pipeline (charge grid -> FFT -> convolution -> potential grid); the input grid is int64
+// fixed point either way.  fp32 measured sufficient: the 1e-3 level recip force errors seen on ApoA1 came from lattice-
+// shifted fp32 coordinates, not from the transform (identical errors with a double pipeline).
+typedef float real;
+typedef float2 real2;
+
 struct FftPlanDev {      // 1-D mixed-radix Stockham plan for one grid dimension
     int n;
     int nstages;
     int radix[B200MD_MAX_FFT_STAGES];
-    const double2* tw;   // tw[k] = exp(-2 pi i k / n), k < n
+    const real2* tw;     // tw[k] = exp(-2 pi i k / n), k < n
 };
 
 // Everything the force kernels need, passed by value.
@@ -83,16 +89,18 @@ struct NbDev {
     // origin of the primary periodic cell used for binning (chosen at set_positions so that a structure centred anywhere,
     // e.g. a PDB centred on 0, is binned WITHOUT lattice shifts: a shift costs one fp32 rounding of the coordinate)
     double origin[3];
+    // CUDA-graph conditional node that holds the list-rebuild kernels (0 = none: rebuild kernels are gated on counters[2])
+    unsigned long long condHandle;
 };
 
 enum { EN_NB = 0, EN_RECIP = 1, EN_BOND = 2, EN_ANGLE = 3, EN_TORSION = 4, EN_EXC = 5, EN_KE = 6, B200MD_NUM_ENERGY = 8 };
 
 struct PmeDev {
     int nx, ny, nz, nzc;
-    double* grid;                // real [nx][ny][nz] (output of the inverse transform, input of the gather)
+    real* grid;                  // real [nx][ny][nz] (output of the inverse transform, input of the gather)
     long long* gridFixed;        // real [nx][ny][nz], 2^32 fixed point: deterministic charge spreading (pme.cc:78-89 option)
-    double2* cgrid;              // complex [nx][ny][nzc]
-    double* eterm;               // [nx][ny][nzc] influence function (no ONE_4PI_EPS0: charges carry sqrt of it)
+    real2* cgrid;                // complex [nx][ny][nzc]
+    real* eterm;                 // [nx][ny][nzc] influence function (no ONE_4PI_EPS0: charges carry sqrt of it)
     const double* moduli[3];
     FftPlanDev plan[3];          // x, y, z
     double alpha;
@@ -128,7 +136,6 @@ struct IntegDev {
 // ---- launchers (defined in the .cu files) ----
 void launch_check_displacement(const NbDev& nb, cudaStream_t s);
 void launch_list_build(const NbDev& nb, cudaStream_t s);          // all list kernels, each gated on counters[2]
-void launch_gather_sorted(const NbDev& nb, cudaStream_t s);
 void launch_pair(const NbDev& nb, bool energy, cudaStream_t s);
 void launch_count_pairs(const NbDev& nb, cudaStream_t s);
 int  list_build_launch_count();
@@ -142,6 +149,7 @@ void launch_fft3d_c2r(const PmeDev& pme, cudaStream_t s);         // cgrid -> gr
 size_t fft_plane_smem_bytes(int ny, int nz);
 size_t fft_line_smem_bytes(int nx);
 bool fft_make_radices(int n, int* radix, int* nstages);
+int pme_fft_launch_count(const PmeDev& pme);
 
 void launch_bonded(const NbDev& nb, const BondedDev& bd, int terms, bool energy, cudaStream_t s);
 

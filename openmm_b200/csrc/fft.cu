@@ -23,69 +23,118 @@
 // rate is ample for 1e5..1e6 grid points and these kernels are latency bound.
 #include "engine.h"
 #include <math.h>
+#include <stdlib.h>
 
 
-// Thread layout of every FFT kernel: blockDim = (n, LY): threadIdx.x = position p inside a line, threadIdx.y strides
-// over the lines of the batch -- no integer division in the hot loops.  Per stage, a packed table entry per position
-// (built once per CTA) holds j (source butterfly offset), e (twiddle increment) and dst (Stockham output position).
+#define FFT_THREADS 512
 #define TID (threadIdx.y*blockDim.x + threadIdx.x)
 #define NTHR (blockDim.x*blockDim.y)
+__device__ __forceinline__ real2 make_real2(real x, real y) { real2 r; r.x = x; r.y = y; return r; }
 
-__device__ __forceinline__ void fft_build_tables(unsigned int* tab, const FftPlanDev& plan) {
-    const int n = plan.n;
-    for (int i = TID; i < plan.nstages*n; i += NTHR) {
-        const int s = i/n, p = i - s*n;
-        int Ns = 1;
-        for (int a = 0; a < s; a++) Ns *= plan.radix[a];
-        const int R = plan.radix[s], nb = n/R;
-        const int j = p/R, q = p - j*R, k = j % Ns;
-        const int e = (k*(n/(Ns*R)) + q*nb) % n;
-        const int dst = (j/Ns)*Ns*R + k + q*Ns;
-        tab[i] = (unsigned int) j | ((unsigned int) e << 10) | ((unsigned int) dst << 20);
-    }
-}
-
-// One Stockham stage of radix R over `nlines` contiguous lines of length n (line l at base + l*n), ONE OUTPUT ELEMENT
-// PER THREAD: output q of butterfly j is sum_t x[j + t n/R] * w^(t e), e = k twStep + q n/R -- the stage twiddle and
-// the radix-R DFT root collapse into a single table lookup whose index advances by e (mod n).  The loop is rolled
-// (same ~40 instructions of code for every radix) and every grid point is an independent work item.
-__device__ __forceinline__ void fft_stage(const double2* __restrict__ in, double2* __restrict__ out, int n, int nlines, int R,
-                                          const unsigned int* __restrict__ tab, const double2* __restrict__ tw, bool inverse) {
-    const int p = threadIdx.x;
-    if (p >= n) return;
-    const unsigned int u = tab[p];
-    const int j = u & 1023u, e = (u >> 10) & 1023u, dst = u >> 20;
-    const int nb = n/R;
-    const double sgn = inverse ? -1.0 : 1.0;
-    for (int line = threadIdx.y; line < nlines; line += blockDim.y) {
-        const double2* src = in + line*n + j;
-        double2 acc = src[0];
-        int idx = e;
-#pragma unroll 4
-        for (int t = 1; t < R; t++) {
-            const double2 x = src[t*nb];
-            const double2 wv = tw[idx];
-            const double wy = sgn*wv.y;
-            acc.x += x.x*wv.x - x.y*wy;
-            acc.y += x.x*wy + x.y*wv.x;
-            idx += e;
-            if (idx >= n) idx -= n;
+// One Stockham stage of radix R over `nlines` contiguous lines of length n (line l at base + l*n), one BUTTERFLY per
+// thread: R inputs are read once into registers, multiplied by the stage twiddles, combined by a generic radix-R DFT
+// (R*R complex MACs against the R-th roots of unity, taken from the twiddle table in shared memory) and written to their
+// autosort positions.  Shared-memory traffic is 2 accesses per point per stage.  (A one-OUTPUT-per-thread variant was
+// tried in round 1: R-fold redundant operand reads made the transform shared-memory-bandwidth bound, 62 us at 56^3.)
+template <int R>
+__device__ __forceinline__ void fft_stage(const real2* __restrict__ in, real2* __restrict__ out, int n, int nlines,
+                                          int Ns, const real2* __restrict__ tw, bool inverse) {
+    const int nb = n/R;                 // butterflies per line
+    const int twStep = n/(Ns*R);
+    const int total = nlines*nb;
+    const real sgn = inverse ? (real) -1 : (real) 1;
+    for (int w = TID; w < total; w += NTHR) {
+        const int line = w/nb;
+        const int j = w - line*nb;
+        const int k = j % Ns;
+        const real2* src = in + line*n + j;
+        real2 v[R];
+#pragma unroll
+        for (int t = 0; t < R; t++) v[t] = src[t*nb];
+        if (k > 0) {
+            int idx = 0;
+#pragma unroll
+            for (int t = 1; t < R; t++) {
+                idx += k*twStep;                     // t*k*twStep < n
+                real2 wv = tw[idx];
+                wv.y *= sgn;
+                const real2 x = v[t];
+                v[t] = make_real2(x.x*wv.x - x.y*wv.y, x.x*wv.y + x.y*wv.x);
+            }
         }
-        out[line*n + dst] = acc;
+        real2* dst = out + line*n + (j/Ns)*Ns*R + k;
+        if (R == 2) {
+            dst[0] = make_real2(v[0].x + v[R-1].x, v[0].y + v[R-1].y);
+            dst[Ns] = make_real2(v[0].x - v[R-1].x, v[0].y - v[R-1].y);
+        }
+        else if (R == 4) {
+            // radix-4 with trivial roots (-i forward, +i inverse): 16 adds, no multiplications
+            const real2 a = make_real2(v[0].x + v[R/2].x, v[0].y + v[R/2].y), b = make_real2(v[0].x - v[R/2].x, v[0].y - v[R/2].y);
+            const real2 c = make_real2(v[1].x + v[R-1].x, v[1].y + v[R-1].y), d = make_real2(v[1].x - v[R-1].x, v[1].y - v[R-1].y);
+            const real2 id = make_real2(sgn*d.y, -sgn*d.x);         // (-i forward / +i inverse) * d
+            dst[0] = make_real2(a.x + c.x, a.y + c.y);
+            dst[Ns] = make_real2(b.x + id.x, b.y + id.y);
+            dst[2*Ns] = make_real2(a.x - c.x, a.y - c.y);
+            dst[3*Ns] = make_real2(b.x - id.x, b.y - id.y);
+        }
+        else {
+            // generic radix: the output loop is ROLLED (one copy of the R-1 MACs, executed R times, roots re-read from
+            // shared memory as warp-uniform broadcasts) -- a fully unrolled R x R butterfly is ~4R^2 instructions that
+            // each warp executes once, which made these kernels instruction-fetch bound
+#pragma unroll 1
+            for (int q = 0; q < R; q++) {
+                real2 acc = v[0];
+                int idx = 0;
+                const int step = q*nb;
+#pragma unroll
+                for (int t = 1; t < R; t++) {
+                    idx += step;
+                    if (idx >= n) idx -= n;
+                    real2 r = tw[idx];
+                    r.y *= sgn;
+                    acc.x += v[t].x*r.x - v[t].y*r.y;
+                    acc.y += v[t].x*r.y + v[t].y*r.x;
+                }
+                dst[q*Ns] = acc;
+            }
+        }
     }
 }
 
 // full 1-D transform of `nlines` contiguous lines; returns the buffer holding the result. Block-wide.
-__device__ double2* fft_lines(double2* a, double2* b, const FftPlanDev& plan, int nlines, const unsigned int* tab, const double2* tw, bool inverse) {
-    double2* in = a;
-    double2* out = b;
+__device__ real2* fft_lines(real2* a, real2* b, const FftPlanDev& plan, int nlines, const unsigned int* tab, const real2* tw, bool inverse) {
+    (void) tab;
+    int Ns = 1;
+    real2* in = a;
+    real2* out = b;
     for (int s = 0; s < plan.nstages; s++) {
-        fft_stage(in, out, plan.n, nlines, plan.radix[s], tab + s*plan.n, tw, inverse);
+        const int R = plan.radix[s];
+        switch (R) {
+            case 2: fft_stage<2>(in, out, plan.n, nlines, Ns, tw, inverse); break;
+            case 3: fft_stage<3>(in, out, plan.n, nlines, Ns, tw, inverse); break;
+            case 4: fft_stage<4>(in, out, plan.n, nlines, Ns, tw, inverse); break;
+            case 5: fft_stage<5>(in, out, plan.n, nlines, Ns, tw, inverse); break;
+            case 6: fft_stage<6>(in, out, plan.n, nlines, Ns, tw, inverse); break;
+            case 7: fft_stage<7>(in, out, plan.n, nlines, Ns, tw, inverse); break;
+            case 8: fft_stage<8>(in, out, plan.n, nlines, Ns, tw, inverse); break;
+            case 9: fft_stage<9>(in, out, plan.n, nlines, Ns, tw, inverse); break;
+            case 10: fft_stage<10>(in, out, plan.n, nlines, Ns, tw, inverse); break;
+            case 11: fft_stage<11>(in, out, plan.n, nlines, Ns, tw, inverse); break;
+            case 12: fft_stage<12>(in, out, plan.n, nlines, Ns, tw, inverse); break;
+            case 13: fft_stage<13>(in, out, plan.n, nlines, Ns, tw, inverse); break;
+            case 14: fft_stage<14>(in, out, plan.n, nlines, Ns, tw, inverse); break;
+            case 15: fft_stage<15>(in, out, plan.n, nlines, Ns, tw, inverse); break;
+            case 16: fft_stage<16>(in, out, plan.n, nlines, Ns, tw, inverse); break;
+            default: break;
+        }
         __syncthreads();
-        double2* t = in; in = out; out = t;
+        Ns *= R;
+        real2* t = in; in = out; out = t;
     }
     return in;
 }
+
+__device__ __forceinline__ void fft_build_tables(unsigned int* tab, const FftPlanDev& plan) { (void) tab; (void) plan; }
 
 // factorisation into radices <= 16 minimising sum(R + 4): R complex MACs per point per generic stage plus a
 // synchronisation cost per stage (exhaustive search, n is small)
@@ -95,7 +144,7 @@ static int best_cost(int n, int* radix, int depth) {
     int best = 1 << 28, sub[B200MD_MAX_FFT_STAGES];
     for (int r = 2; r <= B200MD_MAX_RADIX && r <= n; r++) {
         if (n % r) continue;
-        const int stageCost = r + 4;
+        const int stageCost = (r == 2 ? 2 : (r == 4 ? 3 : 2*r)) + 3;      // radix 2 / 4 have multiplication-free butterflies
         int c = stageCost + best_cost(n/r, sub, depth+1);
         if (c < best) {
             best = c;
@@ -121,17 +170,16 @@ bool fft_make_radices(int n, int* radix, int* nstages) {
 
 #define ZROWS 16          // real rows per CTA in the z passes (8 packed complex lines)
 #define LINE_BATCH 16     // lines per CTA in the y and x passes
-#define FFT_THREADS 256
 
 size_t fft_plane_smem_bytes(int ny, int nz) {       // kept for the engine's capacity check: largest per-CTA need
-    size_t z = (2*(size_t) (ZROWS/2)*nz + 3*nz)*sizeof(double2);
-    size_t y = (2*(size_t) LINE_BATCH*ny + 3*ny)*sizeof(double2);
+    size_t z = (2*(size_t) (ZROWS/2)*nz + 3*nz)*sizeof(real2);
+    size_t y = (2*(size_t) LINE_BATCH*ny + 3*ny)*sizeof(real2);
     return z > y ? z : y;
 }
-size_t fft_line_smem_bytes(int nx) { return (2*(size_t) LINE_BATCH*nx + 3*nx)*sizeof(double2); }
+size_t fft_line_smem_bytes(int nx) { return (2*(size_t) LINE_BATCH*nx + 3*nx)*sizeof(real2); }
 
-// twiddles (n double2) followed by the per-stage position tables (8*n uint32 = 2n double2 of space)
-__device__ __forceinline__ unsigned int* stage_twiddles(double2* tws, const FftPlanDev& plan) {
+// twiddles (n real2) followed by the per-stage position tables (8*n uint32 = 2n real2 of space)
+__device__ __forceinline__ unsigned int* stage_twiddles(real2* tws, const FftPlanDev& plan) {
     for (int i = TID; i < plan.n; i += NTHR) tws[i] = plan.tw[i];
     unsigned int* tab = (unsigned int*) (tws + plan.n);
     fft_build_tables(tab, plan);
@@ -139,105 +187,105 @@ __device__ __forceinline__ unsigned int* stage_twiddles(double2* tws, const FftP
 }
 
 // ---- 1: forward z, real to complex, two rows per complex line ----
-__global__ void __launch_bounds__(1024) k_fft_z_fwd(PmeDev pme) {
-    extern __shared__ double2 smem[];
+__global__ void __launch_bounds__(FFT_THREADS) k_fft_z_fwd(PmeDev pme) {
+    extern __shared__ real2 smem[];
     const int nz = pme.nz, nzc = pme.nzc;
     const int nrowsTotal = pme.nx*pme.ny;
     const int row0 = blockIdx.x*ZROWS;
     const int nrows = min(ZROWS, nrowsTotal - row0);
     const int np = (nrows + 1)/2;
-    double2* A = smem;
-    double2* B = A + (ZROWS/2)*nz;
-    double2* tws = B + (ZROWS/2)*nz;
+    real2* A = smem;
+    real2* B = A + (ZROWS/2)*nz;
+    real2* tws = B + (ZROWS/2)*nz;
     const unsigned int* tab = stage_twiddles(tws, pme.plan[2]);
     if (pme.gridFixed != nullptr) {
         const long long* base = pme.gridFixed + (size_t) row0*nz;
-        const double sc = 1.0/4294967296.0;
+        const real sc = (real) (1.0/4294967296.0);
         for (int i = TID; i < np*nz; i += NTHR) {
             const int p = i/nz, z = i - p*nz;
-            const double re = (double) base[(size_t) (2*p)*nz + z]*sc;
-            const double im = (2*p+1 < nrows) ? (double) base[(size_t) (2*p+1)*nz + z]*sc : 0.0;
-            A[i] = make_double2(re, im);
+            const real re = (real) base[(size_t) (2*p)*nz + z]*sc;
+            const real im = (2*p+1 < nrows) ? (real) base[(size_t) (2*p+1)*nz + z]*sc : (real) 0;
+            A[i] = make_real2(re, im);
         }
     }
     else {
-        const double* base = pme.grid + (size_t) row0*nz;
+        const real* base = pme.grid + (size_t) row0*nz;
         for (int i = TID; i < np*nz; i += NTHR) {
             const int p = i/nz, z = i - p*nz;
-            const double re = base[(size_t) (2*p)*nz + z];
-            const double im = (2*p+1 < nrows) ? base[(size_t) (2*p+1)*nz + z] : 0.0;
-            A[i] = make_double2(re, im);
+            const real re = base[(size_t) (2*p)*nz + z];
+            const real im = (2*p+1 < nrows) ? base[(size_t) (2*p+1)*nz + z] : (real) 0;
+            A[i] = make_real2(re, im);
         }
     }
     __syncthreads();
-    const double2* R = fft_lines(A, B, pme.plan[2], np, tab, tws, false);
+    const real2* R = fft_lines(A, B, pme.plan[2], np, tab, tws, false);
     // unpack the two interleaved real transforms straight to global memory
-    double2* dst = pme.cgrid + (size_t) row0*nzc;
+    real2* dst = pme.cgrid + (size_t) row0*nzc;
     for (int i = TID; i < np*nzc; i += NTHR) {
         const int p = i/nzc, k = i - p*nzc;
-        const double2 Z = R[p*nz + k];
-        double2 Zc = R[p*nz + ((nz - k) % nz)];
+        const real2 Z = R[p*nz + k];
+        real2 Zc = R[p*nz + ((nz - k) % nz)];
         Zc.y = -Zc.y;
-        dst[(size_t) (2*p)*nzc + k] = make_double2(0.5*(Z.x + Zc.x), 0.5*(Z.y + Zc.y));
+        dst[(size_t) (2*p)*nzc + k] = make_real2((real) 0.5*(Z.x + Zc.x), (real) 0.5*(Z.y + Zc.y));
         if (2*p+1 < nrows) {
-            const double2 d = make_double2(0.5*(Z.x - Zc.x), 0.5*(Z.y - Zc.y));
-            dst[(size_t) (2*p+1)*nzc + k] = make_double2(d.y, -d.x);     // -i*d
+            const real2 d = make_real2((real) 0.5*(Z.x - Zc.x), (real) 0.5*(Z.y - Zc.y));
+            dst[(size_t) (2*p+1)*nzc + k] = make_real2(d.y, -d.x);     // -i*d
         }
     }
 }
 
 // ---- 5: inverse z, complex to real ----
-__global__ void __launch_bounds__(1024) k_fft_z_inv(PmeDev pme) {
-    extern __shared__ double2 smem[];
+__global__ void __launch_bounds__(FFT_THREADS) k_fft_z_inv(PmeDev pme) {
+    extern __shared__ real2 smem[];
     const int nz = pme.nz, nzc = pme.nzc;
     const int nrowsTotal = pme.nx*pme.ny;
     const int row0 = blockIdx.x*ZROWS;
     const int nrows = min(ZROWS, nrowsTotal - row0);
     const int np = (nrows + 1)/2;
-    double2* A = smem;
-    double2* B = A + (ZROWS/2)*nz;
-    double2* tws = B + (ZROWS/2)*nz;
+    real2* A = smem;
+    real2* B = A + (ZROWS/2)*nz;
+    real2* tws = B + (ZROWS/2)*nz;
     const unsigned int* tab = stage_twiddles(tws, pme.plan[2]);
-    const double2* src = pme.cgrid + (size_t) row0*nzc;
+    const real2* src = pme.cgrid + (size_t) row0*nzc;
     // pack rows (2p, 2p+1) into one complex line using the Hermitian symmetry along z
     for (int i = TID; i < np*nz; i += NTHR) {
         const int p = i/nz, k = i - p*nz;
         const int kk = (k < nzc) ? k : nz - k;
-        double2 a = src[(size_t) (2*p)*nzc + kk];
-        double2 b = (2*p+1 < nrows) ? src[(size_t) (2*p+1)*nzc + kk] : make_double2(0.0, 0.0);
+        real2 a = src[(size_t) (2*p)*nzc + kk];
+        real2 b = (2*p+1 < nrows) ? src[(size_t) (2*p+1)*nzc + kk] : make_real2(0, 0);
         if (k >= nzc) { a.y = -a.y; b.y = -b.y; }
-        A[i] = make_double2(a.x - b.y, a.y + b.x);       // a + i b
+        A[i] = make_real2(a.x - b.y, a.y + b.x);       // a + i b
     }
     __syncthreads();
-    const double2* Z = fft_lines(A, B, pme.plan[2], np, tab, tws, true);
-    double* dst = pme.grid + (size_t) row0*nz;
+    const real2* Z = fft_lines(A, B, pme.plan[2], np, tab, tws, true);
+    real* dst = pme.grid + (size_t) row0*nz;
     for (int i = TID; i < np*nz; i += NTHR) {
         const int p = i/nz, z = i - p*nz;
-        const double2 v = Z[i];
+        const real2 v = Z[i];
         dst[(size_t) (2*p)*nz + z] = v.x;
         if (2*p+1 < nrows) dst[(size_t) (2*p+1)*nz + z] = v.y;
     }
 }
 
 // ---- 2 / 4: along y, LINE_BATCH adjacent kz columns of one x per CTA ----
-__global__ void __launch_bounds__(1024) k_fft_y(PmeDev pme, int inverse) {
-    extern __shared__ double2 smem[];
+__global__ void __launch_bounds__(FFT_THREADS) k_fft_y(PmeDev pme, int inverse) {
+    extern __shared__ real2 smem[];
     const int ny = pme.ny, nzc = pme.nzc;
     const int nbz = (nzc + LINE_BATCH - 1)/LINE_BATCH;
     const int x = blockIdx.x/nbz, bz = blockIdx.x - x*nbz;
     const int kz0 = bz*LINE_BATCH;
     const int nk = min(LINE_BATCH, nzc - kz0);
-    double2* A = smem;
-    double2* B = A + LINE_BATCH*ny;
-    double2* tws = B + LINE_BATCH*ny;
+    real2* A = smem;
+    real2* B = A + LINE_BATCH*ny;
+    real2* tws = B + LINE_BATCH*ny;
     const unsigned int* tab = stage_twiddles(tws, pme.plan[1]);
-    double2* base = pme.cgrid + (size_t) x*ny*nzc + kz0;
+    real2* base = pme.cgrid + (size_t) x*ny*nzc + kz0;
     for (int i = TID; i < ny*LINE_BATCH; i += NTHR) {
         const int y = i/LINE_BATCH, l = i - y*LINE_BATCH;
         if (l < nk) A[l*ny + y] = base[(size_t) y*nzc + l];
     }
     __syncthreads();
-    const double2* R = fft_lines(A, B, pme.plan[1], nk, tab, tws, inverse != 0);
+    const real2* R = fft_lines(A, B, pme.plan[1], nk, tab, tws, inverse != 0);
     for (int i = TID; i < ny*LINE_BATCH; i += NTHR) {
         const int y = i/LINE_BATCH, l = i - y*LINE_BATCH;
         if (l < nk) base[(size_t) y*nzc + l] = R[l*ny + y];
@@ -247,13 +295,13 @@ __global__ void __launch_bounds__(1024) k_fft_y(PmeDev pme, int inverse) {
 // ---- 3: forward x, convolution + energy, inverse x; one batch of (ky,kz) lines per CTA ----
 // mode 0: forward + convolution + inverse (PME); mode 1: forward only; mode 2: inverse only (stand-alone FFT)
 template <bool ENERGY>
-__global__ void __launch_bounds__(1024) k_fft_x_conv(PmeDev pme, double* energyOut, int mode) {
-    extern __shared__ double2 smem[];
+__global__ void __launch_bounds__(FFT_THREADS) k_fft_x_conv(PmeDev pme, double* energyOut, int mode) {
+    extern __shared__ real2 smem[];
     const int nx = pme.nx;
     const int plane = pme.ny*pme.nzc;
-    double2* A = smem;
-    double2* B = A + LINE_BATCH*nx;
-    double2* tws = B + LINE_BATCH*nx;
+    real2* A = smem;
+    real2* B = A + LINE_BATCH*nx;
+    real2* tws = B + LINE_BATCH*nx;
     const unsigned int* tab = stage_twiddles(tws, pme.plan[0]);
     const int m0 = blockIdx.x*LINE_BATCH;
     const int nl = min(LINE_BATCH, plane - m0);
@@ -262,8 +310,8 @@ __global__ void __launch_bounds__(1024) k_fft_x_conv(PmeDev pme, double* energyO
         if (l < nl) A[l*nx + x] = pme.cgrid[(size_t) x*plane + m0 + l];
     }
     __syncthreads();
-    double2* R = A;
-    double2* other = B;
+    real2* R = A;
+    real2* other = B;
     if (mode != 2) {
         R = fft_lines(A, B, pme.plan[0], nl, tab, tws, false);
         other = (R == A) ? B : A;
@@ -274,14 +322,14 @@ __global__ void __launch_bounds__(1024) k_fft_x_conv(PmeDev pme, double* energyO
             const int x = i/LINE_BATCH, l = i - x*LINE_BATCH;
             if (l < nl) {
                 const int m = m0 + l;
-                const double et = pme.eterm[(size_t) x*plane + m];
-                const double2 v = R[l*nx + x];
+                const real et = pme.eterm[(size_t) x*plane + m];
+                const real2 v = R[l*nx + x];
                 if (ENERGY) {
                     const int kz = m % pme.nzc;
                     const double wgt = (kz == 0 || (2*kz == pme.nz)) ? 1.0 : 2.0;    // Hermitian mirror counted here
                     esum += wgt*et*(v.x*v.x + v.y*v.y);
                 }
-                R[l*nx + x] = make_double2(v.x*et, v.y*et);
+                R[l*nx + x] = make_real2(v.x*et, v.y*et);
             }
         }
         if (ENERGY) {
@@ -309,21 +357,144 @@ static void set_smem(const void* f, size_t bytes) {
     if (bytes > 48*1024) cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
 }
 
+// ---- slab kernels: one x-slab per CTA, the whole (y,z) plane lives in shared memory, z and y passes fused ----
+// Used whenever 2 plane buffers fit in shared memory (ny*nzc <= ~6900 points, i.e. grids up to ~112^2 per slab); then
+// forward + convolution + inverse is THREE launches (slab fwd, x lines + convolution, slab inv), which matters because
+// at 56^3 every launch boundary costs more than the arithmetic of a whole pass.
+struct SlabSmem { real2 *A, *B, *twz, *twy; unsigned int *tabz, *taby; };
+
+__device__ __forceinline__ SlabSmem slab_setup(real2* smem, const PmeDev& pme, size_t elems) {
+    SlabSmem S;
+    S.A = smem; S.B = smem + elems;
+    S.twz = S.B + elems; S.twy = S.twz + pme.nz;
+    S.tabz = (unsigned int*) (S.twy + pme.ny);
+    S.taby = S.tabz + 8*pme.nz;
+    for (int i = TID; i < pme.nz; i += NTHR) S.twz[i] = pme.plan[2].tw[i];
+    for (int i = TID; i < pme.ny; i += NTHR) S.twy[i] = pme.plan[1].tw[i];
+    fft_build_tables(S.tabz, pme.plan[2]);
+    fft_build_tables(S.taby, pme.plan[1]);
+    return S;
+}
+
+static size_t slab_elems(const PmeDev& p) {
+    const size_t np = (p.ny + 1)/2;
+    size_t e = (size_t) p.ny*p.nzc;
+    if (np*p.nz > e) e = np*p.nz;
+    return e;
+}
+static size_t slab_smem_bytes(const PmeDev& p) {
+    return 2*slab_elems(p)*sizeof(real2) + (size_t) (p.nz + p.ny)*sizeof(real2) + (size_t) 8*(p.nz + p.ny)*sizeof(unsigned int);
+}
+
+__global__ void __launch_bounds__(FFT_THREADS) k_fft_slab_fwd(PmeDev pme, size_t elems) {
+    extern __shared__ real2 smem[];
+    const int ny = pme.ny, nz = pme.nz, nzc = pme.nzc;
+    const int np = (ny + 1)/2;
+    SlabSmem S = slab_setup(smem, pme, elems);
+    const int x = blockIdx.x;
+    if (pme.gridFixed != nullptr) {
+        long long* base = pme.gridFixed + (size_t) x*ny*nz;
+        const real sc = (real) (1.0/4294967296.0);
+        for (int i = TID; i < np*nz; i += NTHR) {
+            const int p = i/nz, z = i - p*nz;
+            const real re = (real) base[(size_t) (2*p)*nz + z]*sc;
+            const real im = (2*p+1 < ny) ? (real) base[(size_t) (2*p+1)*nz + z]*sc : (real) 0;
+            S.A[i] = make_real2(re, im);
+        }
+    }
+    else {
+        const real* base = pme.grid + (size_t) x*ny*nz;
+        for (int i = TID; i < np*nz; i += NTHR) {
+            const int p = i/nz, z = i - p*nz;
+            S.A[i] = make_real2(base[(size_t) (2*p)*nz + z], (2*p+1 < ny) ? base[(size_t) (2*p+1)*nz + z] : 0.0);
+        }
+    }
+    __syncthreads();
+    const real2* R = fft_lines(S.A, S.B, pme.plan[2], np, S.tabz, S.twz, false);
+    real2* O = (R == S.A) ? S.B : S.A;
+    // unpack the two interleaved real transforms, transposed to [kz][y] so that the y lines are contiguous
+    for (int i = TID; i < np*nzc; i += NTHR) {
+        const int p = i/nzc, k = i - p*nzc;
+        const real2 Z = R[p*nz + k];
+        real2 Zc = R[p*nz + ((nz - k) % nz)];
+        Zc.y = -Zc.y;
+        O[k*ny + 2*p] = make_real2((real) 0.5*(Z.x + Zc.x), (real) 0.5*(Z.y + Zc.y));
+        if (2*p+1 < ny) {
+            const real2 d = make_real2((real) 0.5*(Z.x - Zc.x), (real) 0.5*(Z.y - Zc.y));
+            O[k*ny + 2*p+1] = make_real2(d.y, -d.x);
+        }
+    }
+    __syncthreads();
+    real2* other = (O == S.A) ? S.B : S.A;
+    const real2* Y = fft_lines(O, other, pme.plan[1], nzc, S.taby, S.twy, false);
+    real2* dst = pme.cgrid + (size_t) x*ny*nzc;
+    for (int i = TID; i < ny*nzc; i += NTHR) {
+        const int y = i/nzc, k = i - y*nzc;
+        dst[i] = Y[k*ny + y];
+    }
+}
+
+__global__ void __launch_bounds__(FFT_THREADS) k_fft_slab_inv(PmeDev pme, size_t elems) {
+    extern __shared__ real2 smem[];
+    const int ny = pme.ny, nz = pme.nz, nzc = pme.nzc;
+    const int np = (ny + 1)/2;
+    SlabSmem S = slab_setup(smem, pme, elems);
+    const int x = blockIdx.x;
+    const real2* src = pme.cgrid + (size_t) x*ny*nzc;
+    for (int i = TID; i < ny*nzc; i += NTHR) {
+        const int y = i/nzc, k = i - y*nzc;
+        S.A[k*ny + y] = src[i];
+    }
+    __syncthreads();
+    const real2* Y = fft_lines(S.A, S.B, pme.plan[1], nzc, S.taby, S.twy, true);
+    real2* O = (Y == S.A) ? S.B : S.A;
+    // pack rows (2p, 2p+1) into one complex line using the Hermitian symmetry along z
+    for (int i = TID; i < np*nz; i += NTHR) {
+        const int p = i/nz, k = i - p*nz;
+        const int kk = (k < nzc) ? k : nz - k;
+        real2 a = Y[kk*ny + 2*p];
+        real2 b = (2*p+1 < ny) ? Y[kk*ny + 2*p+1] : make_real2(0, 0);
+        if (k >= nzc) { a.y = -a.y; b.y = -b.y; }
+        O[i] = make_real2(a.x - b.y, a.y + b.x);
+    }
+    __syncthreads();
+    real2* other = (O == S.A) ? S.B : S.A;
+    const real2* Z = fft_lines(O, other, pme.plan[2], np, S.tabz, S.twz, true);
+    real* dst = pme.grid + (size_t) x*ny*nz;
+    for (int i = TID; i < np*nz; i += NTHR) {
+        const int p = i/nz, z = i - p*nz;
+        const real2 v = Z[i];
+        dst[(size_t) (2*p)*nz + z] = v.x;
+        if (2*p+1 < ny) dst[(size_t) (2*p+1)*nz + z] = v.y;
+    }
+}
+
 static dim3 fft_block(int n, int maxLines) {
-    int ly = FFT_THREADS/n;
-    if (ly < 1) ly = 1;
-    if (ly > maxLines) ly = maxLines;
-    return dim3(n, ly);
+    (void) n; (void) maxLines;
+    return dim3(FFT_THREADS);
 }
 
 struct FftLaunch {
-    size_t zs, ys, xs;
+    size_t zs, ys, xs, ss, selems;
     int zb, yb, xb;
-    dim3 zt, yt, xt;
+    dim3 zt, yt, xt, st;
+    bool slab;
     FftLaunch(const PmeDev& p) {
-        zs = (2*(size_t) (ZROWS/2)*p.nz + 3*p.nz)*sizeof(double2);
-        ys = (2*(size_t) LINE_BATCH*p.ny + 3*p.ny)*sizeof(double2);
-        xs = (2*(size_t) LINE_BATCH*p.nx + 3*p.nx)*sizeof(double2);
+        int dev = 0, maxSmem = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&maxSmem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+        ss = slab_smem_bytes(p);
+        selems = slab_elems(p);
+        const int nmax = p.ny > p.nz ? p.ny : p.nz;
+        slab = ss <= (size_t) maxSmem && nmax <= 1024 && getenv("B200MD_FFT_NOSLAB") == nullptr;
+        if (slab) {
+            st = dim3(FFT_THREADS);
+            set_smem((const void*) k_fft_slab_fwd, ss);
+            set_smem((const void*) k_fft_slab_inv, ss);
+        }
+        zs = (2*(size_t) (ZROWS/2)*p.nz + 3*p.nz)*sizeof(real2);
+        ys = (2*(size_t) LINE_BATCH*p.ny + 3*p.ny)*sizeof(real2);
+        xs = (2*(size_t) LINE_BATCH*p.nx + 3*p.nx)*sizeof(real2);
         zt = fft_block(p.nz, ZROWS/2); yt = fft_block(p.ny, LINE_BATCH); xt = fft_block(p.nx, LINE_BATCH);
         zb = (p.nx*p.ny + ZROWS - 1)/ZROWS;
         yb = p.nx*((p.nzc + LINE_BATCH - 1)/LINE_BATCH);
@@ -336,26 +507,39 @@ struct FftLaunch {
     }
 };
 
+static void fwd_zy(const FftLaunch& L, const PmeDev& pme, cudaStream_t s) {
+    if (L.slab) k_fft_slab_fwd<<<pme.nx, L.st, L.ss, s>>>(pme, L.selems);
+    else {
+        k_fft_z_fwd<<<L.zb, L.zt, L.zs, s>>>(pme);
+        k_fft_y<<<L.yb, L.yt, L.ys, s>>>(pme, 0);
+    }
+}
+static void inv_yz(const FftLaunch& L, const PmeDev& pme, cudaStream_t s) {
+    if (L.slab) k_fft_slab_inv<<<pme.nx, L.st, L.ss, s>>>(pme, L.selems);
+    else {
+        k_fft_y<<<L.yb, L.yt, L.ys, s>>>(pme, 1);
+        k_fft_z_inv<<<L.zb, L.zt, L.zs, s>>>(pme);
+    }
+}
+
+int pme_fft_launch_count(const PmeDev& pme) { FftLaunch L(pme); return L.slab ? 3 : 5; }
+
 void launch_pme_fft_conv(const NbDev& nb, const PmeDev& pme, bool energy, cudaStream_t s) {
     FftLaunch L(pme);
-    k_fft_z_fwd<<<L.zb, L.zt, L.zs, s>>>(pme);
-    k_fft_y<<<L.yb, L.yt, L.ys, s>>>(pme, 0);
+    fwd_zy(L, pme, s);
     if (energy) k_fft_x_conv<true><<<L.xb, L.xt, L.xs, s>>>(pme, nb.energy + EN_RECIP, 0);
     else k_fft_x_conv<false><<<L.xb, L.xt, L.xs, s>>>(pme, nb.energy + EN_RECIP, 0);
-    k_fft_y<<<L.yb, L.yt, L.ys, s>>>(pme, 1);
-    k_fft_z_inv<<<L.zb, L.zt, L.zs, s>>>(pme);
+    inv_yz(L, pme, s);
 }
 
 void launch_fft3d_r2c(const PmeDev& pme, cudaStream_t s) {
     FftLaunch L(pme);
-    k_fft_z_fwd<<<L.zb, L.zt, L.zs, s>>>(pme);
-    k_fft_y<<<L.yb, L.yt, L.ys, s>>>(pme, 0);
+    fwd_zy(L, pme, s);
     k_fft_x_conv<false><<<L.xb, L.xt, L.xs, s>>>(pme, nullptr, 1);
 }
 
 void launch_fft3d_c2r(const PmeDev& pme, cudaStream_t s) {
     FftLaunch L(pme);
     k_fft_x_conv<false><<<L.xb, L.xt, L.xs, s>>>(pme, nullptr, 2);
-    k_fft_y<<<L.yb, L.yt, L.ys, s>>>(pme, 1);
-    k_fft_z_inv<<<L.zb, L.zt, L.zs, s>>>(pme);
+    inv_yz(L, pme, s);
 }

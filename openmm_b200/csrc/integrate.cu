@@ -267,10 +267,11 @@ __global__ void __launch_bounds__(128) k_integrate(NbDev nb, UnitDev un, IntegDe
 __global__ void k_step_advance(IntegDev in) { *in.stepCounter += 1ull; }
 
 void launch_integrate(const NbDev& nb, const UnitDev& units, const IntegDev& integ, cudaStream_t s) {
-    const int grid = (units.nunits + 127)/128;
-    if (integ.kind == B200MD_INT_VERLET) k_integrate<B200MD_INT_VERLET><<<grid, 128, 0, s>>>(nb, units, integ);
-    else if (integ.kind == B200MD_INT_LANGEVIN) k_integrate<B200MD_INT_LANGEVIN><<<grid, 128, 0, s>>>(nb, units, integ);
-    else k_integrate<B200MD_INT_LANGEVIN_MIDDLE><<<grid, 128, 0, s>>>(nb, units, integ);
+    // 64-thread blocks: at DHFR size (8k units) 128-thread blocks fill only 65 of the 148 SMs
+    const int grid = (units.nunits + 63)/64;
+    if (integ.kind == B200MD_INT_VERLET) k_integrate<B200MD_INT_VERLET><<<grid, 64, 0, s>>>(nb, units, integ);
+    else if (integ.kind == B200MD_INT_LANGEVIN) k_integrate<B200MD_INT_LANGEVIN><<<grid, 64, 0, s>>>(nb, units, integ);
+    else k_integrate<B200MD_INT_LANGEVIN_MIDDLE><<<grid, 64, 0, s>>>(nb, units, integ);
     k_step_advance<<<1, 1, 0, s>>>(integ);
 }
 

@@ -12,6 +12,7 @@
 // emitted, so there is no static "exclusion tile" set and no host involvement.
 #include "engine.h"
 #include "../../include/b200md.h"
+#include <algorithm>
 
 #define FULL 0xffffffffu
 
@@ -56,16 +57,43 @@ __device__ __forceinline__ float box_dist2(float3 d, float hx, float hy, float h
 }
 
 // ------------------------------------------------------------------------------------------------
-// 1. rebuild decision: any atom moved more than padding/2 since the last build (findInteractingBlocks.cu:67-76)
-__global__ void k_check_displacement(NbDev nb) {
-    int a = blockIdx.x*blockDim.x + threadIdx.x;
-    if (a >= nb.natoms) return;
-    float4 p = nb.posq[a];
-    float4 r = nb.refPos[a];
-    float dx = p.x-r.x, dy = p.y-r.y, dz = p.z-r.z;
-    float d2 = dx*dx + dy*dy + dz*dz;
-    if (!(d2 <= nb.halfPad2))       // also true for NaN
-        nb.counters[2] = 1;
+// 1. rebuild decision: any atom moved more than padding/2 since the last build (findInteractingBlocks.cu:67-76), fused
+// with the per-step refresh of the sorted position copy (with the CURRENT order; a rebuild in the same step rewrites it).
+// The last block to finish publishes the decision to the CUDA-graph conditional node that holds the rebuild kernels.
+__global__ void __launch_bounds__(256) k_check_gather(NbDev nb) {
+    const int s = blockIdx.x*blockDim.x + threadIdx.x;
+    if (s < nb.natoms) {
+        const float4 p = nb.posq[s];
+        const float4 r = nb.refPos[s];
+        const float dx = p.x-r.x, dy = p.y-r.y, dz = p.z-r.z;
+        const float d2 = dx*dx + dy*dy + dz*dz;
+        if (!(d2 <= nb.halfPad2))       // also true for NaN
+            nb.counters[2] = 1;
+    }
+    if (s < nb.npad) {
+        int a = nb.sorig[s];
+        if (a < 0 || a >= nb.natoms) a = nb.sorig[nb.natoms-1];
+        a = min(max(a, 0), nb.natoms-1);          // garbage-safe before the first build
+        float4 p = nb.posq[a];
+        const float4 sh = nb.sshift[min(s, nb.natoms-1)];
+        if (s >= nb.natoms) p.w = 0.f;
+        nb.sposq[s] = make_float4(p.x+sh.x, p.y+sh.y, p.z+sh.z, p.w);
+    }
+    if (nb.condHandle != 0ull) {
+        __shared__ int last;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            last = (atomicAdd(&nb.counters[8], 1) == (int) gridDim.x - 1);
+        }
+        __syncthreads();
+        if (last && threadIdx.x == 0) {
+            nb.counters[8] = 0;
+            __threadfence();
+            const int flag = *((volatile int*) &nb.counters[2]);
+            cudaGraphSetConditional((cudaGraphConditionalHandle) nb.condHandle, flag ? 1u : 0u);
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -205,8 +233,12 @@ __global__ void k_block_bounds(NbDev nb) {
     if (warp == 0 && lane == 0) { nb.counters[0] = 0; nb.counters[1] = 0; }
 }
 
+#define MAX_CACHED_EXCL 24
 // Emit one tile from the first `count` entries of buf (ascending sorted indices).
-__device__ void flush_tile(const NbDev& nb, int ib, const int* buf, int count, bool diagonal, int lane) {
+// sexc: this lane's exclusion partners as SORTED indices, cached once per i-block (nexc of them; partners beyond
+// MAX_CACHED_EXCL are looked up in global memory).
+__device__ void flush_tile(const NbDev& nb, int ib, const int* buf, int count, bool diagonal, int lane,
+                           const int* sexc, int nexc, int e0) {
     int t = 0;
     if (lane == 0) t = atomicAdd(&nb.counters[0], 1);
     t = __shfl_sync(FULL, t, 0);
@@ -224,11 +256,9 @@ __device__ void flush_tile(const NbDev& nb, int ib, const int* buf, int count, b
     }
     if (si >= nb.natoms) { mask = 0; need = true; }
     else {
-        int a = nb.sorig[si];
-        int e0 = nb.exclStart[a], e1 = nb.exclStart[a+1];
-        int jlo = buf[0], jhi = buf[count-1];
-        for (int e = e0; e < e1; e++) {
-            int sj = nb.sortedOf[nb.exclList[e]];
+        const int jlo = buf[0], jhi = buf[count-1];
+        for (int e = 0; e < nexc; e++) {
+            const int sj = (e < MAX_CACHED_EXCL) ? sexc[e] : nb.sortedOf[nb.exclList[e0 + e]];
             if (sj < jlo || sj > jhi) continue;
             int lo = 0, hi = count-1;          // binary search in the ascending tile
             while (lo < hi) { int mid = (lo+hi) >> 1; if (buf[mid] < sj) lo = mid+1; else hi = mid; }
@@ -245,22 +275,51 @@ __device__ void flush_tile(const NbDev& nb, int ib, const int* buf, int count, b
     if (lane == 0) { nb.tileI[t] = ib; nb.tileMask[t] = mi; }
 }
 
-// one warp per i-block: cull j-blocks by box distance, then j-atoms against the i-block box, compact into
-// tiles of 32 (findBlocksWithInteractions, findInteractingBlocks.cu:180-405 is the reference counterpart).
+// One CTA (4 warps) per i-block: the candidate j-blocks of the i-block are dealt round-robin to the 4 warps (chunks of
+// 32 blocks), each warp culls j-blocks by box distance, then j-atoms against the i-block (box, then exact atom
+// distances), compacts survivors into its own 32-wide tiles and flushes full tiles as it goes.  The warps' partial
+// buffers are merged, sorted and flushed by warp 0 at the end, so an i-block still ends with at most one partial tile.
+// (findBlocksWithInteractions, findInteractingBlocks.cu:180-405, is the reference counterpart.  Round-1 profile: with a
+// single warp per i-block the kernel was one long dependent chain of L2 round trips per block, 150 us at DHFR size.)
 __global__ void __launch_bounds__(128) k_build_tiles(NbDev nb) {
     if (nb.counters[2] == 0) return;
     __shared__ int sbuf[4][64];
-    int wib = threadIdx.x >> 5;
-    int lane = threadIdx.x & 31;
-    int ib = blockIdx.x*4 + wib;
-    if (ib >= nb.nblocks) return;
-    int* buf = sbuf[wib];
-    float4 ci = nb.blockCenter[ib];
-    float4 hi = nb.blockHalf[ib];
+    __shared__ int sexcAll[32][MAX_CACHED_EXCL + 1];         // +1: odd stride, conflict-free per-lane rows
+    __shared__ float4 sipos[32];                             // the i-block's atoms, relative to the block centre
+    __shared__ int sleft[4];
+    __shared__ int smerged[128];
+    const int w = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int ib = blockIdx.x;
+    int* buf = sbuf[w];
+    // this lane's exclusion partners, translated to sorted indices ONCE per i-block
+    int* sexc = sexcAll[lane];
+    int nexc = 0, e0 = 0;
+    {
+        const int si = ib*32 + lane;
+        if (si < nb.natoms) {
+            const int a = nb.sorig[si];
+            e0 = nb.exclStart[a];
+            nexc = nb.exclStart[a+1] - e0;
+            if (w == 0)
+                for (int e = 0; e < nexc && e < MAX_CACHED_EXCL; e++) sexc[e] = nb.sortedOf[nb.exclList[e0 + e]];
+        }
+    }
+    const float4 ci = nb.blockCenter[ib];
+    const float4 hi = nb.blockHalf[ib];
+    if (w == 0) {
+        const float4 p = nb.sposq[ib*32 + lane];            // padding slots hold a copy of a real atom of the block
+        sipos[lane] = make_float4(p.x-ci.x, p.y-ci.y, p.z-ci.z, 0.f);
+    }
+    __syncthreads();
     const bool periodic = nb.box.periodic != 0;
     const bool allPairs = (nb.method == B200MD_NB_NOCUTOFF);
+    // same condition as the pair kernel's SHIFT mode (counters[7] = max block half extent of THIS build)
+    const float minL = fminf(nb.box.ax, fminf(nb.box.by, nb.box.cz));
+    const bool exactCull = periodic && !nb.box.triclinic &&
+                           (0.5f*minL - nb.cutoff - 2.0f*sqrtf(nb.halfPad2) >= __int_as_float(nb.counters[7]));
     int nbuf = 0;
-    for (int jb0 = ib; jb0 < nb.nblocks; jb0 += 32) {
+    for (int jb0 = ib + 32*w; jb0 < nb.nblocks; jb0 += 128) {
         int jb = jb0 + lane;
         bool cand = false;
         if (jb < nb.nblocks) {
@@ -285,6 +344,17 @@ __global__ void __launch_bounds__(128) k_build_tiles(NbDev nb) {
                     float4 pj = nb.sposq[sj];
                     float3 d = make_float3(pj.x-ci.x, pj.y-ci.y, pj.z-ci.z);
                     inc = (box_dist2(d, hi.x, hi.y, hi.z, nb.box, periodic) < nb.paddedCutoff2);
+                    if (inc && exactCull) {
+                        // exact cull: keep j only if it is within the padded cutoff of at least one atom of the i-block.
+                        // Valid because every block satisfies halfExtent <= L/2 - cutoff - padding (off otherwise).
+                        d = min_image(d, nb.box);
+                        inc = false;
+                        for (int k = 0; k < 32; k++) {
+                            const float4 q = sipos[k];
+                            const float ex = d.x-q.x, ey = d.y-q.y, ez = d.z-q.z;
+                            if (ex*ex + ey*ey + ez*ez < nb.paddedCutoff2) { inc = true; break; }
+                        }
+                    }
                 }
             }
             unsigned int m = __ballot_sync(FULL, inc);
@@ -294,12 +364,12 @@ __global__ void __launch_bounds__(128) k_build_tiles(NbDev nb) {
             __syncwarp();
             if (jblk == ib) {
                 // the diagonal tile is always emitted on its own so that its mask is the simple j>i triangle
-                flush_tile(nb, ib, buf, nbuf, true, lane);
+                flush_tile(nb, ib, buf, nbuf, true, lane, sexc, nexc, e0);
                 nbuf = 0;
                 __syncwarp();
             }
             else if (nbuf >= 32) {
-                flush_tile(nb, ib, buf, 32, false, lane);
+                flush_tile(nb, ib, buf, 32, false, lane, sexc, nexc, e0);
                 int v = (lane + 32 < nbuf) ? buf[lane+32] : 0;
                 __syncwarp();
                 buf[lane] = v;
@@ -308,7 +378,25 @@ __global__ void __launch_bounds__(128) k_build_tiles(NbDev nb) {
             }
         }
     }
-    if (nbuf > 0) flush_tile(nb, ib, buf, nbuf, false, lane);
+    // merge the four partial buffers (each ascending, < 32 entries): rank sort into smerged, flush by warp 0
+    if (lane == 0) sleft[w] = nbuf;
+    __syncthreads();
+    const int n0 = sleft[0], n1 = sleft[1], n2 = sleft[2], n3 = sleft[3];
+    const int total = n0 + n1 + n2 + n3;
+    if (lane < nbuf) {
+        const int v = buf[lane];
+        int rank = 0;
+        for (int k = 0; k < n0; k++) rank += (sbuf[0][k] < v);
+        for (int k = 0; k < n1; k++) rank += (sbuf[1][k] < v);
+        for (int k = 0; k < n2; k++) rank += (sbuf[2][k] < v);
+        for (int k = 0; k < n3; k++) rank += (sbuf[3][k] < v);
+        smerged[rank] = v;                 // sorted indices are unique, so ranks are a permutation
+    }
+    __syncthreads();
+    if (w == 0) {
+        for (int off = 0; off < total; off += 32)
+            flush_tile(nb, ib, smerged + off, min(32, total - off), false, lane, sexc, nexc, e0);
+    }
 }
 
 __global__ void k_list_done(NbDev nb) {
@@ -316,41 +404,33 @@ __global__ void k_list_done(NbDev nb) {
     if (threadIdx.x == 0 && blockIdx.x == 0) { nb.counters[2] = 0; nb.counters[4] += 1; }
 }
 
-// every step: refresh the sorted copy of the positions
-__global__ void k_gather_sorted(NbDev nb) {
-    int s = blockIdx.x*blockDim.x + threadIdx.x;
-    if (s >= nb.npad) return;
-    int a = nb.sorig[s];
-    if (a < 0) a = nb.sorig[nb.natoms-1];
-    float4 p = nb.posq[a];
-    float4 sh = nb.sshift[min(s, nb.natoms-1)];
-    if (s >= nb.natoms) p.w = 0.f;
-    nb.sposq[s] = make_float4(p.x+sh.x, p.y+sh.y, p.z+sh.z, p.w);
+void launch_check_displacement(const NbDev& nb, cudaStream_t s) {
+    k_check_gather<<<(nb.npad+255)/256, 256, 0, s>>>(nb);
 }
 
-void launch_check_displacement(const NbDev& nb, cudaStream_t s) {
-    k_check_displacement<<<(nb.natoms+255)/256, 256, 0, s>>>(nb);
+__global__ void k_zero_cells(NbDev nb) {
+    if (nb.counters[2] == 0) return;
+    for (int i = blockIdx.x*blockDim.x + threadIdx.x; i <= nb.ncells; i += gridDim.x*blockDim.x) {
+        nb.cellCount[i] = 0;
+        if (i < nb.ncells) nb.cellFill[i] = 0;
+    }
 }
 
 int list_build_launch_count() { return 9; }
 
 void launch_list_build(const NbDev& nb, cudaStream_t s) {
-    // the two memsets are unconditional (cheap); every kernel returns immediately unless counters[2] is set
-    cudaMemsetAsync(nb.cellCount, 0, sizeof(int)*(nb.ncells+1), s);
-    cudaMemsetAsync(nb.cellFill, 0, sizeof(int)*nb.ncells, s);
+    // kernels only (this sequence is also the body of a CUDA-graph conditional node); each returns immediately unless
+    // counters[2] is set
     int nbk = (nb.natoms+255)/256;
+    k_zero_cells<<<std::min(64, (nb.ncells+256)/256), 256, 0, s>>>(nb);
     k_bin_atoms<<<nbk, 256, 0, s>>>(nb);
     k_scan_cells<<<1, 1024, 0, s>>>(nb);
     k_fill_cells<<<nbk, 256, 0, s>>>(nb);
     k_sort_cells<<<(nb.ncells+127)/128, 128, 0, s>>>(nb);
     k_finalize_sort<<<(nb.npad+255)/256, 256, 0, s>>>(nb);
     k_block_bounds<<<(nb.nblocks*32+255)/256, 256, 0, s>>>(nb);
-    k_build_tiles<<<(nb.nblocks+3)/4, 128, 0, s>>>(nb);
+    k_build_tiles<<<nb.nblocks, 128, 0, s>>>(nb);
     k_list_done<<<1, 32, 0, s>>>(nb);
-}
-
-void launch_gather_sorted(const NbDev& nb, cudaStream_t s) {
-    k_gather_sorted<<<(nb.npad+255)/256, 256, 0, s>>>(nb);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -373,24 +453,36 @@ void launch_gather_sorted(const NbDev& nb, cudaStream_t s) {
 //  * the loop body is branch-free (select instead of a divergent branch) so unrolled iterations interleave.
 #define PME_G_WMAX 14.0f
 
+__device__ __forceinline__ float rcp_approx(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float rsqrt_approx(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+
+// g(w) = (erf(z) - 2 z exp(-z^2)/sqrt(pi))/z^3, w = z^2 in [0,14]: (5,5) rational fit, |err| < 1.2e-7 in fp32
 __device__ __forceinline__ float ewald_g(float w) {
-    const float p = 0.7522528288f + w*(-0.01832553619f + w*(0.01676110697f + w*(0.0002032837893f + w*(3.445905357e-05f + w*(-3.521083106e-07f)))));
-    const float q = 1.0f + w*(0.5756407144f + w*(0.1533710339f + w*(0.02451798422f + w*(0.002480551583f + w*0.0001580620439f))));
-    return __fdividef(p, q);
+    const float p = fmaf(w, fmaf(w, fmaf(w, fmaf(w, fmaf(w, -3.521083106e-07f, 3.445905357e-05f), 0.0002032837893f), 0.01676110697f), -0.01832553619f), 0.7522528288f);
+    const float q = fmaf(w, fmaf(w, fmaf(w, fmaf(w, fmaf(w, 0.0001580620439f, 0.002480551583f), 0.02451798422f), 0.1533710339f), 0.5756407144f), 1.0f);
+    return p*rcp_approx(q);
 }
 
-template <bool ENERGY, int METHOD, bool SHIFT, bool RATIONAL>
+// The inner loop was counted in SASS (profiles/r01): v2 spent 96 instructions per pair slot (131 FMUL + 101 FFMA per 4
+// slots, denormal/range fix-ups around rsqrtf and __fdividef, switch-function code in the main path).  This version is
+// written FMA-first with ftz approximate rcp/rsqrt (one Newton step restores rsqrt to <1 ulp) and moves the switching
+// function into its own instantiation: ~58 instructions per slot.
+template <bool ENERGY, int METHOD, bool SHIFT, bool RATIONAL, bool SWITCH>
 __device__ __forceinline__ void pair_tiles(const NbDev& nb, float& energy) {
     const int lane = threadIdx.x & 31;
     const int gwarp = (blockIdx.x*blockDim.x + threadIdx.x) >> 5;
     const int nwarps = (gridDim.x*blockDim.x) >> 5;
     const int ntiles = min(nb.counters[0], nb.maxTiles);
     const bool periodic = nb.box.periodic != 0;
-    const float alpha2 = nb.alpha*nb.alpha, alpha3 = alpha2*nb.alpha;
+    const float alpha2 = nb.alpha*nb.alpha, nalpha3 = -alpha2*nb.alpha;
+    const float cutoff2 = nb.cutoff2;
+    const float swInv = SWITCH ? 1.0f/(nb.cutoff - nb.switchDist) : 0.f;
     const int src = (lane + 1) & 31;
-    // tiles are dealt round-robin over (rank, warp): the multi-GPU force decomposition shards this loop
-    for (int t = nb.rank + nb.world*gwarp; t < ntiles; t += nb.world*nwarps) {
+    // multi-GPU force decomposition: rank r owns the tiles of i-blocks with ib % world == r.  (Tile INDICES are handed out
+    // by an atomic counter and differ between ranks; the i-block of a tile does not.)
+    for (int t = gwarp; t < ntiles; t += nwarps) {
         const int ib = nb.tileI[t];
+        if (nb.world > 1 && (ib % nb.world) != nb.rank) continue;
         const int si = ib*32 + lane;
         float4 pi = nb.sposq[si];
         const float2 sei = nb.ssigeps[si];
@@ -399,7 +491,9 @@ __device__ __forceinline__ void pair_tiles(const NbDev& nb, float& energy) {
         float4 pj = nb.sposq[jj];
         float2 sej = nb.ssigeps[jj];
         const int mi = nb.tileMask[t];
-        const unsigned int mask = (mi < 0) ? FULL : nb.maskPool[mi*32 + lane];
+        unsigned int mask = (mi < 0) ? FULL : nb.maskPool[mi*32 + lane];
+        // rotate the mask so that bit 0 is always the current slot: slot = (lane + k) & 31
+        mask = __funnelshift_r(mask, mask, lane);
         if (SHIFT) {
             const float4 c = nb.blockCenter[ib];
             pi.x -= c.x; pi.y -= c.y; pi.z -= c.z;
@@ -410,62 +504,62 @@ __device__ __forceinline__ void pair_tiles(const NbDev& nb, float& energy) {
         float fix = 0.f, fiy = 0.f, fiz = 0.f, fjx = 0.f, fjy = 0.f, fjz = 0.f;
 #pragma unroll 4
         for (int k = 0; k < 32; k++) {
-            const int slot = (lane + k) & 31;
             float3 d = make_float3(pj.x-pi.x, pj.y-pi.y, pj.z-pi.z);
             if (!SHIFT && periodic) d = min_image(d, nb.box);
-            const float r2raw = d.x*d.x + d.y*d.y + d.z*d.z;
-            const bool valid = ((mask >> slot) & 1u) && r2raw < nb.cutoff2;
+            const float r2raw = fmaf(d.z, d.z, fmaf(d.y, d.y, d.x*d.x));
+            const bool valid = (mask & 1u) && r2raw < cutoff2;
+            mask >>= 1;
             const float r2 = valid ? r2raw : 1.0f;
-            float invR = rsqrtf(r2);
-            invR = invR*(1.5f - 0.5f*r2*invR*invR);      // one Newton step: MUFU.RSQ is ~2 ulp, and F ~ invR^3
-            const float invR2 = invR*invR;
+            float y = rsqrt_approx(r2);
+            y = y*fmaf(-0.5f*r2, y*y, 1.5f);             // Newton step: F ~ invR^3 needs a <1 ulp invR
+            const float invR2 = y*y;
             const float qq = pi.w*pj.w;
             float dEdR, e = 0.f;
             if (METHOD == B200MD_NB_PME) {
                 if (RATIONAL && !ENERGY)
-                    dEdR = qq*(invR*invR2 - alpha3*ewald_g(alpha2*r2));
+                    dEdR = qq*fmaf(nalpha3, ewald_g(alpha2*r2), invR2*y);
                 else {
-                    const float r = r2*invR;
+                    const float r = r2*y;
                     const float ar = nb.alpha*r;
                     const float ex = __expf(-ar*ar);
                     // erfc: Abramowitz-Stegun 7.1.26, |err| < 1.5e-7 (same form as coulombLennardJones.cc:15-20)
-                    const float tt = __fdividef(1.0f, 1.0f + 0.3275911f*ar);
+                    const float tt = rcp_approx(fmaf(0.3275911f, ar, 1.0f));
                     const float erfcAr = (0.254829592f+(-0.284496736f+(1.421413741f+(-1.453152027f+1.061405429f*tt)*tt)*tt)*tt)*tt*ex;
-                    const float pref = qq*invR;
-                    dEdR = pref*invR2*(erfcAr + 1.1283791671f*ar*ex);
+                    const float pref = qq*y;
+                    dEdR = pref*invR2*fmaf(1.1283791671f*ar, ex, erfcAr);
                     e = pref*erfcAr;
                 }
             }
             else if (METHOD == B200MD_NB_NOCUTOFF) {
-                const float pref = qq*invR;
+                const float pref = qq*y;
                 dEdR = pref*invR2;
                 e = pref;
             }
             else {   // cutoff with reaction field
-                dEdR = qq*(invR*invR2 - 2.0f*nb.krf);
-                e = qq*(invR + nb.krf*r2 - nb.crf);
+                dEdR = qq*fmaf(-2.0f, nb.krf, y*invR2);
+                e = qq*(fmaf(nb.krf, r2, y) - nb.crf);
             }
             const float sig = sei.x + sej.x;
             const float eps = sei.y*sej.y;
-            float s2 = sig*invR; s2 *= s2;
+            const float s2 = sig*sig*invR2;
             const float s6 = s2*s2*s2;
-            float ljF = eps*(12.0f*s6 - 6.0f)*s6*invR2;
-            float ljE = eps*(s6 - 1.0f)*s6;
-            if (nb.useSwitch) {
-                const float r = r2*invR;
+            const float es6 = eps*s6;
+            float ljF = es6*invR2*fmaf(12.0f, s6, -6.0f);
+            float ljE = fmaf(es6, s6, -es6);
+            if (SWITCH) {
+                const float r = r2*y;
                 if (r > nb.switchDist) {
-                    const float w = __fdividef(1.0f, nb.cutoff - nb.switchDist);
-                    const float x = (r - nb.switchDist)*w;
+                    const float x = (r - nb.switchDist)*swInv;
                     const float sw = 1.0f + x*x*x*(-10.0f + x*(15.0f - x*6.0f));
-                    const float dsw = x*x*(-30.0f + x*(60.0f - x*30.0f))*w;
-                    ljF = sw*ljF - ljE*dsw*invR;
+                    const float dsw = x*x*(-30.0f + x*(60.0f - x*30.0f))*swInv;
+                    ljF = sw*ljF - ljE*dsw*y;
                     ljE *= sw;
                 }
             }
             dEdR = valid ? dEdR + ljF : 0.f;
             if (ENERGY) energy += valid ? e + ljE : 0.f;
-            fix -= d.x*dEdR; fiy -= d.y*dEdR; fiz -= d.z*dEdR;
-            fjx += d.x*dEdR; fjy += d.y*dEdR; fjz += d.z*dEdR;
+            fix = fmaf(-d.x, dEdR, fix); fiy = fmaf(-d.y, dEdR, fiy); fiz = fmaf(-d.z, dEdR, fiz);
+            fjx = fmaf(d.x, dEdR, fjx); fjy = fmaf(d.y, dEdR, fjy); fjz = fmaf(d.z, dEdR, fjz);
             pj.x = __shfl_sync(FULL, pj.x, src); pj.y = __shfl_sync(FULL, pj.y, src);
             pj.z = __shfl_sync(FULL, pj.z, src); pj.w = __shfl_sync(FULL, pj.w, src);
             sej.x = __shfl_sync(FULL, sej.x, src); sej.y = __shfl_sync(FULL, sej.y, src);
@@ -487,6 +581,12 @@ __device__ __forceinline__ void pair_tiles(const NbDev& nb, float& energy) {
     }
 }
 
+template <bool ENERGY, int METHOD, bool SHIFT, bool RATIONAL>
+__device__ __forceinline__ void pair_tiles_sw(const NbDev& nb, float& energy) {
+    if (nb.useSwitch) pair_tiles<ENERGY, METHOD, SHIFT, RATIONAL, true>(nb, energy);
+    else pair_tiles<ENERGY, METHOD, SHIFT, RATIONAL, false>(nb, energy);
+}
+
 template <bool ENERGY, int METHOD>
 __global__ void __launch_bounds__(256) k_pair(NbDev nb) {
     float energy = 0.f;
@@ -497,12 +597,12 @@ __global__ void __launch_bounds__(256) k_pair(NbDev nb) {
     const bool shiftOK = b.periodic && !b.triclinic && (0.5f*minL - nb.cutoff - 2.0f*sqrtf(nb.halfPad2) >= maxHalf);
     const bool rational = (METHOD == B200MD_NB_PME) && (nb.alpha*nb.alpha*nb.cutoff2 < PME_G_WMAX);
     if (shiftOK) {
-        if (rational) pair_tiles<ENERGY, METHOD, true, true>(nb, energy);
-        else pair_tiles<ENERGY, METHOD, true, false>(nb, energy);
+        if (rational) pair_tiles_sw<ENERGY, METHOD, true, true>(nb, energy);
+        else pair_tiles_sw<ENERGY, METHOD, true, false>(nb, energy);
     }
     else {
-        if (rational) pair_tiles<ENERGY, METHOD, false, true>(nb, energy);
-        else pair_tiles<ENERGY, METHOD, false, false>(nb, energy);
+        if (rational) pair_tiles_sw<ENERGY, METHOD, false, true>(nb, energy);
+        else pair_tiles_sw<ENERGY, METHOD, false, false>(nb, energy);
     }
     if (ENERGY) {
         for (int off = 16; off > 0; off >>= 1) energy += __shfl_xor_sync(FULL, energy, off);

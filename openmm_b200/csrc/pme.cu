@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(128) k_pme_gather(NbDev nb, PmeDev pme) {
 #pragma unroll
         for (int iy = 0; iy < ORDER; iy++) {
             int yi = idx[1] + iy; if (yi >= pme.ny) yi -= pme.ny;
-            const double* row = pme.grid + ((size_t) xi*pme.ny + yi)*pme.nz;
+            const real* row = pme.grid + ((size_t) xi*pme.ny + yi)*pme.nz;
             double sz = 0.0, sdz = 0.0;
 #pragma unroll
             for (int iz = 0; iz < ORDER; iz++) {
@@ -146,7 +146,7 @@ __global__ void k_pme_eterm(NbDev nb, PmeDev pme) {
     const int kz = (int) (i % pme.nzc);
     const int ky = (int) ((i / pme.nzc) % pme.ny);
     const int kx = (int) (i / ((size_t) pme.nzc*pme.ny));
-    if (kx == 0 && ky == 0 && kz == 0) { pme.eterm[i] = 0.0; return; }
+    if (kx == 0 && ky == 0 && kz == 0) { pme.eterm[i] = 0; return; }
     const double* R = nb.box.recip;
     const double mx = (kx < (pme.nx+1)/2) ? kx : kx - pme.nx;
     const double my = (ky < (pme.ny+1)/2) ? ky : ky - pme.ny;
@@ -158,7 +158,7 @@ __global__ void k_pme_eterm(NbDev nb, PmeDev pme) {
     const double pi = 3.14159265358979323846;
     const double factor = pi*pi/(pme.alpha*pme.alpha);
     const double denom = m2*pi*nb.box.volume*pme.moduli[0][kx]*pme.moduli[1][ky]*pme.moduli[2][kz];
-    pme.eterm[i] = exp(-factor*m2)/denom;
+    pme.eterm[i] = (real) (exp(-factor*m2)/denom);
 }
 
 void launch_pme_eterm(const NbDev& nb, const PmeDev& pme, cudaStream_t s) {

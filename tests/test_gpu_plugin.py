@@ -108,5 +108,12 @@ def test_reference_own_test_bodies_pass_on_b200_platform(name):
     if not os.path.exists(exe):
         pytest.fail("%s not built (make -C plugin reftests where /root/reference exists)" % exe)
     env = dict(os.environ, B200_PLUGIN=PLUGIN)
-    p = subprocess.run([exe], capture_output=True, text=True, timeout=600, env=env)
+    for attempt in range(2):
+        # the reference's statistical assertions (ASSERT_USUALLY_*: "This test is stochastic and may occasionally fail")
+        # get one rerun, as devtools/run-ctest.py:86-118 does for the reference's own CI
+        p = subprocess.run([exe], capture_output=True, text=True, timeout=600, env=env)
+        if p.returncode == 0 and "Done" in p.stdout:
+            break
+        if "stochastic" not in p.stdout:
+            break
     assert p.returncode == 0 and "Done" in p.stdout, p.stdout[-2000:] + p.stderr[-2000:]
