@@ -56,6 +56,9 @@ struct b200md_ctx {
     std::string err;
     cudaStream_t stream = nullptr;
     cudaStream_t stream2 = nullptr;     // body capture of conditional graph nodes
+    cudaStream_t streamPme = nullptr;   // reciprocal space runs concurrently with direct space (high priority: its kernels are small)
+    cudaEvent_t evFork = nullptr, evJoin = nullptr;
+    bool overlapPme = true;
     bool useCond = true;
     // ---- host copy of the system definition ----
     std::vector<double> mass, charge, sigma, epsilon;
@@ -138,6 +141,12 @@ extern "C" int b200md_create(b200md_ctx** out, int device, int natoms) {
         CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
         CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
         if (getenv("B200MD_NO_COND")) c->useCond = false;
+        if (getenv("B200MD_NO_OVERLAP")) c->overlapPme = false;
+        int lo = 0, hi = 0;
+        CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CUDA_CHECK(cudaStreamCreateWithPriority(&c->streamPme, cudaStreamNonBlocking, hi));
+        CUDA_CHECK(cudaEventCreateWithFlags(&c->evFork, cudaEventDisableTiming));
+        CUDA_CHECK(cudaEventCreateWithFlags(&c->evJoin, cudaEventDisableTiming));
         c->mass.assign(natoms, 1.0);
         c->charge.assign(natoms, 0.0); c->sigma.assign(natoms, 1.0); c->epsilon.assign(natoms, 0.0);
         const char* pf = getenv("B200MD_PAD_FRACTION");
@@ -160,6 +169,9 @@ extern "C" void b200md_destroy(b200md_ctx* ctx) {
     if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
+    if (ctx->streamPme) cudaStreamDestroy(ctx->streamPme);
+    if (ctx->evFork) cudaEventDestroy(ctx->evFork);
+    if (ctx->evJoin) cudaEventDestroy(ctx->evJoin);
     delete ctx;
 }
 
@@ -777,20 +789,32 @@ static int enqueue_forces(b200md_ctx* c, int terms, bool energy) {
             launch_list_build(c->nb, s); launches += list_build_launch_count();
         }
     }
-    if (direct) { launch_pair(c->nb, energy, s); launches++; }
+    // Reciprocal space (spread -> FFT/convolution -> gather) and direct space (tile kernel, bonded terms) are independent
+    // until the integrator: fork them onto two streams (also inside the captured step graph).  Both accumulate into the
+    // same fixed-point force buffer, so the overlap cannot change the result.  Single-GPU only: with NCCL the collectives
+    // of one communicator must stay on one stream.
+    const bool fork = direct && recip && c->overlapPme && !(c->world > 1 && c->comm);
+    cudaStream_t sp = fork ? c->streamPme : s;
+    if (fork) {
+        CUDA_CHECK(cudaEventRecord(c->evFork, s));
+        CUDA_CHECK(cudaStreamWaitEvent(sp, c->evFork, 0));
+    }
     if (recip) {
-        launch_pme_spread(c->nb, c->pme, s); launches++;
+        launch_pme_spread(c->nb, c->pme, sp); launches++;
         if (c->world > 1 && c->comm) {
-            int rc = g_nccl.AllReduce(c->gridFixed.p, c->gridFixed.p, (size_t) c->pme.nx*c->pme.ny*c->pme.nz, NCCL_INT64, NCCL_SUM, c->comm, s);
+            int rc = g_nccl.AllReduce(c->gridFixed.p, c->gridFixed.p, (size_t) c->pme.nx*c->pme.ny*c->pme.nz, NCCL_INT64, NCCL_SUM, c->comm, sp);
             if (rc != 0) throw std::runtime_error("ncclAllReduce(grid) failed");
         }
-        launch_pme_fft_conv(c->nb, c->pme, energy && c->rank == 0, s); launches += pme_fft_launch_count(c->pme);
-        launch_pme_gather(c->nb, c->pme, s); launches++;
+        launch_pme_fft_conv(c->nb, c->pme, energy && c->rank == 0, sp); launches += pme_fft_launch_count(c->pme);
+        launch_pme_gather(c->nb, c->pme, sp); launches++;
     }
+    if (fork) CUDA_CHECK(cudaEventRecord(c->evJoin, sp));
+    if (direct) { launch_pair(c->nb, energy, s); launches++; }
     int bterms = terms & (B200MD_TERM_BONDS | B200MD_TERM_ANGLES | B200MD_TERM_TORSIONS);
     if (c->haveNb) bterms |= terms & B200MD_TERM_NB_DIRECT;
     const int nbonded = c->bd.nbonds + c->bd.nangles + c->bd.ntorsions + c->bd.nexc;
     if (bterms && nbonded > 0) { launch_bonded(c->nb, c->bd, bterms, energy, s); launches++; }
+    if (fork) CUDA_CHECK(cudaStreamWaitEvent(s, c->evJoin, 0));
     if (c->world > 1 && c->comm) {
         int rc = g_nccl.AllReduce(c->force.p, c->force.p, (size_t) 3*c->npad, NCCL_INT64, NCCL_SUM, c->comm, s);
         if (rc != 0) throw std::runtime_error("ncclAllReduce(force) failed");
