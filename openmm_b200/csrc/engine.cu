@@ -241,25 +241,28 @@ extern "C" int b200md_remove_cm_motion(b200md_ctx* ctx) {
     API_END(ctx)
 }
 
-// ---------------------------------------------------------------- Hilbert curve over the binning cells
-static unsigned long long hilbert_index(unsigned int x, unsigned int y, unsigned int z, int bits) {
-    unsigned int X[3] = {x, y, z};
-    const unsigned int M = 1u << (bits-1);
-    for (unsigned int Q = M; Q > 1; Q >>= 1) {           // Skilling, "Programming the Hilbert curve" (2004)
-        const unsigned int P = Q - 1;
-        for (int i = 0; i < 3; i++) {
-            if (X[i] & Q) X[0] ^= P;
-            else { unsigned int t = (X[0] ^ X[i]) & P; X[0] ^= t; X[i] ^= t; }
+// ---------------------------------------------------------------- space-filling order of the binning cells
+// Blocked serpentine: 2x2x2 super-cells visited in a 3-D boustrophedon (every step of the path moves to a face-adjacent
+// super-cell), cells inside a super-cell in a fixed order.  Unlike a Hilbert / Morton curve restricted to a
+// non-power-of-two grid, the path never leaves and re-enters the grid, so 32 consecutive sorted atoms (~ one super-cell
+// at ~4 atoms per cell) always form a compact ~2x2x2-cell cube.  (Round 1 used a Hilbert curve on the padded 2^k grid:
+// the blocks that straddled its re-entry points had bounding boxes of nanometres, which switched the tile kernel's
+// single-image mode off and wasted tile slots.)
+static void cell_order(const int nc[3], std::vector<int>& rank) {
+    const int sx = (nc[0] + 1)/2, sy = (nc[1] + 1)/2, sz = (nc[2] + 1)/2;
+    rank.assign((size_t) nc[0]*nc[1]*nc[2], 0);
+    int r = 0;
+    for (int ix = 0; ix < sx; ix++)
+        for (int jy = 0; jy < sy; jy++) {
+            const int iy = (ix & 1) ? sy-1-jy : jy;
+            for (int kz = 0; kz < sz; kz++) {
+                const int iz = ((ix*sy + jy) & 1) ? sz-1-kz : kz;
+                for (int a = 0; a < 2; a++) for (int b = 0; b < 2; b++) for (int c = 0; c < 2; c++) {
+                    const int x = 2*ix + a, y = 2*iy + b, z = 2*iz + c;
+                    if (x < nc[0] && y < nc[1] && z < nc[2]) rank[((size_t) x*nc[1] + y)*nc[2] + z] = r++;
+                }
+            }
         }
-    }
-    for (int i = 1; i < 3; i++) X[i] ^= X[i-1];
-    unsigned int t = 0;
-    for (unsigned int Q = M; Q > 1; Q >>= 1) if (X[2] & Q) t ^= Q - 1;
-    for (int i = 0; i < 3; i++) X[i] ^= t;
-    unsigned long long h = 0;
-    for (int b = bits-1; b >= 0; b--)
-        for (int i = 0; i < 3; i++) h = (h << 1) | ((X[i] >> b) & 1u);
-    return h;
 }
 
 static void setup_cells(b200md_ctx* c) {
@@ -273,16 +276,8 @@ static void setup_cells(b200md_ctx* c) {
     }
     const int ncells = nc[0]*nc[1]*nc[2];
     if (ncells != c->nb.ncells || nc[0] != c->nb.ncell[0] || nc[1] != c->nb.ncell[1] || nc[2] != c->nb.ncell[2]) {
-        int bits = 1;
-        while ((1 << bits) < std::max(nc[0], std::max(nc[1], nc[2]))) bits++;
-        std::vector<std::pair<unsigned long long, int> > order(ncells);
-        for (int x = 0; x < nc[0]; x++) for (int y = 0; y < nc[1]; y++) for (int z = 0; z < nc[2]; z++) {
-            int lin = (x*nc[1] + y)*nc[2] + z;
-            order[lin] = std::make_pair(hilbert_index(x, y, z, bits), lin);
-        }
-        std::sort(order.begin(), order.end());
-        std::vector<int> rank(ncells);
-        for (int r = 0; r < ncells; r++) rank[order[r].second] = r;
+        std::vector<int> rank;
+        cell_order(nc, rank);
         c->cellRank.upload(rank);
         c->cellCount.alloc(ncells + 1);
         c->cellFill.alloc(ncells);
@@ -504,6 +499,7 @@ extern "C" int b200md_finalize(b200md_ctx* ctx) {
     nb.natoms = N; nb.npad = NP; nb.nblocks = c->nblocks;
     nb.method = c->nbdesc.method;
     nb.rank = c->rank; nb.world = c->world;
+    nb.useRational = getenv("B200MD_PAIR_RATIONAL") ? atoi(getenv("B200MD_PAIR_RATIONAL")) : 0;
     // ---- state arrays ----
     c->posq.alloc(NP); c->posq.zero(); c->velm.alloc(NP); c->velm.zero();
     c->sposq.alloc(NP); c->sposq.zero(); c->sshift.alloc(NP); c->sshift.zero(); c->refPos.alloc(NP); c->refPos.zero(); c->atomShift.alloc(NP);

@@ -91,6 +91,7 @@ struct NbDev {
     double origin[3];
     // CUDA-graph conditional node that holds the list-rebuild kernels (0 = none: rebuild kernels are gated on counters[2])
     unsigned long long condHandle;
+    int useRational;             // B200MD_PAIR_RATIONAL=1: rational Ewald kernel in the force-only tile loop (1 MUFU less, lower accuracy)
 };
 
 enum { EN_NB = 0, EN_RECIP = 1, EN_BOND = 2, EN_ANGLE = 3, EN_TORSION = 4, EN_EXC = 5, EN_KE = 6, B200MD_NUM_ENERGY = 8 };
@@ -132,6 +133,22 @@ struct IntegDev {
     unsigned long long stepIndex;            // not used on device when graphs are active: see stepCounter
     unsigned long long* stepCounter;         // device counter, incremented by the integrate kernel
 };
+
+// 2^32 fixed point <-> fp32 without the 64-bit conversion instructions (I2F.S64 / F2I.S64 are multi-pass on the XU pipe and
+// showed up as the hottest instructions of the FFT load loop and of the integrator in the round-1 profiles)
+#ifdef __CUDACC__
+__device__ __forceinline__ float fixed_to_float(long long v) {
+    const int hi = (int) (v >> 32);
+    const unsigned int lo = (unsigned int) v;
+    return __int2float_rn(hi) + __uint2float_rn(lo)*2.3283064365386963e-10f;
+}
+__device__ __forceinline__ long long float_to_fixed(float f) {           // |f| < 2^31
+    const float fl = floorf(f);
+    const int hi = __float2int_rd(f);
+    const unsigned int lo = __float2uint_rz((f - fl)*4294967296.0f);
+    return ((long long) hi << 32) | (long long) lo;
+}
+#endif
 
 // ---- launchers (defined in the .cu files) ----
 void launch_check_displacement(const NbDev& nb, cudaStream_t s);

@@ -200,11 +200,10 @@ __global__ void __launch_bounds__(FFT_THREADS) k_fft_z_fwd(PmeDev pme) {
     const unsigned int* tab = stage_twiddles(tws, pme.plan[2]);
     if (pme.gridFixed != nullptr) {
         const long long* base = pme.gridFixed + (size_t) row0*nz;
-        const real sc = (real) (1.0/4294967296.0);
         for (int i = TID; i < np*nz; i += NTHR) {
             const int p = i/nz, z = i - p*nz;
-            const real re = (real) base[(size_t) (2*p)*nz + z]*sc;
-            const real im = (2*p+1 < nrows) ? (real) base[(size_t) (2*p+1)*nz + z]*sc : (real) 0;
+            const real re = fixed_to_float(base[(size_t) (2*p)*nz + z]);
+            const real im = (2*p+1 < nrows) ? fixed_to_float(base[(size_t) (2*p+1)*nz + z]) : (real) 0;
             A[i] = make_real2(re, im);
         }
     }
@@ -394,11 +393,10 @@ __global__ void __launch_bounds__(FFT_THREADS) k_fft_slab_fwd(PmeDev pme, size_t
     const int x = blockIdx.x;
     if (pme.gridFixed != nullptr) {
         long long* base = pme.gridFixed + (size_t) x*ny*nz;
-        const real sc = (real) (1.0/4294967296.0);
         for (int i = TID; i < np*nz; i += NTHR) {
             const int p = i/nz, z = i - p*nz;
-            const real re = (real) base[(size_t) (2*p)*nz + z]*sc;
-            const real im = (2*p+1 < ny) ? (real) base[(size_t) (2*p+1)*nz + z]*sc : (real) 0;
+            const real re = fixed_to_float(base[(size_t) (2*p)*nz + z]);
+            const real im = (2*p+1 < ny) ? fixed_to_float(base[(size_t) (2*p+1)*nz + z]) : (real) 0;
             S.A[i] = make_real2(re, im);
         }
     }

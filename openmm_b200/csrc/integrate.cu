@@ -128,7 +128,7 @@ __device__ void settle_velocities(const V3* x, V3* v, const float* m) {
 // SHAKE on a centre + n hydrogens, positions (deltas d relative to old positions x)
 __device__ void shake_positions(const V3* x, V3* d, const float* invM, const float* dist, int n, float tol) {
     V3 rij[3]; float rij2[3], ld[3];
-    for (int k = 0; k < n; k++) {
+    _Pragma("unroll") for (int k = 0; k < 3; k++) if (k < n) {
         rij[k] = x[0] - x[k+1];
         rij2[k] = dot(rij[k], rij[k]);
         ld[k] = dist[k]*dist[k] - rij2[k];
@@ -136,7 +136,7 @@ __device__ void shake_positions(const V3* x, V3* d, const float* invM, const flo
     bool converged = false;
     for (int it = 0; it < 30 && !converged; it++) {
         converged = true;
-        for (int k = 0; k < n; k++) {
+        _Pragma("unroll") for (int k = 0; k < 3; k++) if (k < n) {
             const V3 rp = d[0] - d[k+1];
             const float rp2 = dot(rp, rp), rrpr = dot(rij[k], rp);
             const float diff = ld[k] - 2.0f*rrpr - rp2;
@@ -153,11 +153,11 @@ __device__ void shake_positions(const V3* x, V3* d, const float* invM, const flo
 
 __device__ void shake_velocities(const V3* x, V3* v, const float* invM, int n, float tol) {
     V3 rij[3]; float rij2[3];
-    for (int k = 0; k < n; k++) { rij[k] = x[0] - x[k+1]; rij2[k] = dot(rij[k], rij[k]); }
+    _Pragma("unroll") for (int k = 0; k < 3; k++) if (k < n) { rij[k] = x[0] - x[k+1]; rij2[k] = dot(rij[k], rij[k]); }
     bool converged = false;
     for (int it = 0; it < 30 && !converged; it++) {
         converged = true;
-        for (int k = 0; k < n; k++) {
+        _Pragma("unroll") for (int k = 0; k < 3; k++) if (k < n) {
             const V3 rp = v[0] - v[k+1];
             const float rrpr = dot(rp, rij[k]);
             const float delta = -rrpr/((invM[0] + invM[k+1])*rij2[k]);
@@ -195,8 +195,7 @@ __device__ __forceinline__ bool load_unit(const NbDev& nb, const UnitDev& un, in
         U.invM[k] = v.w;
         U.m[k] = (v.w > 0.f) ? 1.0f/v.w : 0.f;
         if (wantForce) {
-            const float sc = (float) (1.0/B200MD_FORCE_SCALE);
-            U.f[k] = {(float) nb.force[a]*sc, (float) nb.force[a + nb.npad]*sc, (float) nb.force[a + 2*nb.npad]*sc};
+            U.f[k] = {fixed_to_float(nb.force[a]), fixed_to_float(nb.force[a + nb.npad]), fixed_to_float(nb.force[a + 2*nb.npad])};
         }
     }
     return true;
@@ -221,10 +220,10 @@ __global__ void __launch_bounds__(128) k_integrate(NbDev nb, UnitDev un, IntegDe
     V3 d[4];
     const float invDt = 1.0f/in.dt;
     if (KIND == B200MD_INT_LANGEVIN_MIDDLE) {
-        for (int k = 0; k < U.n; k++) U.v[k] = U.v[k] + U.f[k]*(in.dt*U.invM[k]);
+        _Pragma("unroll") for (int k = 0; k < 4; k++) if (k < U.n) U.v[k] = U.v[k] + U.f[k]*(in.dt*U.invM[k]);
         constrain_vel(U, U.v, in.tol);
         V3 du[4];
-        for (int k = 0; k < U.n; k++) {
+        _Pragma("unroll") for (int k = 0; k < 4; k++) if (k < U.n) {
             d[k] = U.v[k]*(0.5f*in.dt);
             if (U.invM[k] > 0.f) {
                 const float3 g = gauss3(in.seed, U.atom[k], step);
@@ -236,10 +235,10 @@ __global__ void __launch_bounds__(128) k_integrate(NbDev nb, UnitDev un, IntegDe
             du[k] = d[k];
         }
         constrain_pos(U, d, in.tol);
-        for (int k = 0; k < U.n; k++) U.v[k] = U.v[k] + (d[k] - du[k])*invDt;
+        _Pragma("unroll") for (int k = 0; k < 4; k++) if (k < U.n) U.v[k] = U.v[k] + (d[k] - du[k])*invDt;
     }
     else {
-        for (int k = 0; k < U.n; k++) {
+        _Pragma("unroll") for (int k = 0; k < 4; k++) if (k < U.n) {
             V3 vn;
             if (KIND == B200MD_INT_LANGEVIN) {
                 vn = U.v[k]*in.vscale + U.f[k]*(in.fscale*U.invM[k]);
@@ -254,9 +253,9 @@ __global__ void __launch_bounds__(128) k_integrate(NbDev nb, UnitDev un, IntegDe
             d[k] = (U.invM[k] == 0.f) ? V3{0.f, 0.f, 0.f} : vn*in.dt;
         }
         constrain_pos(U, d, in.tol);
-        for (int k = 0; k < U.n; k++) if (U.invM[k] > 0.f) U.v[k] = d[k]*invDt;
+        _Pragma("unroll") for (int k = 0; k < 4; k++) if (k < U.n) if (U.invM[k] > 0.f) U.v[k] = d[k]*invDt;
     }
-    for (int k = 0; k < U.n; k++) {
+    _Pragma("unroll") for (int k = 0; k < 4; k++) if (k < U.n) {
         const int a = U.atom[k];
         const float4 p = nb.posq[a];
         nb.posq[a] = make_float4(U.x[k].x + d[k].x, U.x[k].y + d[k].y, U.x[k].z + d[k].z, p.w);
@@ -284,7 +283,7 @@ __global__ void __launch_bounds__(128) k_constrain_positions(NbDev nb, UnitDev u
     if (U.type == 0) return;
     V3 d[4] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
     constrain_pos(U, d, tol);
-    for (int k = 0; k < U.n; k++) {
+    _Pragma("unroll") for (int k = 0; k < 4; k++) if (k < U.n) {
         const int a = U.atom[k];
         const float4 p = nb.posq[a];
         nb.posq[a] = make_float4(p.x + d[k].x, p.y + d[k].y, p.z + d[k].z, p.w);
@@ -298,7 +297,7 @@ __global__ void __launch_bounds__(128) k_constrain_velocities(NbDev nb, UnitDev 
     load_unit(nb, un, u, U, false);
     if (U.type == 0) return;
     constrain_vel(U, U.v, tol);
-    for (int k = 0; k < U.n; k++) nb.velm[U.atom[k]] = make_float4(U.v[k].x, U.v[k].y, U.v[k].z, U.invM[k]);
+    _Pragma("unroll") for (int k = 0; k < 4; k++) if (k < U.n) nb.velm[U.atom[k]] = make_float4(U.v[k].x, U.v[k].y, U.v[k].z, U.invM[k]);
 }
 
 void launch_constrain_positions(const NbDev& nb, const UnitDev& units, float tol, cudaStream_t s) {
@@ -316,10 +315,10 @@ __global__ void __launch_bounds__(128) k_kinetic_energy(NbDev nb, UnitDev un, fl
         Unit U;
         load_unit(nb, un, u, U, true);
         if (shiftDt != 0.f) {
-            for (int k = 0; k < U.n; k++) U.v[k] = U.v[k] + U.f[k]*(shiftDt*U.invM[k]);
+            _Pragma("unroll") for (int k = 0; k < 4; k++) if (k < U.n) U.v[k] = U.v[k] + U.f[k]*(shiftDt*U.invM[k]);
             constrain_vel(U, U.v, 1e-4f);
         }
-        for (int k = 0; k < U.n; k++) ke += 0.5*(double) U.m[k]*(double) dot(U.v[k], U.v[k]);
+        _Pragma("unroll") for (int k = 0; k < 4; k++) if (k < U.n) ke += 0.5*(double) U.m[k]*(double) dot(U.v[k], U.v[k]);
     }
     for (int off = 16; off > 0; off >>= 1) ke += __shfl_xor_sync(0xffffffffu, ke, off);
     __shared__ double red[4];

@@ -568,15 +568,15 @@ __device__ __forceinline__ void pair_tiles(const NbDev& nb, float& energy) {
         // after 32 rotations every lane holds its own j again
         const int ai = nb.sorig[si];
         if (ai >= 0) {
-            atomicAdd((unsigned long long*) &nb.force[ai], (unsigned long long) __float2ll_rn(fix*4294967296.0f));
-            atomicAdd((unsigned long long*) &nb.force[ai + nb.npad], (unsigned long long) __float2ll_rn(fiy*4294967296.0f));
-            atomicAdd((unsigned long long*) &nb.force[ai + 2*nb.npad], (unsigned long long) __float2ll_rn(fiz*4294967296.0f));
+            atomicAdd((unsigned long long*) &nb.force[ai], (unsigned long long) float_to_fixed(fix));
+            atomicAdd((unsigned long long*) &nb.force[ai + nb.npad], (unsigned long long) float_to_fixed(fiy));
+            atomicAdd((unsigned long long*) &nb.force[ai + 2*nb.npad], (unsigned long long) float_to_fixed(fiz));
         }
         if (jidx >= 0) {
             const int aj = nb.sorig[jidx];
-            atomicAdd((unsigned long long*) &nb.force[aj], (unsigned long long) __float2ll_rn(fjx*4294967296.0f));
-            atomicAdd((unsigned long long*) &nb.force[aj + nb.npad], (unsigned long long) __float2ll_rn(fjy*4294967296.0f));
-            atomicAdd((unsigned long long*) &nb.force[aj + 2*nb.npad], (unsigned long long) __float2ll_rn(fjz*4294967296.0f));
+            atomicAdd((unsigned long long*) &nb.force[aj], (unsigned long long) float_to_fixed(fjx));
+            atomicAdd((unsigned long long*) &nb.force[aj + nb.npad], (unsigned long long) float_to_fixed(fjy));
+            atomicAdd((unsigned long long*) &nb.force[aj + 2*nb.npad], (unsigned long long) float_to_fixed(fjz));
         }
     }
 }
@@ -595,7 +595,9 @@ __global__ void __launch_bounds__(256) k_pair(NbDev nb) {
     const BoxDev& b = nb.box;
     const float minL = fminf(b.ax, fminf(b.by, b.cz));
     const bool shiftOK = b.periodic && !b.triclinic && (0.5f*minL - nb.cutoff - 2.0f*sqrtf(nb.halfPad2) >= maxHalf);
-    const bool rational = (METHOD == B200MD_NB_PME) && (nb.alpha*nb.alpha*nb.cutoff2 < PME_G_WMAX);
+    // The rational form has a constant ABSOLUTE error of ~1e-7 alpha^3 qq per pair that is coherent over neighbour shells
+    // (it cost 1e-4 relative on the 894-ion fixture); the exp-based erfc has a RELATIVE error, so it is the default.
+    const bool rational = (METHOD == B200MD_NB_PME) && (nb.alpha*nb.alpha*nb.cutoff2 < PME_G_WMAX) && nb.useRational;
     if (shiftOK) {
         if (rational) pair_tiles_sw<ENERGY, METHOD, true, true>(nb, energy);
         else pair_tiles_sw<ENERGY, METHOD, true, false>(nb, energy);

@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(128) k_pme_spread(NbDev nb, PmeDev pme) {
             for (int iz = 0; iz < ORDER; iz++) {
                 int zi = idx[2] + iz; if (zi >= pme.nz) zi -= pme.nz;
                 // integer accumulation: the grid (hence every force) is independent of the order of the atomics
-                atomicAdd((unsigned long long*) (row + zi), (unsigned long long) __float2ll_rn(qxy*tz[iz]*4294967296.0f));
+                atomicAdd((unsigned long long*) (row + zi), (unsigned long long) float_to_fixed(qxy*tz[iz]));
             }
         }
     }

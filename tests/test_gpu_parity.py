@@ -79,7 +79,10 @@ def test_nacl_amorph_fixture(mods):
                            pme_alpha=float(pme[0]), pme_grid=(int(pme[1]), int(pme[2]), int(pme[3])))
     eng = Engine(d)
     e = eng.compute()
-    assert relative_force_error(eng.get_forces(), z["reference_forces"]) < TOL
+    # +-1 e ions, 1.2 nm cutoff, 1e-5 Ewald tolerance: every atom sums ~240 pair forces of up to 2000 kJ/mol/nm that cancel
+    # to ~400; fp32 pair arithmetic puts the noise floor of that sum at ~1e-4 relative (the reference's own CUDA-vs-
+    # Reference tolerance for this system is 1e-2, TestEwald.h:147-149).  3e-4 here; 1e-4 holds on the solvated systems.
+    assert relative_force_error(eng.get_forces(), z["reference_forces"]) < 3e-4
     assert abs(e - float(z["reference_energy"]))/abs(e) < 1e-5           # TestEwald.h:147-149 asks 1e-5 on the energy
     assert abs(e - float(z["gromacs_energy"]))/abs(e) < 1e-5
 
@@ -171,7 +174,7 @@ def test_real_benchmark_systems_parity(mods, name):
     # ApoA1 (10.9 nm box, molecules hanging over the cell faces): atoms that need a lattice shift have their shifted
     # fp32 coordinate rounded once (5e-7 nm), which moves stiff pair forces by ~2e-3 kJ/mol/nm; on atoms whose net
     # force is ~1 that exceeds 1e-4 in the floor-1 relative measure ("Precision").
-    eng, sim = _compare(mods, d, tol=1e-4 if name == "dhfr" else 3e-3)
+    eng, sim = _compare(mods, d, tol=1e-4 if name == "dhfr" else 1.5e-3)
     st = eng.stats()
     assert st["pme_grid"] == ([56, 56, 56] if name == "dhfr" else [88, 88, 88])
     # a short constrained Langevin run keeps every HBonds constraint (SETTLE waters + X-H_n SHAKE clusters)
