@@ -217,6 +217,11 @@ def main():
     alg_bytes = T*(32*4 + 4 + 4) + X*32*4 + NP*(16 + 8) + NP*24       # tiles (j list, i block, mask idx) + masks + posq/sigeps read + force write
     peak, peak_src = peaks()
     achieved = alg_bytes/(pair_ms*1e-3)/1e9
+    traffic = None          # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel
+    tpath = os.path.join(ROOT, "profiles", "r01_final_k_pair_summary.json")
+    if args.workload == "dhfr" and os.path.exists(tpath):
+        tj = json.load(open(tpath))
+        traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
     phases = {ph: round(eng.time_phase(ph, 30)*1e3, 2) for ph in ("pair", "pme_spread", "pme_fft_conv", "pme_gather", "bonded", "integrate", "list_build")}
     flops = T*1024*60.0
     line = {"metric": "ns/day", "value": nsday, "unit": "ns/day", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms/args.steps,
@@ -229,7 +234,7 @@ def main():
                     "note": "per bench step: set_positions+set_velocities from host doubles, %d MD steps, get_positions+get_velocities; final energy %.1f" % (md, e_final)},
             "gpu_launches": int(st1["kernel_launches"] - st0["kernel_launches"]),
             "roofline": {"kernel": "k_pair (direct-space 32x32 tile kernel)", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved/peak,
-                         "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": pair_ms,
+                         "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": pair_ms,
                          "tiles": T, "pairs_in_cutoff": st["pairs_in_cutoff"], "tile_fill": st["pairs_in_cutoff"]/(T*1024.0),
                          "fp32_tflops_algorithmic": flops/(pair_ms*1e-3)/1e12,
                          "note": "compute (FP32/SFU) bound kernel: arithmetic intensity ~%.0f flop/B; see DESIGN.md" % (flops/alg_bytes)},

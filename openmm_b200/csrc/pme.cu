@@ -83,7 +83,8 @@ __global__ void __launch_bounds__(128) k_pme_spread(NbDev nb, PmeDev pme) {
             for (int iz = 0; iz < ORDER; iz++) {
                 int zi = idx[2] + iz; if (zi >= pme.nz) zi -= pme.nz;
                 // integer accumulation: the grid (hence every force) is independent of the order of the atomics
-                atomicAdd((unsigned long long*) (row + zi), (unsigned long long) float_to_fixed(qxy*tz[iz]));
+                // |q theta theta theta| < 32: one F2I.S32 at scale 2^26, widened and shifted to the grid's 2^32 scale
+                atomicAdd((unsigned long long*) (row + zi), (unsigned long long) ((long long) __float2int_rn(qxy*tz[iz]*67108864.0f) << 6));
             }
         }
     }
