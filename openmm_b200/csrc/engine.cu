@@ -551,12 +551,12 @@ extern "C" int b200md_finalize(b200md_ctx* ctx) {
     // ---- tile capacity ----
     {
         const double nbk = c->nblocks;
-        double cap = nbk*(nbk+1)/2 + nbk + 64;
+        double cap = nbk*(nbk+1)/2 + 17*nbk + 64;
         if (nb.method != B200MD_NB_NOCUTOFF && c->haveBox) {
             const double vol = c->boxA[0]*c->boxB[1]*c->boxC[2];
             const double rp = rc*(1.0 + c->padFrac);
             const double pairs = 0.5*N*(N/vol)*(4.0/3.0*M_PI*rp*rp*rp);
-            const double est = pairs/(1024.0*0.15) + 2*nbk + 1024;
+            const double est = pairs/(1024.0*0.15) + 18*nbk + 1024;      // + unused slots of the per-warp reservation chunks
             cap = std::min(cap, est);
         }
         cap = std::min(cap, 16.0e6);
@@ -750,7 +750,27 @@ static int enqueue_forces(b200md_ctx* c, int terms, bool energy) {
     if (energy) CUDA_CHECK(cudaMemsetAsync(c->energy.p, 0, sizeof(double)*B200MD_NUM_ENERGY, s));
     const bool direct = (terms & B200MD_TERM_NB_DIRECT) && c->haveNb;
     const bool recip = (terms & B200MD_TERM_NB_RECIP) && c->haveNb && c->nb.method == B200MD_NB_PME;
-    if (direct || recip) {
+    // Reciprocal space (spread -> FFT/convolution -> gather, in USER atom order: independent of the neighbour list) and
+    // direct space (list check / rebuild, tile kernel, bonded terms) are independent until the integrator: fork them onto
+    // two streams (also inside the captured step graph).  Both accumulate into the same fixed-point force buffer, so the
+    // overlap cannot change the result.  Single-GPU only: with NCCL the collectives of one communicator stay on one stream.
+    const bool fork = direct && recip && c->overlapPme && !(c->world > 1 && c->comm);
+    cudaStream_t sp = fork ? c->streamPme : s;
+    if (fork) {
+        CUDA_CHECK(cudaEventRecord(c->evFork, s));
+        CUDA_CHECK(cudaStreamWaitEvent(sp, c->evFork, 0));
+    }
+    if (recip) {
+        launch_pme_spread(c->nb, c->pme, sp); launches++;
+        if (c->world > 1 && c->comm) {
+            int rc = g_nccl.AllReduce(c->gridFixed.p, c->gridFixed.p, (size_t) c->pme.nx*c->pme.ny*c->pme.nz, NCCL_INT64, NCCL_SUM, c->comm, sp);
+            if (rc != 0) throw std::runtime_error("ncclAllReduce(grid) failed");
+        }
+        launch_pme_fft_conv(c->nb, c->pme, energy && c->rank == 0, sp); launches += pme_fft_launch_count(c->pme);
+        launch_pme_gather(c->nb, c->pme, sp); launches++;
+    }
+    if (fork) CUDA_CHECK(cudaEventRecord(c->evJoin, sp));
+    if (direct) {
         cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
         cudaGraph_t graph = nullptr;
         const cudaGraphNode_t* deps = nullptr;
@@ -785,26 +805,6 @@ static int enqueue_forces(b200md_ctx* c, int terms, bool energy) {
             launch_list_build(c->nb, s); launches += list_build_launch_count();
         }
     }
-    // Reciprocal space (spread -> FFT/convolution -> gather) and direct space (tile kernel, bonded terms) are independent
-    // until the integrator: fork them onto two streams (also inside the captured step graph).  Both accumulate into the
-    // same fixed-point force buffer, so the overlap cannot change the result.  Single-GPU only: with NCCL the collectives
-    // of one communicator must stay on one stream.
-    const bool fork = direct && recip && c->overlapPme && !(c->world > 1 && c->comm);
-    cudaStream_t sp = fork ? c->streamPme : s;
-    if (fork) {
-        CUDA_CHECK(cudaEventRecord(c->evFork, s));
-        CUDA_CHECK(cudaStreamWaitEvent(sp, c->evFork, 0));
-    }
-    if (recip) {
-        launch_pme_spread(c->nb, c->pme, sp); launches++;
-        if (c->world > 1 && c->comm) {
-            int rc = g_nccl.AllReduce(c->gridFixed.p, c->gridFixed.p, (size_t) c->pme.nx*c->pme.ny*c->pme.nz, NCCL_INT64, NCCL_SUM, c->comm, sp);
-            if (rc != 0) throw std::runtime_error("ncclAllReduce(grid) failed");
-        }
-        launch_pme_fft_conv(c->nb, c->pme, energy && c->rank == 0, sp); launches += pme_fft_launch_count(c->pme);
-        launch_pme_gather(c->nb, c->pme, sp); launches++;
-    }
-    if (fork) CUDA_CHECK(cudaEventRecord(c->evJoin, sp));
     if (direct) { launch_pair(c->nb, energy, s); launches++; }
     int bterms = terms & (B200MD_TERM_BONDS | B200MD_TERM_ANGLES | B200MD_TERM_TORSIONS);
     if (c->haveNb) bterms |= terms & B200MD_TERM_NB_DIRECT;
@@ -1003,10 +1003,10 @@ extern "C" int b200md_get_stats(b200md_ctx* ctx, b200md_stats* out) {
     out->natoms = ctx->natoms; out->padded_atoms = ctx->npad; out->num_blocks = ctx->nblocks;
     if (ctx->finalized) {
         launch_count_pairs(ctx->nb, ctx->stream);
-        int h[8];
-        CUDA_CHECK(cudaMemcpyAsync(h, ctx->counters.p, sizeof(int)*8, cudaMemcpyDeviceToHost, ctx->stream));
+        int h[12];
+        CUDA_CHECK(cudaMemcpyAsync(h, ctx->counters.p, sizeof(int)*12, cudaMemcpyDeviceToHost, ctx->stream));
         CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
-        out->num_tiles = h[0]; out->num_mask_tiles = h[1]; out->overflow = h[3]; out->list_builds = h[4]; out->pairs_in_cutoff = h[5];
+        out->num_tiles = h[9]; out->num_mask_tiles = h[1]; out->overflow = h[3]; out->list_builds = h[4]; out->pairs_in_cutoff = h[5];
     }
     out->force_evals = ctx->forceEvals; out->kernel_launches = ctx->kernelLaunches;
     out->pme_grid[0] = ctx->pme.nx; out->pme_grid[1] = ctx->pme.ny; out->pme_grid[2] = ctx->pme.nz; out->ewald_alpha = ctx->pme.alpha;

@@ -77,10 +77,39 @@ __device__ __forceinline__ void fft_stage(const real2* __restrict__ in, real2* _
             dst[2*Ns] = make_real2(a.x - c.x, a.y - c.y);
             dst[3*Ns] = make_real2(b.x - id.x, b.y - id.y);
         }
+        else if (R & 1) {
+            // odd radix, conjugate-pair form: with s_t = x_t + x_{R-t}, d_t = x_t - x_{R-t} (t = 1..h, h = (R-1)/2)
+            //   X_q = x_0 + sum_t s_t cos(2 pi q t/R) -+ i sum_t d_t sin(2 pi q t/R),  X_{R-q} = conj-partner
+            // i.e. h*h real-coefficient MAC pairs instead of (R-1)^2 complex MACs (radix 7: 36 FMA instead of 168).
+            constexpr int H = (R - 1)/2;
+            real2 sm[H > 0 ? H : 1], df[H > 0 ? H : 1];
+            real2 x0 = v[0];
+            real2 sum0 = x0;
+#pragma unroll
+            for (int t = 1; t <= H; t++) {
+                sm[t-1] = make_real2(v[t].x + v[R-t].x, v[t].y + v[R-t].y);
+                df[t-1] = make_real2(v[t].x - v[R-t].x, v[t].y - v[R-t].y);
+                sum0.x += sm[t-1].x; sum0.y += sm[t-1].y;
+            }
+            dst[0] = sum0;
+#pragma unroll
+            for (int q = 1; q <= H; q++) {
+                real2 A = x0, B = make_real2(0, 0);
+#pragma unroll
+                for (int t = 1; t <= H; t++) {
+                    const real2 r = tw[((q*t) % R)*nb];      // (cos, -sin) of 2 pi (q t mod R)/R: warp-uniform broadcast
+                    A.x += sm[t-1].x*r.x; A.y += sm[t-1].y*r.x;
+                    B.x += df[t-1].x*r.y; B.y += df[t-1].y*r.y;
+                }
+                // forward: X_q = A + i*(B with r.y = -sin) -> A - i*sum d sin ; the inverse flips the sign of the sine part
+                const real2 iB = make_real2(-sgn*B.y, sgn*B.x);                  // i*B (forward) / -i*B (inverse)
+                dst[q*Ns] = make_real2(A.x + iB.x, A.y + iB.y);
+                dst[(R-q)*Ns] = make_real2(A.x - iB.x, A.y - iB.y);
+            }
+        }
         else {
-            // generic radix: the output loop is ROLLED (one copy of the R-1 MACs, executed R times, roots re-read from
-            // shared memory as warp-uniform broadcasts) -- a fully unrolled R x R butterfly is ~4R^2 instructions that
-            // each warp executes once, which made these kernels instruction-fetch bound
+            // other even radices (6, 8, 10, ...: the planner avoids them): generic, output loop ROLLED, roots re-read from
+            // shared memory as warp-uniform broadcasts
 #pragma unroll 1
             for (int q = 0; q < R; q++) {
                 real2 acc = v[0];
@@ -144,7 +173,9 @@ static int best_cost(int n, int* radix, int depth) {
     int best = 1 << 28, sub[B200MD_MAX_FFT_STAGES];
     for (int r = 2; r <= B200MD_MAX_RADIX && r <= n; r++) {
         if (n % r) continue;
-        const int stageCost = (r == 2 ? 2 : (r == 4 ? 3 : 2*r)) + 3;      // radix 2 / 4 have multiplication-free butterflies
+        // radix 2 / 4: multiplication-free butterflies; odd radices: conjugate-pair form (~r/2 MACs per point); other even
+        // radices fall back to the generic r MACs per point and are avoided
+        const int stageCost = (r == 2 ? 2 : (r == 4 ? 3 : ((r & 1) ? (r+1)/2 + 1 : 2*r))) + 3;
         int c = stageCost + best_cost(n/r, sub, depth+1);
         if (c < best) {
             best = c;

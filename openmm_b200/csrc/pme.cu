@@ -59,9 +59,10 @@ __global__ void __launch_bounds__(128) k_pme_spread(NbDev nb, PmeDev pme) {
     const int per = (nb.natoms + nb.world - 1)/nb.world;
     const int s = nb.rank*per + blockIdx.x*blockDim.x + threadIdx.x;
     if (s >= min(nb.natoms, (nb.rank+1)*per)) return;
-    // the user-order (never lattice-shifted) coordinate: the fractional position is formed in double, so the grid
-    // index/fraction is exact for fp32 inputs wherever the atom sits relative to the primary cell
-    const float4 p = nb.posq[nb.sorig[s]];
+    // USER order and the user-order (never lattice-shifted) coordinate: reciprocal space then does not depend on the
+    // neighbour list at all and runs concurrently with the list rebuild; the fractional position is formed in double, so
+    // the grid index/fraction is exact for fp32 inputs wherever the atom sits relative to the primary cell
+    const float4 p = nb.posq[s];
     if (p.w == 0.f) return;
     int idx[3];
     float fr[3];
@@ -94,7 +95,7 @@ __global__ void __launch_bounds__(128) k_pme_gather(NbDev nb, PmeDev pme) {
     const int per = (nb.natoms + nb.world - 1)/nb.world;
     const int s = nb.rank*per + blockIdx.x*blockDim.x + threadIdx.x;
     if (s >= min(nb.natoms, (nb.rank+1)*per)) return;
-    const float4 p = nb.posq[nb.sorig[s]];
+    const float4 p = nb.posq[s];
     if (p.w == 0.f) return;
     int idx[3];
     float fr[3];
@@ -131,7 +132,7 @@ __global__ void __launch_bounds__(128) k_pme_gather(NbDev nb, PmeDev pme) {
     const double Fx = -q*(gx*R[0]);
     const double Fy = -q*(gx*R[3] + gy*R[4]);
     const double Fz = -q*(gx*R[6] + gy*R[7] + gz*R[8]);
-    const int a = nb.sorig[s];
+    const int a = s;
     atomicAdd((unsigned long long*) &nb.force[a], (unsigned long long) __double2ll_rn(Fx*B200MD_FORCE_SCALE));
     atomicAdd((unsigned long long*) &nb.force[a + nb.npad], (unsigned long long) __double2ll_rn(Fy*B200MD_FORCE_SCALE));
     atomicAdd((unsigned long long*) &nb.force[a + 2*nb.npad], (unsigned long long) __double2ll_rn(Fz*B200MD_FORCE_SCALE));

@@ -38,7 +38,8 @@ def _compare(mods, desc, pme=None, tol=TOL, etol=TOL):
 
 
 # ---- the bespoke FFT against numpy (template: platforms/cuda/tests/TestCudaFFT3D.cpp:52-135, same odd sizes) ----
-@pytest.mark.parametrize("shape", [(28, 25, 30), (28, 25, 25), (25, 28, 25), (25, 25, 28), (21, 25, 27), (56, 56, 56), (88, 88, 88), (90, 90, 90), (128, 128, 128), (6, 6, 6)])
+@pytest.mark.parametrize("shape", [(28, 25, 30), (28, 25, 25), (25, 28, 25), (25, 25, 28), (21, 25, 27), (56, 56, 56), (88, 88, 88), (90, 90, 90), (128, 128, 128), (6, 6, 6),
+                                   (26, 39, 13), (27, 45, 33), (12, 40, 24), (144, 20, 36)])
 def test_fft3d_matches_numpy(mods, shape):
     _, _, engine, _, _ = mods
     rng = np.random.default_rng(sum(shape))
