@@ -82,6 +82,8 @@ struct b200md_ctx {
     DevBuf<int> sorig, sortedOf, cellRank, cellCount, cellFill, atomCell, tmpSorted, tileI, tileJ, tileMask, counters, exclStart, exclList;
     DevBuf<unsigned int> maskPool;
     DevBuf<unsigned long long> stepCounter;
+    DevBuf<unsigned int> blocksDone;
+    bool stepStateValid = false;         // fused step path: force buffer zeroed and cm accumulator primed
     DevBuf<real> grid, eterm;
     DevBuf<long long> gridFixed;
     DevBuf<real2> cgrid;
@@ -235,6 +237,7 @@ extern "C" int b200md_set_cm_remover(b200md_ctx* ctx, int freq) {
 
 extern "C" int b200md_remove_cm_motion(b200md_ctx* ctx) {
     API_BEGIN(ctx)
+    ctx->stepStateValid = false;
     require(ctx->finalized, "remove_cm_motion before finalize");
     launch_remove_cm(ctx->nb, ctx->cmScratch.p, ctx->stream);
     ctx->kernelLaunches += 2;
@@ -505,7 +508,8 @@ extern "C" int b200md_finalize(b200md_ctx* ctx) {
     c->sposq.alloc(NP); c->sposq.zero(); c->sshift.alloc(NP); c->sshift.zero(); c->refPos.alloc(NP); c->refPos.zero(); c->atomShift.alloc(NP);
     c->sigeps.alloc(NP); c->ssigeps.alloc(NP); c->ssigeps.zero();
     c->force.alloc((size_t) 3*NP); c->force.zero();
-    c->energy.alloc(B200MD_NUM_ENERGY); c->energy.zero(); c->cmScratch.alloc(4);
+    c->energy.alloc(B200MD_NUM_ENERGY); c->energy.zero(); c->cmScratch.alloc(12); c->cmScratch.zero();
+    c->blocksDone.alloc(1); c->blocksDone.zero();
     c->sorig.alloc(NP); c->sortedOf.alloc(NP); c->atomCell.alloc(NP); c->tmpSorted.alloc(NP);
     c->blockCenter.alloc(c->nblocks); c->blockHalf.alloc(c->nblocks);
     c->counters.alloc(16); c->counters.zero();
@@ -586,6 +590,7 @@ extern "C" int b200md_finalize(b200md_ctx* ctx) {
     c->finalized = true;
     apply_box(c);
     c->integ.stepCounter = c->stepCounter.p;
+    c->integ.fused = 0; c->integ.cmEveryStep = 0; c->integ.cmScratch = c->cmScratch.p; c->integ.blocksDone = c->blocksDone.p;
     API_END(ctx)
 }
 
@@ -633,6 +638,7 @@ extern "C" int b200md_update_bonded_params(b200md_ctx* ctx, int kind, int n, con
 // ---------------------------------------------------------------- state
 extern "C" int b200md_set_positions(b200md_ctx* ctx, const double* x) {
     API_BEGIN(ctx)
+    ctx->stepStateValid = false;
     require(ctx->finalized, "set_positions before finalize");
     const int N = ctx->natoms;
     const double sk = std::sqrt(B200MD_ONE_4PI_EPS0);
@@ -664,6 +670,7 @@ extern "C" int b200md_get_positions(b200md_ctx* ctx, double* x) {
 }
 extern "C" int b200md_set_velocities(b200md_ctx* ctx, const double* v) {
     API_BEGIN(ctx)
+    ctx->stepStateValid = false;
     require(ctx->finalized, "set_velocities before finalize");
     ctx->hbuf4.resize(ctx->npad);
     for (int i = 0; i < ctx->npad; i++) ctx->hbuf4[i] = make_float4(0, 0, 0, 0);
@@ -724,6 +731,7 @@ extern "C" int64_t b200md_checkpoint_save(b200md_ctx* ctx, void* buf, int64_t ca
 }
 extern "C" int b200md_checkpoint_load(b200md_ctx* ctx, const void* buf, int64_t size) {
     API_BEGIN(ctx)
+    ctx->stepStateValid = false;
     const int64_t need = sizeof(CkptHeader) + 2*sizeof(float4)*(int64_t) ctx->npad;
     require(size >= need, "checkpoint blob too small");
     CkptHeader h; memcpy(&h, buf, sizeof(h));
@@ -743,10 +751,10 @@ extern "C" int b200md_checkpoint_load(b200md_ctx* ctx, const void* buf, int64_t 
 
 // ---------------------------------------------------------------- force evaluation
 // Enqueue one force evaluation on the stream (no host sync).  Returns the number of kernels launched.
-static int enqueue_forces(b200md_ctx* c, int terms, bool energy) {
+static int enqueue_forces(b200md_ctx* c, int terms, bool energy, bool forcesAlreadyZero = false) {
     int launches = 0;
     cudaStream_t s = c->stream;
-    CUDA_CHECK(cudaMemsetAsync(c->force.p, 0, sizeof(long long)*3*c->npad, s));
+    if (!forcesAlreadyZero) CUDA_CHECK(cudaMemsetAsync(c->force.p, 0, sizeof(long long)*3*c->npad, s));
     if (energy) CUDA_CHECK(cudaMemsetAsync(c->energy.p, 0, sizeof(double)*B200MD_NUM_ENERGY, s));
     const bool direct = (terms & B200MD_TERM_NB_DIRECT) && c->haveNb;
     const bool recip = (terms & B200MD_TERM_NB_RECIP) && c->haveNb && c->nb.method == B200MD_NB_PME;
@@ -832,6 +840,7 @@ static void check_flags(b200md_ctx* c) {
 
 extern "C" int b200md_compute(b200md_ctx* ctx, int terms, int want_forces, double* energy) {
     API_BEGIN(ctx)
+    ctx->stepStateValid = false;
     (void) want_forces;
     require(ctx->finalized, "compute before finalize");
     const bool wantE = energy != nullptr;
@@ -872,6 +881,7 @@ extern "C" int b200md_set_integrator(b200md_ctx* ctx, int kind, double dt, doubl
     in.fscale = (float) (friction == 0 ? dt : (1-vscale)/friction);
     in.noisescale = (float) (kind == B200MD_INT_LANGEVIN_MIDDLE ? std::sqrt(1-vscale*vscale) : std::sqrt(kT*(1-vscale*vscale)));
     in.stepCounter = ctx->stepCounter.p;
+    in.fused = 0; in.cmEveryStep = 0; in.cmScratch = ctx->cmScratch.p; in.blocksDone = ctx->blocksDone.p;
     ctx->dt = dt; ctx->temperature = temperature; ctx->friction = friction;
     ctx->haveIntegrator = true;
     invalidate_graph(ctx);
@@ -879,15 +889,21 @@ extern "C" int b200md_set_integrator(b200md_ctx* ctx, int kind, double dt, doubl
 }
 
 static int enqueue_step(b200md_ctx* c) {
-    int launches = 0;
-    if (c->cmFreq == 1) { launch_remove_cm(c->nb, c->cmScratch.p, c->stream); launches += 2; }   // every step: part of the graph
-    launches += enqueue_forces(c, B200MD_TERM_ALL, false);
-    launch_integrate(c->nb, c->units, c->integ, c->stream); launches += 2;
+    // the fused step: the integrate kernel also removes the centre-of-mass motion (frequency 1), zeroes the force buffer
+    // for the next step and advances the step counter, so a step is: [check] [rebuild?] pair bonded || spread fft gather ; integrate
+    int launches = enqueue_forces(c, B200MD_TERM_ALL, false, true);
+    IntegDev in = c->integ;
+    in.fused = 1;
+    in.cmEveryStep = (c->cmFreq == 1) ? 1 : 0;
+    in.cmScratch = c->cmScratch.p;
+    in.blocksDone = c->blocksDone.p;
+    launch_integrate(c->nb, c->units, in, c->stream); launches += 1;
     return launches;
 }
 
 extern "C" int b200md_integrate_only(b200md_ctx* ctx) {
     API_BEGIN(ctx)
+    ctx->stepStateValid = false;
     require(ctx->finalized && ctx->haveIntegrator, "integrate before finalize / set_integrator");
     launch_integrate(ctx->nb, ctx->units, ctx->integ, ctx->stream);
     ctx->kernelLaunches += 2;
@@ -914,6 +930,15 @@ extern "C" int b200md_step(b200md_ctx* ctx, int nsteps) {
     require(ctx->finalized && ctx->haveIntegrator, "step before finalize / set_integrator");
     b200md_ctx* c = ctx;
     int remaining = nsteps;
+    if (!c->stepStateValid) {
+        CUDA_CHECK(cudaMemsetAsync(c->force.p, 0, sizeof(long long)*3*c->npad, c->stream));
+        if (c->cmFreq == 1) {
+            IntegDev in = c->integ;
+            in.cmScratch = c->cmScratch.p;
+            launch_cm_prime(c->nb, in, c->stream);
+        }
+        c->stepStateValid = true;
+    }
     while (remaining > 0) {
         if (c->cmFreq > 1 && c->stepCount % c->cmFreq == 0) { launch_remove_cm(c->nb, c->cmScratch.p, c->stream); c->kernelLaunches += 2; }
         int done = 1;
@@ -966,6 +991,7 @@ extern "C" int b200md_apply_constraints(b200md_ctx* ctx, double tol) {
 }
 extern "C" int b200md_apply_velocity_constraints(b200md_ctx* ctx, double tol) {
     API_BEGIN(ctx)
+    ctx->stepStateValid = false;
     launch_constrain_velocities(ctx->nb, ctx->units, (float) tol, ctx->stream);
     ctx->kernelLaunches++;
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));

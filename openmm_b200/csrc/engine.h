@@ -132,6 +132,10 @@ struct IntegDev {
     unsigned int seed;
     unsigned long long stepIndex;            // not used on device when graphs are active: see stepCounter
     unsigned long long* stepCounter;         // device counter, incremented by the integrate kernel
+    int fused;                               // step path: zero forces, fused CM removal, last block advances the counter
+    int cmEveryStep;                         // CMMotionRemover with frequency 1
+    double* cmScratch;                       // [3][4] rotating momentum/mass accumulators
+    unsigned int* blocksDone;
 };
 
 // 2^32 fixed point <-> fp32 without the 64-bit conversion instructions (I2F.S64 / F2I.S64 are multi-pass on the XU pipe and
@@ -175,3 +179,4 @@ void launch_constrain_positions(const NbDev& nb, const UnitDev& units, float tol
 void launch_constrain_velocities(const NbDev& nb, const UnitDev& units, float tol, cudaStream_t s);
 void launch_kinetic_energy(const NbDev& nb, const UnitDev& units, const IntegDev& integ, float shiftDt, cudaStream_t s);
 void launch_remove_cm(const NbDev& nb, double* scratch, cudaStream_t s);
+void launch_cm_prime(const NbDev& nb, const IntegDev& integ, cudaStream_t s);

@@ -210,15 +210,37 @@ __device__ __forceinline__ void constrain_vel(const Unit& U, V3* v, float tol) {
     else if (U.type == 2) shake_velocities(U.x, v, U.invM, U.n-1, tol);
 }
 
+// Fused epilogue work (in.fused != 0, the b200md_step path):
+//  * centre-of-mass motion removal (CMMotionRemover, frequency 1): the momentum of the velocities this kernel WRITES is
+//    reduced into cm[(step+1)%3]; the next step subtracts cm[step%3]/mass before integrating (same velocities, so the same
+//    result as removing it at the start of that step, ReferenceKernels RemoveCMMotion); cm[(step+2)%3] is zeroed for reuse.
+//  * the force buffer is zeroed after it has been read (saves the memset node at the head of the next step's graph).
+//  * the last block to finish advances the step counter (saves a 1-thread kernel).
 template <int KIND>
 __global__ void __launch_bounds__(128) k_integrate(NbDev nb, UnitDev un, IntegDev in) {
     const int u = blockIdx.x*blockDim.x + threadIdx.x;
-    if (u >= un.nunits) return;
-    Unit U;
-    load_unit(nb, un, u, U, true);
+    const bool active = u < un.nunits;
     const unsigned long long step = *in.stepCounter;
+    Unit U;
+    U.n = 0;
     V3 d[4];
     const float invDt = 1.0f/in.dt;
+    const bool cmFused = in.fused && in.cmEveryStep;
+    V3 vcm = {0.f, 0.f, 0.f};
+    if (cmFused) {
+        const double* c = in.cmScratch + 4*(step % 3ull);
+        const double im = (c[3] > 0.0) ? 1.0/c[3] : 0.0;
+        vcm = {(float) (c[0]*im), (float) (c[1]*im), (float) (c[2]*im)};
+    }
+    if (active) {
+    load_unit(nb, un, u, U, true);
+    if (in.fused) {
+        _Pragma("unroll") for (int k = 0; k < 4; k++) if (k < U.n) {
+            const int a = U.atom[k];
+            nb.force[a] = 0; nb.force[a + nb.npad] = 0; nb.force[a + 2*nb.npad] = 0;
+            if (U.invM[k] > 0.f) U.v[k] = U.v[k] - vcm;
+        }
+    }
     if (KIND == B200MD_INT_LANGEVIN_MIDDLE) {
         _Pragma("unroll") for (int k = 0; k < 4; k++) if (k < U.n) U.v[k] = U.v[k] + U.f[k]*(in.dt*U.invM[k]);
         constrain_vel(U, U.v, in.tol);
@@ -261,9 +283,72 @@ __global__ void __launch_bounds__(128) k_integrate(NbDev nb, UnitDev un, IntegDe
         nb.posq[a] = make_float4(U.x[k].x + d[k].x, U.x[k].y + d[k].y, U.x[k].z + d[k].z, p.w);
         nb.velm[a] = make_float4(U.v[k].x, U.v[k].y, U.v[k].z, U.invM[k]);
     }
+    }   // active
+    if (!in.fused) return;
+    if (cmFused) {
+        double px = 0, py = 0, pz = 0, m = 0;
+        _Pragma("unroll") for (int k = 0; k < 4; k++) if (k < U.n && U.invM[k] > 0.f) {
+            const double mk = U.m[k];
+            px += mk*U.v[k].x; py += mk*U.v[k].y; pz += mk*U.v[k].z; m += mk;
+        }
+        for (int off = 16; off > 0; off >>= 1) {
+            px += __shfl_xor_sync(0xffffffffu, px, off); py += __shfl_xor_sync(0xffffffffu, py, off);
+            pz += __shfl_xor_sync(0xffffffffu, pz, off); m += __shfl_xor_sync(0xffffffffu, m, off);
+        }
+        __shared__ double red[4][4];
+        if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5][0] = px; red[threadIdx.x >> 5][1] = py; red[threadIdx.x >> 5][2] = pz; red[threadIdx.x >> 5][3] = m; }
+        __syncthreads();
+        if (threadIdx.x < 4) {
+            double t = 0;
+            for (int w = 0; w < (int) (blockDim.x >> 5); w++) t += red[w][threadIdx.x];
+            atomicAdd(&in.cmScratch[4*((step + 1ull) % 3ull) + threadIdx.x], t);
+            if (blockIdx.x == 0) in.cmScratch[4*((step + 2ull) % 3ull) + threadIdx.x] = 0.0;
+        }
+    }
+    // last block to finish: advance the step counter
+    __shared__ int last;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        last = (atomicAdd(in.blocksDone, 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (last && threadIdx.x == 0) {
+        *in.blocksDone = 0u;
+        *in.stepCounter = step + 1ull;
+    }
 }
 
 __global__ void k_step_advance(IntegDev in) { *in.stepCounter += 1ull; }
+
+// momentum of the current velocities into cm[step % 3] (validates the fused scheme after the state was set from outside)
+__global__ void __launch_bounds__(256) k_cm_prime(NbDev nb, IntegDev in) {
+    const unsigned long long step = *in.stepCounter;
+    double* c = in.cmScratch + 4*(step % 3ull);
+    const int a = blockIdx.x*blockDim.x + threadIdx.x;
+    double px = 0, py = 0, pz = 0, m = 0;
+    if (a < nb.natoms) {
+        const float4 v = nb.velm[a];
+        if (v.w > 0.f) { m = 1.0/v.w; px = m*v.x; py = m*v.y; pz = m*v.z; }
+    }
+    for (int off = 16; off > 0; off >>= 1) {
+        px += __shfl_xor_sync(0xffffffffu, px, off); py += __shfl_xor_sync(0xffffffffu, py, off);
+        pz += __shfl_xor_sync(0xffffffffu, pz, off); m += __shfl_xor_sync(0xffffffffu, m, off);
+    }
+    __shared__ double red[8][4];
+    if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5][0] = px; red[threadIdx.x >> 5][1] = py; red[threadIdx.x >> 5][2] = pz; red[threadIdx.x >> 5][3] = m; }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        double t = 0;
+        for (int w = 0; w < 8; w++) t += red[w][threadIdx.x];
+        atomicAdd(&c[threadIdx.x], t);
+    }
+}
+
+void launch_cm_prime(const NbDev& nb, const IntegDev& integ, cudaStream_t s) {
+    cudaMemsetAsync(integ.cmScratch, 0, 12*sizeof(double), s);
+    k_cm_prime<<<(nb.natoms + 255)/256, 256, 0, s>>>(nb, integ);
+}
 
 void launch_integrate(const NbDev& nb, const UnitDev& units, const IntegDev& integ, cudaStream_t s) {
     // 64-thread blocks: at DHFR size (8k units) 128-thread blocks fill only 65 of the 148 SMs
@@ -271,7 +356,7 @@ void launch_integrate(const NbDev& nb, const UnitDev& units, const IntegDev& int
     if (integ.kind == B200MD_INT_VERLET) k_integrate<B200MD_INT_VERLET><<<grid, 64, 0, s>>>(nb, units, integ);
     else if (integ.kind == B200MD_INT_LANGEVIN) k_integrate<B200MD_INT_LANGEVIN><<<grid, 64, 0, s>>>(nb, units, integ);
     else k_integrate<B200MD_INT_LANGEVIN_MIDDLE><<<grid, 64, 0, s>>>(nb, units, integ);
-    k_step_advance<<<1, 1, 0, s>>>(integ);
+    if (!integ.fused) k_step_advance<<<1, 1, 0, s>>>(integ);
 }
 
 // ApplyConstraintsKernel::apply: project the current positions onto the constraints (reference & target identical)

@@ -54,11 +54,14 @@ __device__ __forceinline__ bool grid_index(const float4& p, const NbDev& nb, con
     return ok;
 }
 
+// 8 lanes per atom, lane ix < 5 owns one x-plane of the 5x5x5 stencil (25 grid points): five times more independent
+// atomics / loads in flight per atom than the one-thread-per-atom form (both kernels are L2-latency bound at 24k atoms).
 __global__ void __launch_bounds__(128) k_pme_spread(NbDev nb, PmeDev pme) {
-    // atoms are dealt to ranks in contiguous chunks of the sorted order (multi-GPU: each rank spreads its share)
     const int per = (nb.natoms + nb.world - 1)/nb.world;
-    const int s = nb.rank*per + blockIdx.x*blockDim.x + threadIdx.x;
-    if (s >= min(nb.natoms, (nb.rank+1)*per)) return;
+    const int t = blockIdx.x*blockDim.x + threadIdx.x;
+    const int s = nb.rank*per + (t >> 3);
+    const int ix = t & 7;
+    if (s >= min(nb.natoms, (nb.rank+1)*per) || ix >= ORDER) return;
     // USER order and the user-order (never lattice-shifted) coordinate: reciprocal space then does not depend on the
     // neighbour list at all and runs concurrently with the list rebuild; the fractional position is formed in double, so
     // the grid index/fraction is exact for fp32 inputs wherever the atom sits relative to the primary cell
@@ -71,64 +74,76 @@ __global__ void __launch_bounds__(128) k_pme_spread(NbDev nb, PmeDev pme) {
     bspline(fr[0], tx, dd);
     bspline(fr[1], ty, dd);
     bspline(fr[2], tz, dd);
+    float txi = tx[0];
 #pragma unroll
-    for (int ix = 0; ix < ORDER; ix++) {
-        int xi = idx[0] + ix; if (xi >= pme.nx) xi -= pme.nx;
-        const float qx = p.w*tx[ix];
+    for (int k = 1; k < ORDER; k++) if (ix == k) txi = tx[k];
+    int xi = idx[0] + ix; if (xi >= pme.nx) xi -= pme.nx;
+    const float qx = p.w*txi;
 #pragma unroll
-        for (int iy = 0; iy < ORDER; iy++) {
-            int yi = idx[1] + iy; if (yi >= pme.ny) yi -= pme.ny;
-            const float qxy = qx*ty[iy];
-            long long* row = pme.gridFixed + ((size_t) xi*pme.ny + yi)*pme.nz;
+    for (int iy = 0; iy < ORDER; iy++) {
+        int yi = idx[1] + iy; if (yi >= pme.ny) yi -= pme.ny;
+        const float qxy = qx*ty[iy];
+        long long* row = pme.gridFixed + ((size_t) xi*pme.ny + yi)*pme.nz;
 #pragma unroll
-            for (int iz = 0; iz < ORDER; iz++) {
-                int zi = idx[2] + iz; if (zi >= pme.nz) zi -= pme.nz;
-                // integer accumulation: the grid (hence every force) is independent of the order of the atomics
-                // |q theta theta theta| < 32: one F2I.S32 at scale 2^26, widened and shifted to the grid's 2^32 scale
-                atomicAdd((unsigned long long*) (row + zi), (unsigned long long) ((long long) __float2int_rn(qxy*tz[iz]*67108864.0f) << 6));
-            }
+        for (int iz = 0; iz < ORDER; iz++) {
+            int zi = idx[2] + iz; if (zi >= pme.nz) zi -= pme.nz;
+            // integer accumulation: the grid (hence every force) is independent of the order of the atomics.
+            // |q theta theta theta| < 32: one F2I.S32 at scale 2^26, widened and shifted to the grid's 2^32 scale
+            atomicAdd((unsigned long long*) (row + zi), (unsigned long long) ((long long) __float2int_rn(qxy*tz[iz]*67108864.0f) << 6));
         }
     }
 }
 
 __global__ void __launch_bounds__(128) k_pme_gather(NbDev nb, PmeDev pme) {
     const int per = (nb.natoms + nb.world - 1)/nb.world;
-    const int s = nb.rank*per + blockIdx.x*blockDim.x + threadIdx.x;
-    if (s >= min(nb.natoms, (nb.rank+1)*per)) return;
-    const float4 p = nb.posq[s];
-    if (p.w == 0.f) return;
+    const int t = blockIdx.x*blockDim.x + threadIdx.x;
+    const int s = nb.rank*per + (t >> 3);
+    const int ix = t & 7;
+    const bool inRange = s < min(nb.natoms, (nb.rank+1)*per);
+    float4 p = make_float4(0, 0, 0, 0);
+    if (inRange) p = nb.posq[s];
     int idx[3];
     float fr[3];
-    if (!grid_index(p, nb, pme, idx, fr)) return;
-    float tx[ORDER], ty[ORDER], tz[ORDER], dx[ORDER], dy[ORDER], dz[ORDER];
-    bspline(fr[0], tx, dx);
-    bspline(fr[1], ty, dy);
-    bspline(fr[2], tz, dz);
-    double fx = 0.0, fy = 0.0, fz = 0.0;
+    const bool ok = inRange && p.w != 0.f && grid_index(p, nb, pme, idx, fr);
+    float fx = 0.f, fy = 0.f, fz = 0.f;
+    if (ok && ix < ORDER) {
+        float tx[ORDER], ty[ORDER], tz[ORDER], dx[ORDER], dy[ORDER], dz[ORDER];
+        bspline(fr[0], tx, dx);
+        bspline(fr[1], ty, dy);
+        bspline(fr[2], tz, dz);
+        float txi = tx[0], dxi = dx[0];
 #pragma unroll
-    for (int ix = 0; ix < ORDER; ix++) {
+        for (int k = 1; k < ORDER; k++) if (ix == k) { txi = tx[k]; dxi = dx[k]; }
         int xi = idx[0] + ix; if (xi >= pme.nx) xi -= pme.nx;
 #pragma unroll
         for (int iy = 0; iy < ORDER; iy++) {
             int yi = idx[1] + iy; if (yi >= pme.ny) yi -= pme.ny;
             const real* row = pme.grid + ((size_t) xi*pme.ny + yi)*pme.nz;
-            double sz = 0.0, sdz = 0.0;
+            float sz = 0.f, sdz = 0.f;
 #pragma unroll
             for (int iz = 0; iz < ORDER; iz++) {
                 int zi = idx[2] + iz; if (zi >= pme.nz) zi -= pme.nz;
-                const double g = __ldg(row + zi);
+                const float g = __ldg(row + zi);
                 sz += tz[iz]*g;
                 sdz += dz[iz]*g;
             }
-            fx += dx[ix]*ty[iy]*sz;
-            fy += tx[ix]*dy[iy]*sz;
-            fz += tx[ix]*ty[iy]*sdz;
+            fx += dxi*ty[iy]*sz;
+            fy += txi*dy[iy]*sz;
+            fz += txi*ty[iy]*sdz;
         }
     }
+    // sum the five x-planes (aligned groups of 8 lanes)
+#pragma unroll
+    for (int off = 4; off > 0; off >>= 1) {
+        fx += __shfl_xor_sync(0xffffffffu, fx, off);
+        fy += __shfl_xor_sync(0xffffffffu, fy, off);
+        fz += __shfl_xor_sync(0xffffffffu, fz, off);
+    }
+    if (!ok || ix != 0) return;
     // ReferencePME.cpp:708-711 (triclinic-aware)
     const double* R = nb.box.recip;
     const double q = p.w;
-    const double gx = fx*pme.nx, gy = fy*pme.ny, gz = fz*pme.nz;
+    const double gx = (double) fx*pme.nx, gy = (double) fy*pme.ny, gz = (double) fz*pme.nz;
     const double Fx = -q*(gx*R[0]);
     const double Fy = -q*(gx*R[3] + gy*R[4]);
     const double Fz = -q*(gx*R[6] + gy*R[7] + gz*R[8]);
@@ -171,10 +186,10 @@ void launch_pme_eterm(const NbDev& nb, const PmeDev& pme, cudaStream_t s) {
 void launch_pme_spread(const NbDev& nb, const PmeDev& pme, cudaStream_t s) {
     cudaMemsetAsync(pme.gridFixed, 0, sizeof(long long)*(size_t) pme.nx*pme.ny*pme.nz, s);
     const int per = (nb.natoms + nb.world - 1)/nb.world;
-    k_pme_spread<<<(per + 127)/128, 128, 0, s>>>(nb, pme);
+    k_pme_spread<<<(per*8 + 127)/128, 128, 0, s>>>(nb, pme);
 }
 
 void launch_pme_gather(const NbDev& nb, const PmeDev& pme, cudaStream_t s) {
     const int per = (nb.natoms + nb.world - 1)/nb.world;
-    k_pme_gather<<<(per + 127)/128, 128, 0, s>>>(nb, pme);
+    k_pme_gather<<<(per*8 + 127)/128, 128, 0, s>>>(nb, pme);
 }
