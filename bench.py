@@ -136,16 +136,17 @@ def main():
     torch.cuda.set_device(local)
     comm = None
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # control plane on gloo (CPU tensors), data plane = the engine's own NCCL communicator: torch never enqueues an NCCL
+        # kernel next to the engine's in-graph collectives (two communicators racing on one GPU can deadlock)
+        dist.init_process_group("gloo")
         os.environ.setdefault("B200MD_NCCL_LIB", os.path.join(os.path.dirname(torch.__file__), "..", "nvidia", "nccl", "lib", "libnccl.so.2"))
         uid = torch.zeros(128, dtype=torch.uint8)
         if rank == 0:
             buf = C.create_string_buffer(128)
             assert _lib.load().b200md_comm_unique_id(C.cast(buf, C.c_void_p)) == 0
             uid = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).clone()
-        uid = uid.cuda()
-        dist.broadcast(uid, 0)
-        comm = (rank, world, bytes(uid.cpu().numpy().tobytes()))
+        dist.broadcast(uid, 0)                       # CPU tensor -> gloo
+        comm = (rank, world, bytes(uid.numpy().tobytes()))
 
     d = load_workload(args.workload)
     eng = Engine(d, device=local, comm=comm)
@@ -154,8 +155,9 @@ def main():
     flush = torch.empty(256*1024*1024, dtype=torch.uint8, device="cuda")      # > 126 MB L2
 
     def barrier():
+        torch.cuda.synchronize()
         if world > 1:
-            dist.barrier()
+            dist.all_reduce(torch.zeros(1))          # gloo barrier (CPU tensor)
         torch.cuda.synchronize()
 
     md = args.md_steps
@@ -182,7 +184,7 @@ def main():
     sampler.stop_flag = True
     st1 = eng.stats()
     if world > 1:
-        t = torch.tensor([ms], device="cuda")
+        t = torch.tensor([ms])
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     nsday = args.dt*1e-3*md*args.steps*86400/(ms*1e-3)
@@ -202,12 +204,15 @@ def main():
     barrier()
     e2e_sec = time.perf_counter() - t0
     if world > 1:
-        t = torch.tensor([e2e_sec], device="cuda")
+        t = torch.tensor([e2e_sec])
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_sec = float(t.item())
     e2e_nsday = args.dt*1e-3*md*args.steps*86400/e2e_sec
     nbytes = d.natoms*3*8
 
+    if world > 1:
+        barrier()
+        dist.destroy_process_group()
     if rank != 0:
         return
     # ---- roofline of the dominant kernel (the direct-space tile kernel), timed live with CUDA events on its stream ----
@@ -227,7 +232,7 @@ def main():
     line = {"metric": "ns/day", "value": nsday, "unit": "ns/day", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms/args.steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": args.workload, "atoms": d.natoms, "md_steps_per_step": md, "dt_fs": args.dt*1e3, "integrator": "Langevin 300K 1/ps + SETTLE/SHAKE (HBonds)",
-                       "cutoff_nm": d.cutoff, "pme_grid": st["pme_grid"], "parallelism": "force-decomposition x%d" % world if world > 1 else "single GPU",
+                       "cutoff_nm": d.cutoff, "pme_grid": st["pme_grid"], "parallelism": ("replicated atoms: %d direct-space ranks + 1 PME rank, int64 force all-reduce" % (world-1)) if world > 1 else "single GPU",
                        "l2": "256 MiB buffer written between timed iterations (inside the timed region)", "us_per_md_step": 1e3*ms/(args.steps*md)},
             "clocks": sampler.summary(),
             "e2e": {"value": e2e_nsday, "unit": "ns/day", "h2d_bytes_per_step": 2*nbytes, "d2h_bytes_per_step": 2*nbytes + 8,
@@ -258,8 +263,6 @@ def main():
         except Exception as ex:       # the baseline is a reported number, never the product path
             line["cpu_baseline"] = {"value": None, "unit": "ns/day", "cores": os.cpu_count(), "kind": "reference", "sample": "failed: %s" % ex}
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

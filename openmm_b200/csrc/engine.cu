@@ -756,8 +756,20 @@ static int enqueue_forces(b200md_ctx* c, int terms, bool energy, bool forcesAlre
     cudaStream_t s = c->stream;
     if (!forcesAlreadyZero) CUDA_CHECK(cudaMemsetAsync(c->force.p, 0, sizeof(long long)*3*c->npad, s));
     if (energy) CUDA_CHECK(cudaMemsetAsync(c->energy.p, 0, sizeof(double)*B200MD_NUM_ENERGY, s));
-    const bool direct = (terms & B200MD_TERM_NB_DIRECT) && c->haveNb;
-    const bool recip = (terms & B200MD_TERM_NB_RECIP) && c->haveNb && c->nb.method == B200MD_NB_PME;
+    bool direct = (terms & B200MD_TERM_NB_DIRECT) && c->haveNb;
+    bool recip = (terms & B200MD_TERM_NB_RECIP) && c->haveNb && c->nb.method == B200MD_NB_PME;
+    // Multi-GPU role split (replicated atoms): the LAST rank computes reciprocal space for all atoms and nothing else; the
+    // other world-1 ranks share the direct-space tiles (by i-block) and the bonded terms.  The two halves of the force
+    // field thus overlap on different GPUs, there is no charge-grid collective, and one int64 all-reduce of the force buffer
+    // per step joins them.  (With PME and world > 1 only; otherwise every rank takes a share of everything.)
+    const bool split = c->world > 1 && c->comm && c->nb.method == B200MD_NB_PME && c->haveNb;
+    const int pmeRank = c->world - 1;
+    NbDev nbSave = c->nb;
+    if (split) {
+        if (c->rank == pmeRank) { direct = false; c->nb.rank = 0; c->nb.world = 1; }
+        else { recip = false; c->nb.world = c->world - 1; }
+    }
+    struct Restore { b200md_ctx* c; NbDev saved; ~Restore() { unsigned long long h = c->nb.condHandle; c->nb = saved; c->nb.condHandle = h; } } restore{c, nbSave};
     // Reciprocal space (spread -> FFT/convolution -> gather, in USER atom order: independent of the neighbour list) and
     // direct space (list check / rebuild, tile kernel, bonded terms) are independent until the integrator: fork them onto
     // two streams (also inside the captured step graph).  Both accumulate into the same fixed-point force buffer, so the
@@ -770,11 +782,11 @@ static int enqueue_forces(b200md_ctx* c, int terms, bool energy, bool forcesAlre
     }
     if (recip) {
         launch_pme_spread(c->nb, c->pme, sp); launches++;
-        if (c->world > 1 && c->comm) {
+        if (c->world > 1 && c->comm && !split) {
             int rc = g_nccl.AllReduce(c->gridFixed.p, c->gridFixed.p, (size_t) c->pme.nx*c->pme.ny*c->pme.nz, NCCL_INT64, NCCL_SUM, c->comm, sp);
             if (rc != 0) throw std::runtime_error("ncclAllReduce(grid) failed");
         }
-        launch_pme_fft_conv(c->nb, c->pme, energy && c->rank == 0, sp); launches += pme_fft_launch_count(c->pme);
+        launch_pme_fft_conv(c->nb, c->pme, energy && (split || c->rank == 0), sp); launches += pme_fft_launch_count(c->pme);
         launch_pme_gather(c->nb, c->pme, sp); launches++;
     }
     if (fork) CUDA_CHECK(cudaEventRecord(c->evJoin, sp));
@@ -817,7 +829,7 @@ static int enqueue_forces(b200md_ctx* c, int terms, bool energy, bool forcesAlre
     int bterms = terms & (B200MD_TERM_BONDS | B200MD_TERM_ANGLES | B200MD_TERM_TORSIONS);
     if (c->haveNb) bterms |= terms & B200MD_TERM_NB_DIRECT;
     const int nbonded = c->bd.nbonds + c->bd.nangles + c->bd.ntorsions + c->bd.nexc;
-    if (bterms && nbonded > 0) { launch_bonded(c->nb, c->bd, bterms, energy, s); launches++; }
+    if (bterms && nbonded > 0 && !(split && c->rank == pmeRank)) { launch_bonded(c->nb, c->bd, bterms, energy, s); launches++; }
     if (fork) CUDA_CHECK(cudaStreamWaitEvent(s, c->evJoin, 0));
     if (c->world > 1 && c->comm) {
         int rc = g_nccl.AllReduce(c->force.p, c->force.p, (size_t) 3*c->npad, NCCL_INT64, NCCL_SUM, c->comm, s);

@@ -96,24 +96,20 @@ __global__ void __launch_bounds__(128) k_pme_spread(NbDev nb, PmeDev pme) {
 
 __global__ void __launch_bounds__(128) k_pme_gather(NbDev nb, PmeDev pme) {
     const int per = (nb.natoms + nb.world - 1)/nb.world;
-    const int t = blockIdx.x*blockDim.x + threadIdx.x;
-    const int s = nb.rank*per + (t >> 3);
-    const int ix = t & 7;
-    const bool inRange = s < min(nb.natoms, (nb.rank+1)*per);
-    float4 p = make_float4(0, 0, 0, 0);
-    if (inRange) p = nb.posq[s];
+    const int s = nb.rank*per + blockIdx.x*blockDim.x + threadIdx.x;
+    if (s >= min(nb.natoms, (nb.rank+1)*per)) return;
+    const float4 p = nb.posq[s];
+    if (p.w == 0.f) return;
     int idx[3];
     float fr[3];
-    const bool ok = inRange && p.w != 0.f && grid_index(p, nb, pme, idx, fr);
+    if (!grid_index(p, nb, pme, idx, fr)) return;
+    float tx[ORDER], ty[ORDER], tz[ORDER], dx[ORDER], dy[ORDER], dz[ORDER];
+    bspline(fr[0], tx, dx);
+    bspline(fr[1], ty, dy);
+    bspline(fr[2], tz, dz);
     float fx = 0.f, fy = 0.f, fz = 0.f;
-    if (ok && ix < ORDER) {
-        float tx[ORDER], ty[ORDER], tz[ORDER], dx[ORDER], dy[ORDER], dz[ORDER];
-        bspline(fr[0], tx, dx);
-        bspline(fr[1], ty, dy);
-        bspline(fr[2], tz, dz);
-        float txi = tx[0], dxi = dx[0];
 #pragma unroll
-        for (int k = 1; k < ORDER; k++) if (ix == k) { txi = tx[k]; dxi = dx[k]; }
+    for (int ix = 0; ix < ORDER; ix++) {
         int xi = idx[0] + ix; if (xi >= pme.nx) xi -= pme.nx;
 #pragma unroll
         for (int iy = 0; iy < ORDER; iy++) {
@@ -127,19 +123,11 @@ __global__ void __launch_bounds__(128) k_pme_gather(NbDev nb, PmeDev pme) {
                 sz += tz[iz]*g;
                 sdz += dz[iz]*g;
             }
-            fx += dxi*ty[iy]*sz;
-            fy += txi*dy[iy]*sz;
-            fz += txi*ty[iy]*sdz;
+            fx += dx[ix]*ty[iy]*sz;
+            fy += tx[ix]*dy[iy]*sz;
+            fz += tx[ix]*ty[iy]*sdz;
         }
     }
-    // sum the five x-planes (aligned groups of 8 lanes)
-#pragma unroll
-    for (int off = 4; off > 0; off >>= 1) {
-        fx += __shfl_xor_sync(0xffffffffu, fx, off);
-        fy += __shfl_xor_sync(0xffffffffu, fy, off);
-        fz += __shfl_xor_sync(0xffffffffu, fz, off);
-    }
-    if (!ok || ix != 0) return;
     // ReferencePME.cpp:708-711 (triclinic-aware)
     const double* R = nb.box.recip;
     const double q = p.w;
@@ -191,5 +179,5 @@ void launch_pme_spread(const NbDev& nb, const PmeDev& pme, cudaStream_t s) {
 
 void launch_pme_gather(const NbDev& nb, const PmeDev& pme, cudaStream_t s) {
     const int per = (nb.natoms + nb.world - 1)/nb.world;
-    k_pme_gather<<<(per*8 + 127)/128, 128, 0, s>>>(nb, pme);
+    k_pme_gather<<<(per + 127)/128, 128, 0, s>>>(nb, pme);
 }

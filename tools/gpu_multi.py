@@ -12,21 +12,21 @@ def log(*a):
     print("[rank %d %.1fs]" % (rank, time.time()-t0), *a, flush=True)
 t0 = time.time()
 torch.cuda.set_device(local)
-dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+dist.init_process_group("gloo")
 os.environ.setdefault("B200MD_NCCL_LIB", os.path.join(os.path.dirname(torch.__file__), "..", "nvidia", "nccl", "lib", "libnccl.so.2"))
 uid = torch.zeros(128, dtype=torch.uint8)
 if rank == 0:
     buf = C.create_string_buffer(128)
     assert _lib.load().b200md_comm_unique_id(C.cast(buf, C.c_void_p)) == 0
     uid = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).clone()
-uid = uid.cuda(); dist.broadcast(uid, 0)
+dist.broadcast(uid, 0)
 log("uid broadcast done")
 name = sys.argv[1] if len(sys.argv) > 1 else "water"
 d = systems.water_box(10, cutoff=0.9).rounded() if name == "water" else systems.SystemDesc.load(os.path.join("data", name + ".npz")).rounded()
 ref = Engine(d, device=local)
 eref = ref.compute(); fref = ref.get_forces()
 log("single-GPU reference computed", eref)
-eng = Engine(d, device=local, comm=(rank, world, bytes(uid.cpu().numpy().tobytes())))
+eng = Engine(d, device=local, comm=(rank, world, bytes(uid.numpy().tobytes())))
 log("comm engine created")
 e = eng.compute(); f = eng.get_forces()
 log("decomposed compute: E %.6f vs %.6f  max|dF| %.3e" % (e, eref, np.abs(f-fref).max()))
@@ -35,11 +35,11 @@ for g in (ref, eng):
 ref.step(40); eng.step(40)
 x = eng.get_positions(); xr = ref.get_positions()
 log("40 steps: max|dx| %.3e" % np.abs(x-xr).max())
-torch.cuda.synchronize(); dist.barrier()
+torch.cuda.synchronize(); dist.all_reduce(torch.zeros(1))
 for nm, g in (("single", ref), ("x%d" % world, eng)):
     g.step(200); g.synchronize()
     t = time.time(); g.step(1000); g.synchronize(); dt = time.time()-t
     log("%s: %.1f us/step" % (nm, 1e3*dt))
-dist.barrier()
+dist.all_reduce(torch.zeros(1))
 log("done")
 dist.destroy_process_group()
