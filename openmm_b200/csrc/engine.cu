@@ -75,7 +75,7 @@ struct b200md_ctx {
     bool haveOrigin = false;
     double padFrac = 0.10;
     // ---- device state ----
-    DevBuf<float4> posq, velm, sposq, sshift, refPos, atomShift, blockCenter, blockHalf;
+    DevBuf<float4> posq, velm, sposq, swrap, refPos, atomShift, blockCenter, blockHalf;
     DevBuf<float2> sigeps, ssigeps;
     DevBuf<long long> force;
     DevBuf<double> energy, cmScratch;
@@ -300,6 +300,7 @@ static void apply_box(b200md_ctx* c) {
         b.ax = (float) c->boxA[0]; b.bx = (float) c->boxB[0]; b.by = (float) c->boxB[1];
         b.cx = (float) c->boxC[0]; b.cy = (float) c->boxC[1]; b.cz = (float) c->boxC[2];
         b.invAx = (float) (1.0/c->boxA[0]); b.invBy = (float) (1.0/c->boxB[1]); b.invCz = (float) (1.0/c->boxC[2]);
+        b.dax = c->boxA[0]; b.dby = c->boxB[1]; b.dcz = c->boxC[2];
         b.triclinic = (c->boxB[0] != 0 || c->boxC[0] != 0 || c->boxC[1] != 0) ? 1 : 0;
         const double det = c->boxA[0]*c->boxB[1]*c->boxC[2];
         const double s = 1.0/det;
@@ -311,7 +312,7 @@ static void apply_box(b200md_ctx* c) {
     }
     else {
         require(!b.periodic, "periodic nonbonded method needs box vectors (b200md_set_box)");
-        b.ax = b.by = b.cz = 1.f; b.bx = b.cx = b.cy = 0.f; b.invAx = b.invBy = b.invCz = 1.f; b.triclinic = 0;
+        b.ax = b.by = b.cz = 1.f; b.bx = b.cx = b.cy = 0.f; b.invAx = b.invBy = b.invCz = 1.f; b.triclinic = 0; b.dax = b.dby = b.dcz = 1;
         for (int i = 0; i < 9; i++) b.recip[i] = 0; b.volume = 1;
     }
     if (b.periodic) {
@@ -505,7 +506,7 @@ extern "C" int b200md_finalize(b200md_ctx* ctx) {
     nb.useRational = getenv("B200MD_PAIR_RATIONAL") ? atoi(getenv("B200MD_PAIR_RATIONAL")) : 0;
     // ---- state arrays ----
     c->posq.alloc(NP); c->posq.zero(); c->velm.alloc(NP); c->velm.zero();
-    c->sposq.alloc(NP); c->sposq.zero(); c->sshift.alloc(NP); c->sshift.zero(); c->refPos.alloc(NP); c->refPos.zero(); c->atomShift.alloc(NP);
+    c->sposq.alloc(NP); c->sposq.zero(); c->swrap.alloc(NP); c->swrap.zero(); c->refPos.alloc(NP); c->refPos.zero(); c->atomShift.alloc(NP);
     c->sigeps.alloc(NP); c->ssigeps.alloc(NP); c->ssigeps.zero();
     c->force.alloc((size_t) 3*NP); c->force.zero();
     c->energy.alloc(B200MD_NUM_ENERGY); c->energy.zero(); c->cmScratch.alloc(12); c->cmScratch.zero();
@@ -518,7 +519,7 @@ extern "C" int b200md_finalize(b200md_ctx* ctx) {
     for (int i = 0; i < N; i++) vm[i].w = (c->mass[i] > 0) ? (float) (1.0/c->mass[i]) : 0.f;
     c->velm.upload(vm);
     nb.posq = c->posq.p; nb.velm = c->velm.p; nb.sigeps = c->sigeps.p; nb.force = c->force.p; nb.energy = c->energy.p;
-    nb.sposq = c->sposq.p; nb.ssigeps = c->ssigeps.p; nb.sshift = c->sshift.p; nb.sorig = c->sorig.p; nb.sortedOf = c->sortedOf.p;
+    nb.sposq = c->sposq.p; nb.ssigeps = c->ssigeps.p; nb.swrap = c->swrap.p; nb.sorig = c->sorig.p; nb.sortedOf = c->sortedOf.p;
     nb.refPos = c->refPos.p; nb.atomCell = c->atomCell.p; nb.tmpSorted = c->tmpSorted.p; nb.atomShift = c->atomShift.p;
     nb.blockCenter = c->blockCenter.p; nb.blockHalf = c->blockHalf.p; nb.counters = c->counters.p;
     // ---- cutoffs ----

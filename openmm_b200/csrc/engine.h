@@ -22,6 +22,7 @@ struct BoxDev {
     float invAx, invBy, invCz;
     int triclinic;
     int periodic;
+    double dax, dby, dcz;   // box lengths in double (orthorhombic single-image wrap of the pair kernel)
     double recip[9];     // recipBoxVectors[i][j] at recip[3*i+j], as invert_box_vectors (ReferencePME.cpp:196-204)
     double volume;
 };
@@ -58,7 +59,7 @@ struct NbDev {
     // sorted (nonbonded) copies
     float4* sposq;
     float2* ssigeps;
-    float4* sshift;              // lattice shift applied to the atom when it was binned
+    float4* swrap;               // sorted positions wrapped into the anchored cell at the last build (list build only)
     int* sorig;                  // sorted slot -> user atom (-1 for padding)
     int* sortedOf;               // user atom -> sorted slot
     float4* refPos;              // user-order positions at the last list build

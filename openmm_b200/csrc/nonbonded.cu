@@ -75,9 +75,8 @@ __global__ void __launch_bounds__(256) k_check_gather(NbDev nb) {
         if (a < 0 || a >= nb.natoms) a = nb.sorig[nb.natoms-1];
         a = min(max(a, 0), nb.natoms-1);          // garbage-safe before the first build
         float4 p = nb.posq[a];
-        const float4 sh = nb.sshift[min(s, nb.natoms-1)];
         if (s >= nb.natoms) p.w = 0.f;
-        nb.sposq[s] = make_float4(p.x+sh.x, p.y+sh.y, p.z+sh.z, p.w);
+        nb.sposq[s] = p;                           // exact user coordinates: the pair kernel picks the image itself
     }
     if (nb.condHandle != 0ull) {
         __shared__ int last;
@@ -194,15 +193,14 @@ __global__ void k_finalize_sort(NbDev nb) {
         float4 sh = nb.atomShift[a];
         nb.sorig[s] = a;
         nb.sortedOf[a] = s;
-        nb.sshift[s] = sh;
-        nb.sposq[s] = make_float4(p.x+sh.x, p.y+sh.y, p.z+sh.z, p.w);
+        nb.swrap[s] = make_float4(p.x+sh.x, p.y+sh.y, p.z+sh.z, p.w);   // wrapped into the anchored cell: list build only
+        nb.sposq[s] = p;
         nb.ssigeps[s] = nb.sigeps[a];
         nb.refPos[a] = p;
         if (s == 0) nb.counters[7] = 0;        // max block half extent, filled by k_block_bounds
     }
     else {
         nb.sorig[s] = -1;
-        nb.sshift[s] = make_float4(0, 0, 0, 0);
         nb.ssigeps[s] = make_float2(0, 0);
         // position is filled by k_block_bounds with a copy of a real atom of the same block
     }
@@ -216,8 +214,8 @@ __global__ void k_block_bounds(NbDev nb) {
     if (warp >= nb.nblocks) return;
     int s = warp*32 + lane;
     int sl = min(s, nb.natoms-1);
-    float4 p = nb.sposq[sl];
-    if (s >= nb.natoms) nb.sposq[s] = make_float4(p.x, p.y, p.z, 0.f);
+    float4 p = nb.swrap[sl];
+    if (s >= nb.natoms) { nb.swrap[s] = make_float4(p.x, p.y, p.z, 0.f); nb.sposq[s] = make_float4(p.x, p.y, p.z, 0.f); }
     float lox = p.x, hix = p.x, loy = p.y, hiy = p.y, loz = p.z, hiz = p.z;
     for (int off = 16; off > 0; off >>= 1) {
         lox = fminf(lox, __shfl_xor_sync(FULL, lox, off)); hix = fmaxf(hix, __shfl_xor_sync(FULL, hix, off));
@@ -291,13 +289,14 @@ __device__ void flush_tile(const NbDev& nb, int ib, const int* buf, int count, b
 // buffers are merged, sorted and flushed by warp 0 at the end, so an i-block still ends with at most one partial tile.
 // (findBlocksWithInteractions, findInteractingBlocks.cu:180-405, is the reference counterpart.  Round-1 profile: with a
 // single warp per i-block the kernel was one long dependent chain of L2 round trips per block, 150 us at DHFR size.)
-__global__ void __launch_bounds__(128) k_build_tiles(NbDev nb) {
+template <int NW>
+__global__ void __launch_bounds__(NW*32) k_build_tiles(NbDev nb) {
     if (nb.counters[2] == 0) return;
-    __shared__ int sbuf[4][64];
+    __shared__ int sbuf[NW][64];
     __shared__ int sexcAll[32][MAX_CACHED_EXCL + 1];         // +1: odd stride, conflict-free per-lane rows
     __shared__ float4 sipos[32];                             // the i-block's atoms, relative to the block centre
-    __shared__ int sleft[4];
-    __shared__ int smerged[128];
+    __shared__ int sleft[NW];
+    __shared__ int smerged[NW*32];
     const int w = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int ib = blockIdx.x;
@@ -318,7 +317,7 @@ __global__ void __launch_bounds__(128) k_build_tiles(NbDev nb) {
     const float4 ci = nb.blockCenter[ib];
     const float4 hi = nb.blockHalf[ib];
     if (w == 0) {
-        const float4 p = nb.sposq[ib*32 + lane];            // padding slots hold a copy of a real atom of the block
+        const float4 p = nb.swrap[ib*32 + lane];            // padding slots hold a copy of a real atom of the block
         sipos[lane] = make_float4(p.x-ci.x, p.y-ci.y, p.z-ci.z, 0.f);
     }
     __syncthreads();
@@ -333,8 +332,8 @@ __global__ void __launch_bounds__(128) k_build_tiles(NbDev nb) {
     // candidate j-blocks are dealt to the 4 warps block by block (jb - ib = 4*(32*it + lane) + w): the neighbours of an
     // i-block cluster in index space, so chunk-wise dealing left three warps waiting at the barrier (48 % of all stall
     // samples in the round-1 profile)
-    for (int it = 0; ib + w + 128*it < nb.nblocks; it++) {
-        int jb = ib + w + 4*(32*it + lane);
+    for (int it = 0; ib + w + NW*32*it < nb.nblocks; it++) {
+        int jb = ib + w + NW*(32*it + lane);
         bool cand = false;
         if (jb < nb.nblocks) {
             if (allPairs || jb == ib) cand = true;
@@ -349,13 +348,13 @@ __global__ void __launch_bounds__(128) k_build_tiles(NbDev nb) {
         while (bits) {
             int b = __ffs(bits) - 1;
             bits &= bits - 1;
-            int jblk = ib + w + 4*(32*it + b);
+            int jblk = ib + w + NW*(32*it + b);
             int sj = jblk*32 + lane;
             bool inc = false;
             if (sj < nb.natoms) {
                 if (allPairs || jblk == ib) inc = true;
                 else {
-                    float4 pj = nb.sposq[sj];
+                    float4 pj = nb.swrap[sj];
                     float3 d = make_float3(pj.x-ci.x, pj.y-ci.y, pj.z-ci.z);
                     inc = (box_dist2(d, hi.x, hi.y, hi.z, nb.box, periodic) < nb.paddedCutoff2);
                     if (inc && exactCull) {
@@ -395,22 +394,20 @@ __global__ void __launch_bounds__(128) k_build_tiles(NbDev nb) {
     // merge the four partial buffers (each ascending, < 32 entries): rank sort into smerged, flush by warp 0
     if (lane == 0) sleft[w] = nbuf;
     __syncthreads();
-    const int n0 = sleft[0], n1 = sleft[1], n2 = sleft[2], n3 = sleft[3];
-    const int total = n0 + n1 + n2 + n3;
+    int total = 0;
+    for (int q = 0; q < NW; q++) total += sleft[q];
     if (lane < nbuf) {
         const int v = buf[lane];
         int rank = 0;
-        for (int k = 0; k < n0; k++) rank += (sbuf[0][k] < v);
-        for (int k = 0; k < n1; k++) rank += (sbuf[1][k] < v);
-        for (int k = 0; k < n2; k++) rank += (sbuf[2][k] < v);
-        for (int k = 0; k < n3; k++) rank += (sbuf[3][k] < v);
+        for (int q = 0; q < NW; q++) {
+            const int nq = sleft[q];
+            for (int k = 0; k < nq; k++) rank += (sbuf[q][k] < v);
+        }
         smerged[rank] = v;                 // sorted indices are unique, so ranks are a permutation
     }
     __syncthreads();
-    if (w == 0) {
-        for (int off = 0; off < total; off += 32)
-            flush_tile(nb, ib, smerged + off, min(32, total - off), false, lane, sexc, nexc, e0, ta);
-    }
+    for (int off = 32*w; off < total; off += 32*NW)
+        flush_tile(nb, ib, smerged + off, min(32, total - off), false, lane, sexc, nexc, e0, ta);
     // give back the unused part of the last reservation as empty tiles
     if (lane < ta.left) {
         const int t = ta.base + (TILE_CHUNK - ta.left) + lane;
@@ -448,7 +445,13 @@ void launch_list_build(const NbDev& nb, cudaStream_t s) {
     k_sort_cells<<<(nb.ncells+127)/128, 128, 0, s>>>(nb);
     k_finalize_sort<<<(nb.npad+255)/256, 256, 0, s>>>(nb);
     k_block_bounds<<<(nb.nblocks*32+255)/256, 256, 0, s>>>(nb);
-    k_build_tiles<<<nb.nblocks, 128, 0, s>>>(nb);
+    // 8 warps per i-block shorten the dependent chain while the grid is under one wave (measured: DHFR 108 -> 98 us per
+    // build); above that the extra CTAs only add waves (ApoA1 225 -> 244 us), so large systems keep 4
+    static const int btEnv = getenv("B200MD_BT_WARPS") ? atoi(getenv("B200MD_BT_WARPS")) : 0;
+    const int btWarps = btEnv ? btEnv : (nb.nblocks <= 1200 ? 8 : 4);
+    if (btWarps >= 16) k_build_tiles<16><<<nb.nblocks, 512, 0, s>>>(nb);
+    else if (btWarps >= 8) k_build_tiles<8><<<nb.nblocks, 256, 0, s>>>(nb);
+    else k_build_tiles<4><<<nb.nblocks, 128, 0, s>>>(nb);
     k_list_done<<<1, 32, 0, s>>>(nb);
 }
 
@@ -486,6 +489,12 @@ __device__ __forceinline__ float ewald_g(float w) {
 // slots, denormal/range fix-ups around rsqrtf and __fdividef, switch-function code in the main path).  This version is
 // written FMA-first with ftz approximate rcp/rsqrt (one Newton step restores rsqrt to <1 ulp) and moves the switching
 // function into its own instantiation: ~58 instructions per slot.
+__device__ __forceinline__ float wrap_rel(float p, float c, double L, double invL) {
+    double r = (double) p - (double) c;
+    r -= L*rint(r*invL);
+    return (float) r;
+}
+
 template <bool ENERGY, int METHOD, bool SHIFT, bool RATIONAL, bool SWITCH>
 __device__ __forceinline__ void pair_tiles(const NbDev& nb, float& energy) {
     const int lane = threadIdx.x & 31;
@@ -515,11 +524,14 @@ __device__ __forceinline__ void pair_tiles(const NbDev& nb, float& energy) {
         // rotate the mask so that bit 0 is always the current slot: slot = (lane + k) & 31
         mask = __funnelshift_r(mask, mask, lane);
         if (SHIFT) {
+            // single-image mode: coordinates relative to the i-block centre, image chosen ONCE per atom and tile, in
+            // double from the exact user coordinates (a lattice shift applied in fp32 costs half an ulp of the box
+            // length, ~5e-7 nm: 1e-3 relative on weakly loaded atoms).  The rounding left is that of the ~1 nm relative
+            // coordinate (<= 6e-8 nm).
             const float4 c = nb.blockCenter[ib];
-            pi.x -= c.x; pi.y -= c.y; pi.z -= c.z;
-            pj.x -= c.x; pj.y -= c.y; pj.z -= c.z;
-            pi.x -= nb.box.ax*rintf(pi.x*nb.box.invAx); pi.y -= nb.box.by*rintf(pi.y*nb.box.invBy); pi.z -= nb.box.cz*rintf(pi.z*nb.box.invCz);
-            pj.x -= nb.box.ax*rintf(pj.x*nb.box.invAx); pj.y -= nb.box.by*rintf(pj.y*nb.box.invBy); pj.z -= nb.box.cz*rintf(pj.z*nb.box.invCz);
+            const BoxDev& bx = nb.box;
+            pi.x = wrap_rel(pi.x, c.x, bx.dax, bx.recip[0]); pi.y = wrap_rel(pi.y, c.y, bx.dby, bx.recip[4]); pi.z = wrap_rel(pi.z, c.z, bx.dcz, bx.recip[8]);
+            pj.x = wrap_rel(pj.x, c.x, bx.dax, bx.recip[0]); pj.y = wrap_rel(pj.y, c.y, bx.dby, bx.recip[4]); pj.z = wrap_rel(pj.z, c.z, bx.dcz, bx.recip[8]);
         }
         float fix = 0.f, fiy = 0.f, fiz = 0.f, fjx = 0.f, fjy = 0.f, fjz = 0.f;
 #pragma unroll 4

@@ -172,10 +172,11 @@ def test_real_benchmark_systems_parity(mods, name):
     from conftest import ROOT
     systems = mods[0]
     d = systems.SystemDesc.load(os.path.join(ROOT, "data", name + ".npz")).rounded()
-    # ApoA1 (10.9 nm box, molecules hanging over the cell faces): atoms that need a lattice shift have their shifted
-    # fp32 coordinate rounded once (5e-7 nm), which moves stiff pair forces by ~2e-3 kJ/mol/nm; on atoms whose net
-    # force is ~1 that exceeds 1e-4 in the floor-1 relative measure ("Precision").
-    eng, sim = _compare(mods, d, tol=1e-4 if name == "dhfr" else 1.5e-3)
+    # ApoA1: direct space and reciprocal space are each within 1e-4 / 2e-4 of the Reference platform measured against
+    # their own force (tools/gpu_iter.py parity), but 57 of 92,224 atoms carry a total force of ~1 kJ/mol/nm that is the
+    # difference of two ~100 kJ/mol/nm sums: the fp32 pair arithmetic floor (~1e-3 absolute) shows as up to 8e-4 in the
+    # floor-1 relative measure of ASSERT_EQUAL_VEC ("Precision").
+    eng, sim = _compare(mods, d, tol=1e-4 if name == "dhfr" else 1.0e-3)
     st = eng.stats()
     assert st["pme_grid"] == ([56, 56, 56] if name == "dhfr" else [88, 88, 88])
     # a short constrained Langevin run keeps every HBonds constraint (SETTLE waters + X-H_n SHAKE clusters)
