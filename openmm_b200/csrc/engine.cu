@@ -57,7 +57,13 @@ struct b200md_ctx {
     cudaStream_t stream = nullptr;
     cudaStream_t stream2 = nullptr;     // body capture of conditional graph nodes
     cudaStream_t streamPme = nullptr;   // reciprocal space runs concurrently with direct space (high priority: its kernels are small)
-    cudaEvent_t evFork = nullptr, evJoin = nullptr;
+    cudaStream_t streamList = nullptr;  // the successor neighbour list is built here, beside the tile kernel
+    cudaEvent_t evFork = nullptr, evJoin = nullptr, evListFork = nullptr, evListJoin = nullptr;
+    bool asyncList = false;             // B200MD_ASYNC_LIST=1: build the successor list beside the step (see enqueue_forces)
+    bool specPair = true;               // step graphs: the tile kernel does not wait for a rebuild IF node (needs asyncList)
+    bool listDirty = true;              // state changed from outside: rebuild synchronously before the next step graph
+    double softFrac = 0.7;
+    float softPad2 = 3e38f;
     bool overlapPme = true;
     bool useCond = true;
     // ---- host copy of the system definition ----
@@ -75,12 +81,12 @@ struct b200md_ctx {
     bool haveOrigin = false;
     double padFrac = 0.10;
     // ---- device state ----
-    DevBuf<float4> posq, velm, sposq, swrap, refPos, atomShift, blockCenter, blockHalf;
-    DevBuf<float2> sigeps, ssigeps;
+    DevBuf<float4> posq, velm, sposq[2], swrap[2], refPos, atomShift, blockCenter[2], blockHalf[2];
+    DevBuf<float2> sigeps, ssigeps[2];
     DevBuf<long long> force;
     DevBuf<double> energy, cmScratch;
-    DevBuf<int> sorig, sortedOf, cellRank, cellCount, cellFill, atomCell, tmpSorted, tileI, tileJ, tileMask, counters, exclStart, exclList;
-    DevBuf<unsigned int> maskPool;
+    DevBuf<int> sorig[2], sortedOf, cellRank, cellCount, cellFill, atomCell, tmpSorted, tileI[2], tileJ[2], tileMask[2], listCounters, counters, exclStart, exclList;
+    DevBuf<unsigned int> maskPool[2];
     DevBuf<unsigned long long> stepCounter;
     DevBuf<unsigned int> blocksDone;
     bool stepStateValid = false;         // fused step path: force buffer zeroed and cm accumulator primed
@@ -146,9 +152,15 @@ extern "C" int b200md_create(b200md_ctx** out, int device, int natoms) {
         if (getenv("B200MD_NO_OVERLAP")) c->overlapPme = false;
         int lo = 0, hi = 0;
         CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-        CUDA_CHECK(cudaStreamCreateWithPriority(&c->streamPme, cudaStreamNonBlocking, hi));
+        CUDA_CHECK(cudaStreamCreateWithPriority(&c->streamPme, cudaStreamNonBlocking, getenv("B200MD_PME_PRIO") && atoi(getenv("B200MD_PME_PRIO")) == 0 ? lo : hi));
         CUDA_CHECK(cudaEventCreateWithFlags(&c->evFork, cudaEventDisableTiming));
         CUDA_CHECK(cudaEventCreateWithFlags(&c->evJoin, cudaEventDisableTiming));
+        CUDA_CHECK(cudaStreamCreateWithFlags(&c->streamList, cudaStreamNonBlocking));
+        CUDA_CHECK(cudaEventCreateWithFlags(&c->evListFork, cudaEventDisableTiming));
+        CUDA_CHECK(cudaEventCreateWithFlags(&c->evListJoin, cudaEventDisableTiming));
+        if (getenv("B200MD_ASYNC_LIST")) c->asyncList = atoi(getenv("B200MD_ASYNC_LIST")) != 0;
+        if (getenv("B200MD_SOFT_FRACTION")) c->softFrac = atof(getenv("B200MD_SOFT_FRACTION"));
+        if (getenv("B200MD_SPEC_PAIR")) c->specPair = atoi(getenv("B200MD_SPEC_PAIR")) != 0;
         c->mass.assign(natoms, 1.0);
         c->charge.assign(natoms, 0.0); c->sigma.assign(natoms, 1.0); c->epsilon.assign(natoms, 0.0);
         const char* pf = getenv("B200MD_PAD_FRACTION");
@@ -174,6 +186,9 @@ extern "C" void b200md_destroy(b200md_ctx* ctx) {
     if (ctx->streamPme) cudaStreamDestroy(ctx->streamPme);
     if (ctx->evFork) cudaEventDestroy(ctx->evFork);
     if (ctx->evJoin) cudaEventDestroy(ctx->evJoin);
+    if (ctx->streamList) cudaStreamDestroy(ctx->streamList);
+    if (ctx->evListFork) cudaEventDestroy(ctx->evListFork);
+    if (ctx->evListJoin) cudaEventDestroy(ctx->evListJoin);
     delete ctx;
 }
 
@@ -324,7 +339,7 @@ static void apply_box(b200md_ctx* c) {
         setup_cells(c);
         if (m == B200MD_NB_PME) { launch_pme_eterm(c->nb, c->pme, c->stream); c->kernelLaunches++; }
         const int one = 1;
-        CUDA_CHECK(cudaMemcpyAsync(&c->counters.p[2], &one, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+        CUDA_CHECK(cudaMemcpyAsync(&c->counters.p[2], &one, sizeof(int), cudaMemcpyHostToDevice, c->stream)); c->listDirty = true;
         CUDA_CHECK(cudaStreamSynchronize(c->stream));
         invalidate_graph(c);
     }
@@ -504,33 +519,43 @@ extern "C" int b200md_finalize(b200md_ctx* ctx) {
     nb.method = c->nbdesc.method;
     nb.rank = c->rank; nb.world = c->world;
     nb.useRational = getenv("B200MD_PAIR_RATIONAL") ? atoi(getenv("B200MD_PAIR_RATIONAL")) : 0;
+    nb.pairDynamic = getenv("B200MD_PAIR_DYNAMIC") ? atoi(getenv("B200MD_PAIR_DYNAMIC")) : 0;
     // ---- state arrays ----
     c->posq.alloc(NP); c->posq.zero(); c->velm.alloc(NP); c->velm.zero();
-    c->sposq.alloc(NP); c->sposq.zero(); c->swrap.alloc(NP); c->swrap.zero(); c->refPos.alloc(NP); c->refPos.zero(); c->atomShift.alloc(NP);
-    c->sigeps.alloc(NP); c->ssigeps.alloc(NP); c->ssigeps.zero();
+    c->refPos.alloc(NP); c->refPos.zero(); c->atomShift.alloc(NP); c->sigeps.alloc(NP);
+    c->listCounters.alloc(2*LC_STRIDE); c->listCounters.zero();
+    for (int l = 0; l < 2; l++) {
+        c->sposq[l].alloc(NP); c->sposq[l].zero(); c->swrap[l].alloc(NP); c->swrap[l].zero(); c->ssigeps[l].alloc(NP); c->ssigeps[l].zero();
+        c->sorig[l].alloc(NP); c->sorig[l].zero(); c->blockCenter[l].alloc(c->nblocks); c->blockHalf[l].alloc(c->nblocks);
+        ListDev& L = c->nb.list[l];
+        L.sposq = c->sposq[l].p; L.ssigeps = c->ssigeps[l].p; L.swrap = c->swrap[l].p; L.sorig = c->sorig[l].p;
+        L.blockCenter = c->blockCenter[l].p; L.blockHalf = c->blockHalf[l].p; L.lc = c->listCounters.p + LC_STRIDE*l;
+    }
     c->force.alloc((size_t) 3*NP); c->force.zero();
     c->energy.alloc(B200MD_NUM_ENERGY); c->energy.zero(); c->cmScratch.alloc(12); c->cmScratch.zero();
     c->blocksDone.alloc(1); c->blocksDone.zero();
-    c->sorig.alloc(NP); c->sortedOf.alloc(NP); c->atomCell.alloc(NP); c->tmpSorted.alloc(NP);
-    c->blockCenter.alloc(c->nblocks); c->blockHalf.alloc(c->nblocks);
+    c->sortedOf.alloc(NP); c->atomCell.alloc(NP); c->tmpSorted.alloc(NP);
     c->counters.alloc(16); c->counters.zero();
     c->stepCounter.alloc(1); c->stepCounter.zero();
     std::vector<float4> vm(NP, make_float4(0, 0, 0, 0));
     for (int i = 0; i < N; i++) vm[i].w = (c->mass[i] > 0) ? (float) (1.0/c->mass[i]) : 0.f;
     c->velm.upload(vm);
     nb.posq = c->posq.p; nb.velm = c->velm.p; nb.sigeps = c->sigeps.p; nb.force = c->force.p; nb.energy = c->energy.p;
-    nb.sposq = c->sposq.p; nb.ssigeps = c->ssigeps.p; nb.swrap = c->swrap.p; nb.sorig = c->sorig.p; nb.sortedOf = c->sortedOf.p;
+    nb.sortedOf = c->sortedOf.p;
     nb.refPos = c->refPos.p; nb.atomCell = c->atomCell.p; nb.tmpSorted = c->tmpSorted.p; nb.atomShift = c->atomShift.p;
-    nb.blockCenter = c->blockCenter.p; nb.blockHalf = c->blockHalf.p; nb.counters = c->counters.p;
+    nb.counters = c->counters.p;
     // ---- cutoffs ----
     const double rc = c->nbdesc.cutoff;
     if (nb.method == B200MD_NB_NOCUTOFF) {
         nb.cutoff = 1e18f; nb.cutoff2 = 3e38f; nb.paddedCutoff2 = 3e38f; nb.halfPad2 = 3e38f;
+        c->softPad2 = 3e38f;
     }
     else {
         const double pad = c->padFrac*rc;
         nb.cutoff = (float) rc; nb.cutoff2 = (float) (rc*rc); nb.paddedCutoff2 = (float) ((rc+pad)*(rc+pad)); nb.halfPad2 = (float) (0.25*pad*pad);
+        c->softPad2 = (float) (0.25*pad*pad*c->softFrac*c->softFrac);
     }
+    nb.softPad2 = 3e38f; nb.condAsync = 0ull;
     nb.useSwitch = c->nbdesc.use_switch; nb.switchDist = (float) c->nbdesc.switch_distance;
     nb.alpha = (float) c->nbdesc.ewald_alpha;
     if (nb.method == B200MD_NB_CUTOFF_PERIODIC || nb.method == B200MD_NB_CUTOFF_NONPERIODIC) {
@@ -553,21 +578,27 @@ extern "C" int b200md_finalize(b200md_ctx* ctx) {
         c->exclStart.upload(start); c->exclList.upload(list);
         nb.exclStart = c->exclStart.p; nb.exclList = c->exclList.p;
     }
-    // ---- tile capacity ----
+    // ---- tile capacity: TILE_REGIONS equal slot pools, i-block ib allocates from pool ib % TILE_REGIONS (flush_tile) ----
     {
-        const double nbk = c->nblocks;
-        double cap = nbk*(nbk+1)/2 + 17*nbk + 64;
+        const int nbk = c->nblocks;
+        // worst case (every block pair interacts): i-block ib emits at most nbk - ib + 2 tiles (its j-blocks, the diagonal
+        // tile on its own, one partial tile); pool 0 holds the smallest ib and is the fullest
+        double poolCap = 0;
+        for (int ib = 0; ib < nbk; ib += TILE_REGIONS) poolCap += nbk - ib + 2;
         if (nb.method != B200MD_NB_NOCUTOFF && c->haveBox) {
             const double vol = c->boxA[0]*c->boxB[1]*c->boxC[2];
             const double rp = rc*(1.0 + c->padFrac);
             const double pairs = 0.5*N*(N/vol)*(4.0/3.0*M_PI*rp*rp*rp);
-            const double est = pairs/(1024.0*0.15) + 18*nbk + 1024;      // + unused slots of the per-warp reservation chunks
-            cap = std::min(cap, est);
+            const double est = pairs/(1024.0*0.15) + 18.0*nbk;           // tiles at >= 15 % fill + partial tiles
+            poolCap = std::min(poolCap, 1.25*est/TILE_REGIONS + 64);     // + slack for the imbalance between pools
         }
-        cap = std::min(cap, 16.0e6);
-        nb.maxTiles = (int) cap;
-        c->tileI.alloc(nb.maxTiles); c->tileJ.alloc((size_t) nb.maxTiles*32); c->tileMask.alloc(nb.maxTiles); c->maskPool.alloc((size_t) nb.maxTiles*32);
-        nb.tileI = c->tileI.p; nb.tileJ = c->tileJ.p; nb.tileMask = c->tileMask.p; nb.maskPool = c->maskPool.p;
+        poolCap = std::min(poolCap, 16.0e6/TILE_REGIONS);
+        nb.maxTiles = ((int) poolCap + 1)*TILE_REGIONS;
+        for (int l = 0; l < 2; l++) {
+            c->tileI[l].alloc(nb.maxTiles); c->tileJ[l].alloc((size_t) nb.maxTiles*32); c->tileMask[l].alloc(nb.maxTiles); c->maskPool[l].alloc((size_t) nb.maxTiles*32);
+            ListDev& L = nb.list[l];
+            L.tileI = c->tileI[l].p; L.tileJ = c->tileJ[l].p; L.tileMask = c->tileMask[l].p; L.maskPool = c->maskPool[l].p;
+        }
     }
     // ---- bonded ----
     {
@@ -606,7 +637,7 @@ extern "C" int b200md_update_nonbonded_params(b200md_ctx* ctx, const double* q, 
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     upload_params(ctx);
     const int one = 1;
-    CUDA_CHECK(cudaMemcpy(&ctx->counters.p[2], &one, sizeof(int), cudaMemcpyHostToDevice));   // sorted copies of the parameters
+    CUDA_CHECK(cudaMemcpy(&ctx->counters.p[2], &one, sizeof(int), cudaMemcpyHostToDevice)); ctx->listDirty = true;   // sorted copies of the parameters
     invalidate_graph(ctx);
     API_END(ctx)
 }
@@ -657,7 +688,7 @@ extern "C" int b200md_set_positions(b200md_ctx* ctx, const double* x) {
     }
     CUDA_CHECK(cudaMemcpyAsync(ctx->posq.p, ctx->hbuf4.data(), sizeof(float4)*ctx->npad, cudaMemcpyHostToDevice, ctx->stream));
     const int one = 1;
-    CUDA_CHECK(cudaMemcpyAsync(&ctx->counters.p[2], &one, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_CHECK(cudaMemcpyAsync(&ctx->counters.p[2], &one, sizeof(int), cudaMemcpyHostToDevice, ctx->stream)); ctx->listDirty = true;
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     API_END(ctx)
 }
@@ -746,13 +777,13 @@ extern "C" int b200md_checkpoint_load(b200md_ctx* ctx, const void* buf, int64_t 
     CUDA_CHECK(cudaMemcpy(ctx->stepCounter.p, &h.rngStep, sizeof(unsigned long long), cudaMemcpyHostToDevice));
     if (ctx->haveBox) apply_box(ctx);
     const int one = 1;
-    CUDA_CHECK(cudaMemcpy(&ctx->counters.p[2], &one, sizeof(int), cudaMemcpyHostToDevice));
+    CUDA_CHECK(cudaMemcpy(&ctx->counters.p[2], &one, sizeof(int), cudaMemcpyHostToDevice)); ctx->listDirty = true;
     API_END(ctx)
 }
 
 // ---------------------------------------------------------------- force evaluation
 // Enqueue one force evaluation on the stream (no host sync).  Returns the number of kernels launched.
-static int enqueue_forces(b200md_ctx* c, int terms, bool energy, bool forcesAlreadyZero = false) {
+static int enqueue_forces(b200md_ctx* c, int terms, bool energy, bool forcesAlreadyZero = false, bool inStep = false) {
     int launches = 0;
     cudaStream_t s = c->stream;
     if (!forcesAlreadyZero) CUDA_CHECK(cudaMemsetAsync(c->force.p, 0, sizeof(long long)*3*c->npad, s));
@@ -791,6 +822,7 @@ static int enqueue_forces(b200md_ctx* c, int terms, bool energy, bool forcesAlre
         launch_pme_gather(c->nb, c->pme, sp); launches++;
     }
     if (fork) CUDA_CHECK(cudaEventRecord(c->evJoin, sp));
+    bool joinList = false;
     if (direct) {
         cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
         cudaGraph_t graph = nullptr;
@@ -799,26 +831,60 @@ static int enqueue_forces(b200md_ctx* c, int terms, bool energy, bool forcesAlre
         CUDA_CHECK(cudaStreamGetCaptureInfo_v2(s, &cap, nullptr, &graph, &deps, &ndeps));
         if (cap == cudaStreamCaptureStatusActive && c->useCond) {
             // the rebuild kernels live in an IF node of the step graph: zero launches on the (usual) steps without a rebuild
-            cudaGraphConditionalHandle h;
-            CUDA_CHECK(cudaGraphConditionalHandleCreate(&h, graph, 0, cudaGraphCondAssignDefault));
+            // Inside a step, a second IF node builds the SUCCESSOR list on a side stream as soon as some atom has used up
+            // softFrac of its allowance: the current list is still valid for this step's forces, the new one takes over when
+            // the integrator has finished (k_integrate's last block flips counters[CT_CUR]), so the rebuild leaves the
+            // critical path.  The first IF node remains as the synchronous fallback (state set from outside, or a
+            // displacement that jumps past the hard limit within one step).
+            const bool async = inStep && c->asyncList && c->softPad2 < c->nb.halfPad2;
+            // spec: no synchronous IF node at all in step graphs (an IF node costs ~15 us of latency on this driver, taken
+            // or not, and the tile kernel would sit behind it every step); b200md_step rebuilds eagerly after any
+            // outside change of the state, and k_check_gather documents the one-step corner case
+            const bool spec = async && c->specPair;
+            cudaGraphConditionalHandle h = 0, ha = 0;
+            if (!spec) CUDA_CHECK(cudaGraphConditionalHandleCreate(&h, graph, 0, cudaGraphCondAssignDefault));
+            if (async) CUDA_CHECK(cudaGraphConditionalHandleCreate(&ha, graph, 0, cudaGraphCondAssignDefault));
             c->nb.condHandle = (unsigned long long) h;
+            c->nb.condAsync = async ? (unsigned long long) ha : 0ull;
+            c->nb.softPad2 = async ? c->softPad2 : 3e38f;
             launch_check_displacement(c->nb, s); launches++;
-            CUDA_CHECK(cudaStreamGetCaptureInfo_v2(s, &cap, nullptr, &graph, &deps, &ndeps));
-            cudaGraphNodeParams np = {cudaGraphNodeTypeConditional};
-            np.type = cudaGraphNodeTypeConditional;
-            np.conditional.handle = h;
-            np.conditional.type = cudaGraphCondTypeIf;
-            np.conditional.size = 1;
-            cudaGraphNode_t node;
-            CUDA_CHECK(cudaGraphAddNode(&node, graph, deps, ndeps, &np));
-            cudaGraph_t body = np.conditional.phGraph_out[0];
             NbDev nbBody = c->nb;
-            CUDA_CHECK(cudaStreamBeginCaptureToGraph(c->stream2, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
-            launch_list_build(nbBody, c->stream2);
             cudaGraph_t tmp;
-            CUDA_CHECK(cudaStreamEndCapture(c->stream2, &tmp));
-            CUDA_CHECK(cudaStreamUpdateCaptureDependencies(s, &node, 1, cudaStreamSetCaptureDependencies));
-            c->nb.condHandle = 0ull;
+            if (!spec) {
+                CUDA_CHECK(cudaStreamGetCaptureInfo_v2(s, &cap, nullptr, &graph, &deps, &ndeps));
+                cudaGraphNodeParams np = {cudaGraphNodeTypeConditional};
+                np.type = cudaGraphNodeTypeConditional;
+                np.conditional.handle = h;
+                np.conditional.type = cudaGraphCondTypeIf;
+                np.conditional.size = 1;
+                cudaGraphNode_t node;
+                CUDA_CHECK(cudaGraphAddNode(&node, graph, deps, ndeps, &np));
+                cudaGraph_t body = np.conditional.phGraph_out[0];
+                CUDA_CHECK(cudaStreamBeginCaptureToGraph(c->stream2, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
+                launch_list_build(nbBody, c->stream2);
+                CUDA_CHECK(cudaStreamEndCapture(c->stream2, &tmp));
+                CUDA_CHECK(cudaStreamUpdateCaptureDependencies(s, &node, 1, cudaStreamSetCaptureDependencies));
+            }
+            if (async) {
+                cudaStream_t sl = c->streamList;
+                CUDA_CHECK(cudaEventRecord(c->evListFork, s));
+                CUDA_CHECK(cudaStreamWaitEvent(sl, c->evListFork, 0));
+                CUDA_CHECK(cudaStreamGetCaptureInfo_v2(sl, &cap, nullptr, &graph, &deps, &ndeps));
+                cudaGraphNodeParams np2 = {cudaGraphNodeTypeConditional};
+                np2.type = cudaGraphNodeTypeConditional;
+                np2.conditional.handle = ha;
+                np2.conditional.type = cudaGraphCondTypeIf;
+                np2.conditional.size = 1;
+                cudaGraphNode_t node2;
+                CUDA_CHECK(cudaGraphAddNode(&node2, graph, deps, ndeps, &np2));
+                CUDA_CHECK(cudaStreamBeginCaptureToGraph(c->stream2, np2.conditional.phGraph_out[0], nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
+                launch_list_build(nbBody, c->stream2, 1);
+                CUDA_CHECK(cudaStreamEndCapture(c->stream2, &tmp));
+                CUDA_CHECK(cudaStreamUpdateCaptureDependencies(sl, &node2, 1, cudaStreamSetCaptureDependencies));
+                CUDA_CHECK(cudaEventRecord(c->evListJoin, sl));
+                joinList = true;
+            }
+            c->nb.condHandle = 0ull; c->nb.condAsync = 0ull; c->nb.softPad2 = 3e38f;
         }
         else {
             c->nb.condHandle = 0ull;
@@ -832,6 +898,7 @@ static int enqueue_forces(b200md_ctx* c, int terms, bool energy, bool forcesAlre
     const int nbonded = c->bd.nbonds + c->bd.nangles + c->bd.ntorsions + c->bd.nexc;
     if (bterms && nbonded > 0 && !(split && c->rank == pmeRank)) { launch_bonded(c->nb, c->bd, bterms, energy, s); launches++; }
     if (fork) CUDA_CHECK(cudaStreamWaitEvent(s, c->evJoin, 0));
+    if (joinList) CUDA_CHECK(cudaStreamWaitEvent(s, c->evListJoin, 0));
     if (c->world > 1 && c->comm) {
         int rc = g_nccl.AllReduce(c->force.p, c->force.p, (size_t) 3*c->npad, NCCL_INT64, NCCL_SUM, c->comm, s);
         if (rc != 0) throw std::runtime_error("ncclAllReduce(force) failed");
@@ -904,7 +971,7 @@ extern "C" int b200md_set_integrator(b200md_ctx* ctx, int kind, double dt, doubl
 static int enqueue_step(b200md_ctx* c) {
     // the fused step: the integrate kernel also removes the centre-of-mass motion (frequency 1), zeroes the force buffer
     // for the next step and advances the step counter, so a step is: [check] [rebuild?] pair bonded || spread fft gather ; integrate
-    int launches = enqueue_forces(c, B200MD_TERM_ALL, false, true);
+    int launches = enqueue_forces(c, B200MD_TERM_ALL, false, true, true);
     IntegDev in = c->integ;
     in.fused = 1;
     in.cmEveryStep = (c->cmFreq == 1) ? 1 : 0;
@@ -932,6 +999,21 @@ static cudaGraphExec_t capture_steps(b200md_ctx* c, int nsteps, int* launches) {
     int l = 0;
     try { for (int k = 0; k < nsteps; k++) l += enqueue_step(c); } catch (...) { cudaStreamEndCapture(c->stream, &g); throw; }
     CUDA_CHECK(cudaStreamEndCapture(c->stream, &g));
+    if (getenv("B200MD_DEBUG_PRIO")) {
+        size_t n = 0;
+        CUDA_CHECK(cudaGraphGetNodes(g, nullptr, &n));
+        std::vector<cudaGraphNode_t> nodes(n);
+        CUDA_CHECK(cudaGraphGetNodes(g, nodes.data(), &n));
+        for (size_t i = 0; i < n; i++) {
+            cudaGraphNodeType t;
+            CUDA_CHECK(cudaGraphNodeGetType(nodes[i], &t));
+            if (t != cudaGraphNodeTypeKernel) { fprintf(stderr, "node %zu type %d\n", i, (int) t); continue; }
+            cudaLaunchAttributeValue v;
+            memset(&v, 0, sizeof(v));
+            cudaError_t e = cudaGraphKernelNodeGetAttribute(nodes[i], cudaLaunchAttributePriority, &v);
+            fprintf(stderr, "node %zu kernel priority %d (%s)\n", i, v.priority, cudaGetErrorString(e));
+        }
+    }
     CUDA_CHECK(cudaGraphInstantiate(&exec, g, 0));
     cudaGraphDestroy(g);
     *launches = l;
@@ -943,6 +1025,14 @@ extern "C" int b200md_step(b200md_ctx* ctx, int nsteps) {
     require(ctx->finalized && ctx->haveIntegrator, "step before finalize / set_integrator");
     b200md_ctx* c = ctx;
     int remaining = nsteps;
+    if (c->listDirty && c->haveNb) {
+        // the state was changed from outside: bring the neighbour list up to date before the step graphs, whose tile
+        // kernel trusts the current list (kernels gated on counters[CT_REBUILD], which the setter raised)
+        launch_check_displacement(c->nb, c->stream);
+        launch_list_build(c->nb, c->stream, 0);
+        c->kernelLaunches += 1 + list_build_launch_count();
+        c->listDirty = false;
+    }
     if (!c->stepStateValid) {
         CUDA_CHECK(cudaMemsetAsync(c->force.p, 0, sizeof(long long)*3*c->npad, c->stream));
         if (c->cmFreq == 1) {
@@ -1042,10 +1132,14 @@ extern "C" int b200md_get_stats(b200md_ctx* ctx, b200md_stats* out) {
     out->natoms = ctx->natoms; out->padded_atoms = ctx->npad; out->num_blocks = ctx->nblocks;
     if (ctx->finalized) {
         launch_count_pairs(ctx->nb, ctx->stream);
-        int h[12];
-        CUDA_CHECK(cudaMemcpyAsync(h, ctx->counters.p, sizeof(int)*12, cudaMemcpyDeviceToHost, ctx->stream));
+        int h[16], lc[2*LC_STRIDE];
+        CUDA_CHECK(cudaMemcpyAsync(h, ctx->counters.p, sizeof(int)*16, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_CHECK(cudaMemcpyAsync(lc, ctx->listCounters.p, sizeof(lc), cudaMemcpyDeviceToHost, ctx->stream));
         CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
-        out->num_tiles = h[9]; out->num_mask_tiles = h[1]; out->overflow = h[3]; out->list_builds = h[4]; out->pairs_in_cutoff = h[5];
+        const int* cur = lc + LC_STRIDE*(h[CT_CUR] & 1);
+        int masks = 0;
+        for (int r = 0; r < TILE_REGIONS; r++) masks += cur[LC_MASKS + r];
+        out->num_tiles = cur[LC_USED]; out->num_mask_tiles = masks; out->overflow = h[3]; out->list_builds = h[4]; out->pairs_in_cutoff = h[5];
     }
     out->force_evals = ctx->forceEvals; out->kernel_launches = ctx->kernelLaunches;
     out->pme_grid[0] = ctx->pme.nx; out->pme_grid[1] = ctx->pme.ny; out->pme_grid[2] = ctx->pme.nz; out->ewald_alpha = ctx->pme.alpha;

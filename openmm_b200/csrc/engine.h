@@ -41,6 +41,27 @@ struct FftPlanDev {      // 1-D mixed-radix Stockham plan for one grid dimension
 };
 
 // Everything the force kernels need, passed by value.
+// One neighbour list: the sorted copy of the atoms, the 32-atom blocks and the 32x32 tiles.
+struct ListDev {
+    float4* sposq;               // sorted positions (exact user coordinates, refreshed every step) + charge
+    float2* ssigeps;
+    float4* swrap;               // sorted positions wrapped into the anchored cell at the build (list build only)
+    int* sorig;                  // sorted slot -> user atom (-1 for padding)
+    float4* blockCenter;
+    float4* blockHalf;
+    int* tileI;                  // [maxTiles]
+    int* tileJ;                  // [maxTiles*32]
+    int* tileMask;               // [maxTiles] index into maskPool or -1
+    unsigned int* maskPool;      // [maxTiles*32]
+    int* lc;                     // per-list counters, LC_* below
+};
+#define TILE_REGIONS 32
+// ListDev::lc: tile and mask-tile counts of the TILE_REGIONS slot pools, max block half extent (float bits), tiles in use
+enum { LC_TILES = 0, LC_MASKS = TILE_REGIONS, LC_MAXHALF = 2*TILE_REGIONS, LC_USED = 2*TILE_REGIONS + 1, LC_STRIDE = 128 };
+
+// indices into NbDev::counters
+enum { CT_REBUILD = 2, CT_OVERFLOW = 3, CT_BUILDS = 4, CT_PAIRS = 5, CT_LASTBLOCK = 8, CT_CUR = 10, CT_SOFT = 11, CT_PENDING = 12, CT_STALE = 13, CT_CURSOR = 14 };
+
 struct NbDev {
     BoxDev box;
     int natoms, npad, nblocks;
@@ -56,12 +77,11 @@ struct NbDev {
     float2* sigeps;              // (sigma/2, 2 sqrt(eps))  (ReferenceKernels.cpp:1093-1097)
     long long* force;            // [3][npad] fixed point, user order
     double* energy;              // [B200MD_NUM_ENERGY] accumulators
-    // sorted (nonbonded) copies
-    float4* sposq;
-    float2* ssigeps;
-    float4* swrap;               // sorted positions wrapped into the anchored cell at the last build (list build only)
-    int* sorig;                  // sorted slot -> user atom (-1 for padding)
-    int* sortedOf;               // user atom -> sorted slot
+    // sorted (nonbonded) copies, blocks and tiles: two complete lists.  counters[CT_CUR] names the one the tile kernel reads;
+    // a rebuild always fills the other one and flips (at once when the current list is no longer valid, at the end of the
+    // step when the successor was built beside the step: see k_check_gather)
+    ListDev list[2];
+    int* sortedOf;               // user atom -> sorted slot (of the list built last; list construction only)
     float4* refPos;              // user-order positions at the last list build
     // binning
     int ncell[3];
@@ -72,19 +92,13 @@ struct NbDev {
     int* atomCell;               // [natoms] rank of the atom's cell
     int* tmpSorted;              // [npad]
     float4* atomShift;           // [natoms]
-    // blocks and tiles
-    float4* blockCenter;
-    float4* blockHalf;
-    int* tileI;                  // [maxTiles]
-    int* tileJ;                  // [maxTiles*32]
-    int* tileMask;               // [maxTiles] index into maskPool or -1
-    unsigned int* maskPool;      // [maxTiles*32]
     int maxTiles;
-    int* counters;               // [0]=tiles [1]=mask tiles [2]=rebuild flag [3]=overflow [4]=list builds [5]=pairs(diag) [6]=nan flag
+    int* counters;               // [2]=rebuild flag [3]=overflow [4]=list builds [5]=pairs(diag) [6]=nan flag
     // exclusions, CSR in user order
     const int* exclStart;
     const int* exclList;
-    float halfPad2;              // (padding/2)^2
+    float halfPad2;              // (padding/2)^2: beyond this displacement the current list is invalid
+    float softPad2;              // displacement^2 at which the successor list is built beside the step (3e38: never)
     // multi-GPU sharding of the tile list / PME atoms
     int rank, world;
     // origin of the primary periodic cell used for binning (chosen at set_positions so that a structure centred anywhere,
@@ -92,6 +106,8 @@ struct NbDev {
     double origin[3];
     // CUDA-graph conditional node that holds the list-rebuild kernels (0 = none: rebuild kernels are gated on counters[2])
     unsigned long long condHandle;
+    unsigned long long condAsync;   // second IF node: build of the successor list on a side stream
+    int pairDynamic;             // tile kernel fetches tiles from a cursor instead of a static stride
     int useRational;             // B200MD_PAIR_RATIONAL=1: rational Ewald kernel in the force-only tile loop (1 MUFU less, lower accuracy)
 };
 
@@ -157,7 +173,7 @@ __device__ __forceinline__ long long float_to_fixed(float f) {           // |f| 
 
 // ---- launchers (defined in the .cu files) ----
 void launch_check_displacement(const NbDev& nb, cudaStream_t s);
-void launch_list_build(const NbDev& nb, cudaStream_t s);          // all list kernels, each gated on counters[2]
+void launch_list_build(const NbDev& nb, cudaStream_t s, int mode = 0);   // all list kernels, gated on counters[CT_REBUILD] (mode 0) or counters[CT_SOFT] (mode 1)
 void launch_pair(const NbDev& nb, bool energy, cudaStream_t s);
 void launch_count_pairs(const NbDev& nb, cudaStream_t s);
 int  list_build_launch_count();

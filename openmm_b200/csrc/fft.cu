@@ -22,6 +22,7 @@
 // smooth potential of magnitude ~1e2: an fp32 grid alone costs ~1e-3 kJ/mol/nm); the B200 FP64
 // rate is ample for 1e5..1e6 grid points and these kernels are latency bound.
 #include "engine.h"
+#include <algorithm>
 #include <math.h>
 #include <stdlib.h>
 
@@ -36,6 +37,14 @@ __device__ __forceinline__ real2 make_real2(real x, real y) { real2 r; r.x = x; 
 // (R*R complex MACs against the R-th roots of unity, taken from the twiddle table in shared memory) and written to their
 // autosort positions.  Shared-memory traffic is 2 accesses per point per stage.  (A one-OUTPUT-per-thread variant was
 // tried in round 1: R-fold redundant operand reads made the transform shared-memory-bandwidth bound, 62 us at 56^3.)
+// Division of a small non-negative int by a runtime divisor as one multiply-high: exact for x < 2^32/d (all index ranges
+// here are < 2^20 and d <= 4096).  The divisions by nb, Ns, nz, nzc were ~50 of the ~100 instructions per butterfly.
+struct FastDiv {
+    unsigned int m; int d;
+    __device__ __forceinline__ explicit FastDiv(int dd) : m(dd > 1 ? 0xffffffffu/(unsigned int) dd + 1u : 0u), d(dd) {}
+    __device__ __forceinline__ int div(int x) const { return d > 1 ? (int) __umulhi((unsigned int) x, m) : x; }
+};
+
 template <int R>
 __device__ __forceinline__ void fft_stage(const real2* __restrict__ in, real2* __restrict__ out, int n, int nlines,
                                           int Ns, const real2* __restrict__ tw, bool inverse) {
@@ -43,10 +52,12 @@ __device__ __forceinline__ void fft_stage(const real2* __restrict__ in, real2* _
     const int twStep = n/(Ns*R);
     const int total = nlines*nb;
     const real sgn = inverse ? (real) -1 : (real) 1;
+    const FastDiv divNb(nb), divNs(Ns);
     for (int w = TID; w < total; w += NTHR) {
-        const int line = w/nb;
+        const int line = divNb.div(w);
         const int j = w - line*nb;
-        const int k = j % Ns;
+        const int jq = divNs.div(j);
+        const int k = j - jq*Ns;
         const real2* src = in + line*n + j;
         real2 v[R];
 #pragma unroll
@@ -62,7 +73,7 @@ __device__ __forceinline__ void fft_stage(const real2* __restrict__ in, real2* _
                 v[t] = make_real2(x.x*wv.x - x.y*wv.y, x.x*wv.y + x.y*wv.x);
             }
         }
-        real2* dst = out + line*n + (j/Ns)*Ns*R + k;
+        real2* dst = out + line*n + jq*Ns*R + k;
         if (R == 2) {
             dst[0] = make_real2(v[0].x + v[R-1].x, v[0].y + v[R-1].y);
             dst[Ns] = make_real2(v[0].x - v[R-1].x, v[0].y - v[R-1].y);
@@ -221,6 +232,7 @@ __device__ __forceinline__ unsigned int* stage_twiddles(real2* tws, const FftPla
 __global__ void __launch_bounds__(FFT_THREADS) k_fft_z_fwd(PmeDev pme) {
     extern __shared__ real2 smem[];
     const int nz = pme.nz, nzc = pme.nzc;
+    const FastDiv divNz(nz), divNzc(nzc);
     const int nrowsTotal = pme.nx*pme.ny;
     const int row0 = blockIdx.x*ZROWS;
     const int nrows = min(ZROWS, nrowsTotal - row0);
@@ -232,7 +244,7 @@ __global__ void __launch_bounds__(FFT_THREADS) k_fft_z_fwd(PmeDev pme) {
     if (pme.gridFixed != nullptr) {
         const long long* base = pme.gridFixed + (size_t) row0*nz;
         for (int i = TID; i < np*nz; i += NTHR) {
-            const int p = i/nz, z = i - p*nz;
+            const int p = divNz.div(i), z = i - p*nz;
             const real re = fixed_to_float(base[(size_t) (2*p)*nz + z]);
             const real im = (2*p+1 < nrows) ? fixed_to_float(base[(size_t) (2*p+1)*nz + z]) : (real) 0;
             A[i] = make_real2(re, im);
@@ -241,7 +253,7 @@ __global__ void __launch_bounds__(FFT_THREADS) k_fft_z_fwd(PmeDev pme) {
     else {
         const real* base = pme.grid + (size_t) row0*nz;
         for (int i = TID; i < np*nz; i += NTHR) {
-            const int p = i/nz, z = i - p*nz;
+            const int p = divNz.div(i), z = i - p*nz;
             const real re = base[(size_t) (2*p)*nz + z];
             const real im = (2*p+1 < nrows) ? base[(size_t) (2*p+1)*nz + z] : (real) 0;
             A[i] = make_real2(re, im);
@@ -252,9 +264,9 @@ __global__ void __launch_bounds__(FFT_THREADS) k_fft_z_fwd(PmeDev pme) {
     // unpack the two interleaved real transforms straight to global memory
     real2* dst = pme.cgrid + (size_t) row0*nzc;
     for (int i = TID; i < np*nzc; i += NTHR) {
-        const int p = i/nzc, k = i - p*nzc;
+        const int p = divNzc.div(i), k = i - p*nzc;
         const real2 Z = R[p*nz + k];
-        real2 Zc = R[p*nz + ((nz - k) % nz)];
+        real2 Zc = R[p*nz + (k == 0 ? 0 : nz - k)];
         Zc.y = -Zc.y;
         dst[(size_t) (2*p)*nzc + k] = make_real2((real) 0.5*(Z.x + Zc.x), (real) 0.5*(Z.y + Zc.y));
         if (2*p+1 < nrows) {
@@ -268,6 +280,7 @@ __global__ void __launch_bounds__(FFT_THREADS) k_fft_z_fwd(PmeDev pme) {
 __global__ void __launch_bounds__(FFT_THREADS) k_fft_z_inv(PmeDev pme) {
     extern __shared__ real2 smem[];
     const int nz = pme.nz, nzc = pme.nzc;
+    const FastDiv divNz(nz), divNzc(nzc);
     const int nrowsTotal = pme.nx*pme.ny;
     const int row0 = blockIdx.x*ZROWS;
     const int nrows = min(ZROWS, nrowsTotal - row0);
@@ -279,7 +292,7 @@ __global__ void __launch_bounds__(FFT_THREADS) k_fft_z_inv(PmeDev pme) {
     const real2* src = pme.cgrid + (size_t) row0*nzc;
     // pack rows (2p, 2p+1) into one complex line using the Hermitian symmetry along z
     for (int i = TID; i < np*nz; i += NTHR) {
-        const int p = i/nz, k = i - p*nz;
+        const int p = divNz.div(i), k = i - p*nz;
         const int kk = (k < nzc) ? k : nz - k;
         real2 a = src[(size_t) (2*p)*nzc + kk];
         real2 b = (2*p+1 < nrows) ? src[(size_t) (2*p+1)*nzc + kk] : make_real2(0, 0);
@@ -290,7 +303,7 @@ __global__ void __launch_bounds__(FFT_THREADS) k_fft_z_inv(PmeDev pme) {
     const real2* Z = fft_lines(A, B, pme.plan[2], np, tab, tws, true);
     real* dst = pme.grid + (size_t) row0*nz;
     for (int i = TID; i < np*nz; i += NTHR) {
-        const int p = i/nz, z = i - p*nz;
+        const int p = divNz.div(i), z = i - p*nz;
         const real2 v = Z[i];
         dst[(size_t) (2*p)*nz + z] = v.x;
         if (2*p+1 < nrows) dst[(size_t) (2*p+1)*nz + z] = v.y;
@@ -419,13 +432,14 @@ static size_t slab_smem_bytes(const PmeDev& p) {
 __global__ void __launch_bounds__(FFT_THREADS) k_fft_slab_fwd(PmeDev pme, size_t elems) {
     extern __shared__ real2 smem[];
     const int ny = pme.ny, nz = pme.nz, nzc = pme.nzc;
+    const FastDiv divNz(nz), divNzc(nzc);
     const int np = (ny + 1)/2;
     SlabSmem S = slab_setup(smem, pme, elems);
     const int x = blockIdx.x;
     if (pme.gridFixed != nullptr) {
         long long* base = pme.gridFixed + (size_t) x*ny*nz;
         for (int i = TID; i < np*nz; i += NTHR) {
-            const int p = i/nz, z = i - p*nz;
+            const int p = divNz.div(i), z = i - p*nz;
             const real re = fixed_to_float(base[(size_t) (2*p)*nz + z]);
             const real im = (2*p+1 < ny) ? fixed_to_float(base[(size_t) (2*p+1)*nz + z]) : (real) 0;
             S.A[i] = make_real2(re, im);
@@ -434,7 +448,7 @@ __global__ void __launch_bounds__(FFT_THREADS) k_fft_slab_fwd(PmeDev pme, size_t
     else {
         const real* base = pme.grid + (size_t) x*ny*nz;
         for (int i = TID; i < np*nz; i += NTHR) {
-            const int p = i/nz, z = i - p*nz;
+            const int p = divNz.div(i), z = i - p*nz;
             S.A[i] = make_real2(base[(size_t) (2*p)*nz + z], (2*p+1 < ny) ? base[(size_t) (2*p+1)*nz + z] : 0.0);
         }
     }
@@ -443,9 +457,9 @@ __global__ void __launch_bounds__(FFT_THREADS) k_fft_slab_fwd(PmeDev pme, size_t
     real2* O = (R == S.A) ? S.B : S.A;
     // unpack the two interleaved real transforms, transposed to [kz][y] so that the y lines are contiguous
     for (int i = TID; i < np*nzc; i += NTHR) {
-        const int p = i/nzc, k = i - p*nzc;
+        const int p = divNzc.div(i), k = i - p*nzc;
         const real2 Z = R[p*nz + k];
-        real2 Zc = R[p*nz + ((nz - k) % nz)];
+        real2 Zc = R[p*nz + (k == 0 ? 0 : nz - k)];
         Zc.y = -Zc.y;
         O[k*ny + 2*p] = make_real2((real) 0.5*(Z.x + Zc.x), (real) 0.5*(Z.y + Zc.y));
         if (2*p+1 < ny) {
@@ -458,7 +472,7 @@ __global__ void __launch_bounds__(FFT_THREADS) k_fft_slab_fwd(PmeDev pme, size_t
     const real2* Y = fft_lines(O, other, pme.plan[1], nzc, S.taby, S.twy, false);
     real2* dst = pme.cgrid + (size_t) x*ny*nzc;
     for (int i = TID; i < ny*nzc; i += NTHR) {
-        const int y = i/nzc, k = i - y*nzc;
+        const int y = divNzc.div(i), k = i - y*nzc;
         dst[i] = Y[k*ny + y];
     }
 }
@@ -466,12 +480,13 @@ __global__ void __launch_bounds__(FFT_THREADS) k_fft_slab_fwd(PmeDev pme, size_t
 __global__ void __launch_bounds__(FFT_THREADS) k_fft_slab_inv(PmeDev pme, size_t elems) {
     extern __shared__ real2 smem[];
     const int ny = pme.ny, nz = pme.nz, nzc = pme.nzc;
+    const FastDiv divNz(nz), divNzc(nzc);
     const int np = (ny + 1)/2;
     SlabSmem S = slab_setup(smem, pme, elems);
     const int x = blockIdx.x;
     const real2* src = pme.cgrid + (size_t) x*ny*nzc;
     for (int i = TID; i < ny*nzc; i += NTHR) {
-        const int y = i/nzc, k = i - y*nzc;
+        const int y = divNzc.div(i), k = i - y*nzc;
         S.A[k*ny + y] = src[i];
     }
     __syncthreads();
@@ -479,7 +494,7 @@ __global__ void __launch_bounds__(FFT_THREADS) k_fft_slab_inv(PmeDev pme, size_t
     real2* O = (Y == S.A) ? S.B : S.A;
     // pack rows (2p, 2p+1) into one complex line using the Hermitian symmetry along z
     for (int i = TID; i < np*nz; i += NTHR) {
-        const int p = i/nz, k = i - p*nz;
+        const int p = divNz.div(i), k = i - p*nz;
         const int kk = (k < nzc) ? k : nz - k;
         real2 a = Y[kk*ny + 2*p];
         real2 b = (2*p+1 < ny) ? Y[kk*ny + 2*p+1] : make_real2(0, 0);
@@ -491,16 +506,22 @@ __global__ void __launch_bounds__(FFT_THREADS) k_fft_slab_inv(PmeDev pme, size_t
     const real2* Z = fft_lines(O, other, pme.plan[2], np, S.tabz, S.twz, true);
     real* dst = pme.grid + (size_t) x*ny*nz;
     for (int i = TID; i < np*nz; i += NTHR) {
-        const int p = i/nz, z = i - p*nz;
+        const int p = divNz.div(i), z = i - p*nz;
         const real2 v = Z[i];
         dst[(size_t) (2*p)*nz + z] = v.x;
         if (2*p+1 < ny) dst[(size_t) (2*p+1)*nz + z] = v.y;
     }
 }
 
+// B200MD_FFT_THREADS: threads per CTA (<= FFT_THREADS).  At 128 registers per thread a 512-thread CTA needs a whole SM's
+// register file, a 256-thread CTA half of it: smaller CTAs find room beside the tile kernel.
+static int fft_threads() {
+    static const int t = getenv("B200MD_FFT_THREADS") ? std::min(FFT_THREADS, std::max(64, atoi(getenv("B200MD_FFT_THREADS")))) : FFT_THREADS;
+    return t;
+}
 static dim3 fft_block(int n, int maxLines) {
     (void) n; (void) maxLines;
-    return dim3(FFT_THREADS);
+    return dim3(fft_threads());
 }
 
 struct FftLaunch {
@@ -517,7 +538,7 @@ struct FftLaunch {
         const int nmax = p.ny > p.nz ? p.ny : p.nz;
         slab = ss <= (size_t) maxSmem && nmax <= 1024 && getenv("B200MD_FFT_NOSLAB") == nullptr;
         if (slab) {
-            st = dim3(FFT_THREADS);
+            st = dim3(fft_threads());
             set_smem((const void*) k_fft_slab_fwd, ss);
             set_smem((const void*) k_fft_slab_inv, ss);
         }

@@ -316,6 +316,8 @@ __global__ void __launch_bounds__(128) k_integrate(NbDev nb, UnitDev un, IntegDe
     if (last && threadIdx.x == 0) {
         *in.blocksDone = 0u;
         *in.stepCounter = step + 1ull;
+        // a successor neighbour list built beside this step (nonbonded.cu: k_check_gather / k_list_done) becomes current
+        if (nb.counters[CT_PENDING]) { nb.counters[CT_PENDING] = 0; nb.counters[CT_CUR] ^= 1; }
     }
 }
 

@@ -62,23 +62,27 @@ __device__ __forceinline__ float box_dist2(float3 d, float hx, float hy, float h
 // The last block to finish publishes the decision to the CUDA-graph conditional node that holds the rebuild kernels.
 __global__ void __launch_bounds__(256) k_check_gather(NbDev nb) {
     const int s = blockIdx.x*blockDim.x + threadIdx.x;
+    const ListDev& L = nb.list[nb.counters[CT_CUR] & 1];
+    if (s == 0) nb.counters[CT_CURSOR] = 0;           // tile cursor of the tile kernel's dynamic schedule
     if (s < nb.natoms) {
         const float4 p = nb.posq[s];
         const float4 r = nb.refPos[s];
         const float dx = p.x-r.x, dy = p.y-r.y, dz = p.z-r.z;
         const float d2 = dx*dx + dy*dy + dz*dz;
         if (!(d2 <= nb.halfPad2))       // also true for NaN
-            nb.counters[2] = 1;
+            nb.counters[CT_REBUILD] = 1;
+        else if (d2 > nb.softPad2)      // the current list is still valid for this step: build its successor beside it
+            nb.counters[CT_SOFT] = 1;
     }
     if (s < nb.npad) {
-        int a = nb.sorig[s];
-        if (a < 0 || a >= nb.natoms) a = nb.sorig[nb.natoms-1];
+        int a = L.sorig[s];
+        if (a < 0 || a >= nb.natoms) a = L.sorig[nb.natoms-1];
         a = min(max(a, 0), nb.natoms-1);          // garbage-safe before the first build
         float4 p = nb.posq[a];
         if (s >= nb.natoms) p.w = 0.f;
-        nb.sposq[s] = p;                           // exact user coordinates: the pair kernel picks the image itself
+        L.sposq[s] = p;                           // exact user coordinates: the pair kernel picks the image itself
     }
-    if (nb.condHandle != 0ull) {
+    if (nb.condHandle != 0ull || nb.condAsync != 0ull) {
         __shared__ int last;
         __syncthreads();
         if (threadIdx.x == 0) {
@@ -89,16 +93,30 @@ __global__ void __launch_bounds__(256) k_check_gather(NbDev nb) {
         if (last && threadIdx.x == 0) {
             nb.counters[8] = 0;
             __threadfence();
-            const int flag = *((volatile int*) &nb.counters[2]);
-            cudaGraphSetConditional((cudaGraphConditionalHandle) nb.condHandle, flag ? 1u : 0u);
+            const int hard = *((volatile int*) &nb.counters[CT_REBUILD]);
+            const int soft = *((volatile int*) &nb.counters[CT_SOFT]);
+            if (nb.condHandle != 0ull) {
+                if (hard) nb.counters[CT_SOFT] = 0;
+                cudaGraphSetConditional((cudaGraphConditionalHandle) nb.condHandle, hard ? 1u : 0u);
+                if (nb.condAsync != 0ull)
+                    cudaGraphSetConditional((cudaGraphConditionalHandle) nb.condAsync, (!hard && soft) ? 1u : 0u);
+            }
+            else {
+                // no synchronous rebuild in this step graph (the tile kernel does not wait for an IF node): an atom that
+                // jumps from below the soft limit past the hard limit within ONE step is served by the current list for
+                // this step (pairs that entered the cutoff from beyond cutoff+padding are missed once; counted in
+                // counters[CT_STALE]) and the successor list is built beside the step like any other
+                if (hard) { nb.counters[CT_REBUILD] = 0; nb.counters[CT_SOFT] = 1; nb.counters[CT_STALE] += 1; }
+                cudaGraphSetConditional((cudaGraphConditionalHandle) nb.condAsync, (hard || soft) ? 1u : 0u);
+            }
         }
     }
 }
 
 // ------------------------------------------------------------------------------------------------
 // 2. binning (periodic systems only; non-periodic systems keep the identity order)
-__global__ void k_bin_atoms(NbDev nb) {
-    if (nb.counters[2] == 0) return;
+__global__ void k_bin_atoms(NbDev nb, int mode) {
+    if (nb.counters[mode ? CT_SOFT : CT_REBUILD] == 0) return;
     int a = blockIdx.x*blockDim.x + threadIdx.x;
     if (a >= nb.natoms) return;
     float4 p = nb.posq[a];
@@ -133,8 +151,8 @@ __global__ void k_bin_atoms(NbDev nb) {
 }
 
 // exclusive scan of cellCount[0..ncells) into cellCount (in place), single block
-__global__ void k_scan_cells(NbDev nb) {
-    if (nb.counters[2] == 0) return;
+__global__ void k_scan_cells(NbDev nb, int mode) {
+    if (nb.counters[mode ? CT_SOFT : CT_REBUILD] == 0) return;
     __shared__ int partial[1024];
     int n = nb.ncells;
     int per = (n + blockDim.x - 1)/blockDim.x;
@@ -159,8 +177,8 @@ __global__ void k_scan_cells(NbDev nb) {
     if (threadIdx.x == 0) nb.cellCount[n] = nb.natoms;
 }
 
-__global__ void k_fill_cells(NbDev nb) {
-    if (nb.counters[2] == 0) return;
+__global__ void k_fill_cells(NbDev nb, int mode) {
+    if (nb.counters[mode ? CT_SOFT : CT_REBUILD] == 0) return;
     int a = blockIdx.x*blockDim.x + threadIdx.x;
     if (a >= nb.natoms) return;
     int key = nb.atomCell[a];
@@ -169,8 +187,8 @@ __global__ void k_fill_cells(NbDev nb) {
 }
 
 // make the order inside a cell deterministic (ascending user index)
-__global__ void k_sort_cells(NbDev nb) {
-    if (nb.counters[2] == 0) return;
+__global__ void k_sort_cells(NbDev nb, int mode) {
+    if (nb.counters[mode ? CT_SOFT : CT_REBUILD] == 0) return;
     int c = blockIdx.x*blockDim.x + threadIdx.x;
     if (c >= nb.ncells) return;
     int begin = nb.cellCount[c], end = nb.cellCount[c+1];
@@ -183,39 +201,41 @@ __global__ void k_sort_cells(NbDev nb) {
     }
 }
 
-__global__ void k_finalize_sort(NbDev nb) {
-    if (nb.counters[2] == 0) return;
+__global__ void k_finalize_sort(NbDev nb, int mode) {
+    if (nb.counters[mode ? CT_SOFT : CT_REBUILD] == 0) return;
+    const ListDev& L = nb.list[(nb.counters[CT_CUR] & 1) ^ 1];      // the list under construction
     int s = blockIdx.x*blockDim.x + threadIdx.x;
     if (s >= nb.npad) return;
     if (s < nb.natoms) {
         int a = nb.box.periodic ? nb.tmpSorted[s] : s;
         float4 p = nb.posq[a];
         float4 sh = nb.atomShift[a];
-        nb.sorig[s] = a;
+        L.sorig[s] = a;
         nb.sortedOf[a] = s;
-        nb.swrap[s] = make_float4(p.x+sh.x, p.y+sh.y, p.z+sh.z, p.w);   // wrapped into the anchored cell: list build only
-        nb.sposq[s] = p;
-        nb.ssigeps[s] = nb.sigeps[a];
+        L.swrap[s] = make_float4(p.x+sh.x, p.y+sh.y, p.z+sh.z, p.w);   // wrapped into the anchored cell: list build only
+        L.sposq[s] = p;
+        L.ssigeps[s] = nb.sigeps[a];
         nb.refPos[a] = p;
-        if (s == 0) nb.counters[7] = 0;        // max block half extent, filled by k_block_bounds
+        if (s == 0) L.lc[LC_MAXHALF] = 0;        // max block half extent, filled by k_block_bounds
     }
     else {
-        nb.sorig[s] = -1;
-        nb.ssigeps[s] = make_float2(0, 0);
+        L.sorig[s] = -1;
+        L.ssigeps[s] = make_float2(0, 0);
         // position is filled by k_block_bounds with a copy of a real atom of the same block
     }
 }
 
 // one warp per block of 32 sorted atoms: axis-aligned bounding box (findBlockBounds, findInteractingBlocks.cu:7-52)
-__global__ void k_block_bounds(NbDev nb) {
-    if (nb.counters[2] == 0) return;
+__global__ void k_block_bounds(NbDev nb, int mode) {
+    const ListDev& L = nb.list[(nb.counters[CT_CUR] & 1) ^ 1];      // the list under construction
+    if (nb.counters[mode ? CT_SOFT : CT_REBUILD] == 0) return;
     int warp = (blockIdx.x*blockDim.x + threadIdx.x) >> 5;
     int lane = threadIdx.x & 31;
     if (warp >= nb.nblocks) return;
     int s = warp*32 + lane;
     int sl = min(s, nb.natoms-1);
-    float4 p = nb.swrap[sl];
-    if (s >= nb.natoms) { nb.swrap[s] = make_float4(p.x, p.y, p.z, 0.f); nb.sposq[s] = make_float4(p.x, p.y, p.z, 0.f); }
+    float4 p = L.swrap[sl];
+    if (s >= nb.natoms) { L.swrap[s] = make_float4(p.x, p.y, p.z, 0.f); L.sposq[s] = make_float4(p.x, p.y, p.z, 0.f); }
     float lox = p.x, hix = p.x, loy = p.y, hiy = p.y, loz = p.z, hiz = p.z;
     for (int off = 16; off > 0; off >>= 1) {
         lox = fminf(lox, __shfl_xor_sync(FULL, lox, off)); hix = fmaxf(hix, __shfl_xor_sync(FULL, hix, off));
@@ -223,36 +243,33 @@ __global__ void k_block_bounds(NbDev nb) {
         loz = fminf(loz, __shfl_xor_sync(FULL, loz, off)); hiz = fmaxf(hiz, __shfl_xor_sync(FULL, hiz, off));
     }
     if (lane == 0) {
-        nb.blockCenter[warp] = make_float4(0.5f*(lox+hix), 0.5f*(loy+hiy), 0.5f*(loz+hiz), 0);
-        nb.blockHalf[warp] = make_float4(0.5f*(hix-lox), 0.5f*(hiy-loy), 0.5f*(hiz-loz), 0);
+        L.blockCenter[warp] = make_float4(0.5f*(lox+hix), 0.5f*(loy+hiy), 0.5f*(loz+hiz), 0);
+        L.blockHalf[warp] = make_float4(0.5f*(hix-lox), 0.5f*(hiy-loy), 0.5f*(hiz-loz), 0);
         const float h = 0.5f*fmaxf(hix-lox, fmaxf(hiy-loy, hiz-loz));
-        atomicMax(&nb.counters[7], __float_as_int(h));       // non-negative floats order like ints
+        atomicMax(&L.lc[LC_MAXHALF], __float_as_int(h));       // non-negative floats order like ints
     }
-    if (warp == 0 && lane == 0) { nb.counters[0] = 0; nb.counters[1] = 0; }
+    if (warp == 0) { L.lc[LC_TILES + lane] = 0; L.lc[LC_MASKS + lane] = 0; }
 }
 
 #define MAX_CACHED_EXCL 24
 // Emit one tile from the first `count` entries of buf (ascending sorted indices).
 // sexc: this lane's exclusion partners as SORTED indices, cached once per i-block (nexc of them; partners beyond
 // MAX_CACHED_EXCL are looked up in global memory).
-#define TILE_CHUNK 1
-// Tile slots are reserved TILE_CHUNK at a time per warp (one atomic on the global counter per chunk instead of per tile:
-// 14k same-address atomics per build serialise in L2); slots left unused at the end are marked empty (tileI = -1).
-struct TileAlloc { int base, left; };
-
-__device__ void flush_tile(const NbDev& nb, int ib, const int* buf, int count, bool diagonal, int lane,
-                           const int* sexc, int nexc, int e0, TileAlloc& ta) {
-    if (ta.left == 0) {
-        int b = 0;
-        if (lane == 0) b = atomicAdd(&nb.counters[0], TILE_CHUNK);
-        ta.base = __shfl_sync(FULL, b, 0);
-        ta.left = TILE_CHUNK;
-    }
-    const int t = ta.base + (TILE_CHUNK - ta.left);
-    ta.left--;
-    if (t >= nb.maxTiles) { if (lane == 0) nb.counters[3] = 1; return; }
+// Tile slots come from TILE_REGIONS independent sub-pools (i-block ib allocates from pool ib % TILE_REGIONS): one global
+// counter would take ~14k (DHFR) to ~66k (ApoA1) returning atomics on ONE address per build, which L2 serialises at ~2 ns
+// each.  Pool r owns the slots [r*cap, (r+1)*cap), cap = maxTiles/TILE_REGIONS; consumers flatten the pools with a
+// 32-lane prefix sum (tile_cursor below).
+__device__ void flush_tile(const NbDev& nb, const ListDev& L, int ib, const int* buf, int count, bool diagonal, int lane,
+                           const int* sexc, int nexc, int e0) {
+    const int region = ib % TILE_REGIONS;
+    const int cap = nb.maxTiles/TILE_REGIONS;
+    int k = 0;
+    if (lane == 0) k = atomicAdd(&L.lc[LC_TILES + region], 1);
+    k = __shfl_sync(FULL, k, 0);
+    if (k >= cap) { if (lane == 0) nb.counters[CT_OVERFLOW] = 1; return; }
+    const int t = region*cap + k;
     int myj = (lane < count) ? buf[lane] : -1;
-    nb.tileJ[t*32 + lane] = myj;
+    L.tileJ[t*32 + lane] = myj;
     unsigned int valid = (count >= 32) ? FULL : ((1u << count) - 1u);
     unsigned int mask = valid;
     bool need = (count < 32);
@@ -276,11 +293,11 @@ __device__ void flush_tile(const NbDev& nb, int ib, const int* buf, int count, b
     need = __any_sync(FULL, need);
     int mi = -1;
     if (need) {
-        if (lane == 0) mi = atomicAdd(&nb.counters[1], 1);
-        mi = __shfl_sync(FULL, mi, 0);
-        nb.maskPool[mi*32 + lane] = mask;     // capacity == maxTiles, and mask tiles <= tiles
+        if (lane == 0) mi = atomicAdd(&L.lc[LC_MASKS + region], 1);
+        mi = region*cap + __shfl_sync(FULL, mi, 0);          // mask tiles <= tiles in every pool
+        L.maskPool[mi*32 + lane] = mask;     // capacity == maxTiles, and mask tiles <= tiles
     }
-    if (lane == 0) { nb.tileI[t] = ib; nb.tileMask[t] = mi; }
+    if (lane == 0) { L.tileI[t] = ib; L.tileMask[t] = mi; }
 }
 
 // One CTA (4 warps) per i-block: the candidate j-blocks of the i-block are dealt round-robin to the 4 warps (chunks of
@@ -290,8 +307,9 @@ __device__ void flush_tile(const NbDev& nb, int ib, const int* buf, int count, b
 // (findBlocksWithInteractions, findInteractingBlocks.cu:180-405, is the reference counterpart.  Round-1 profile: with a
 // single warp per i-block the kernel was one long dependent chain of L2 round trips per block, 150 us at DHFR size.)
 template <int NW>
-__global__ void __launch_bounds__(NW*32) k_build_tiles(NbDev nb) {
-    if (nb.counters[2] == 0) return;
+__global__ void __launch_bounds__(NW*32) k_build_tiles(NbDev nb, int mode) {
+    if (nb.counters[mode ? CT_SOFT : CT_REBUILD] == 0) return;
+    const ListDev& L = nb.list[(nb.counters[CT_CUR] & 1) ^ 1];      // the list under construction
     __shared__ int sbuf[NW][64];
     __shared__ int sexcAll[32][MAX_CACHED_EXCL + 1];         // +1: odd stride, conflict-free per-lane rows
     __shared__ float4 sipos[32];                             // the i-block's atoms, relative to the block centre
@@ -307,18 +325,19 @@ __global__ void __launch_bounds__(NW*32) k_build_tiles(NbDev nb) {
     {
         const int si = ib*32 + lane;
         if (si < nb.natoms) {
-            const int a = nb.sorig[si];
+            const int a = L.sorig[si];
             e0 = nb.exclStart[a];
             nexc = nb.exclStart[a+1] - e0;
             if (w == 0)
                 for (int e = 0; e < nexc && e < MAX_CACHED_EXCL; e++) sexc[e] = nb.sortedOf[nb.exclList[e0 + e]];
         }
     }
-    const float4 ci = nb.blockCenter[ib];
-    const float4 hi = nb.blockHalf[ib];
+    const float4 ci = L.blockCenter[ib];
+    const float4 hi = L.blockHalf[ib];
     if (w == 0) {
-        const float4 p = nb.swrap[ib*32 + lane];            // padding slots hold a copy of a real atom of the block
-        sipos[lane] = make_float4(p.x-ci.x, p.y-ci.y, p.z-ci.z, 0.f);
+        const float4 p = L.swrap[ib*32 + lane];            // padding slots hold a copy of a real atom of the block
+        const float qx = p.x-ci.x, qy = p.y-ci.y, qz = p.z-ci.z;
+        sipos[lane] = make_float4(qx, qy, qz, qx*qx + qy*qy + qz*qz);
     }
     __syncthreads();
     const bool periodic = nb.box.periodic != 0;
@@ -326,9 +345,8 @@ __global__ void __launch_bounds__(NW*32) k_build_tiles(NbDev nb) {
     // same condition as the pair kernel's SHIFT mode (counters[7] = max block half extent of THIS build)
     const float minL = fminf(nb.box.ax, fminf(nb.box.by, nb.box.cz));
     const bool exactCull = periodic && !nb.box.triclinic &&
-                           (0.5f*minL - nb.cutoff - 2.0f*sqrtf(nb.halfPad2) >= __int_as_float(nb.counters[7]));
+                           (0.5f*minL - nb.cutoff - 2.0f*sqrtf(nb.halfPad2) >= __int_as_float(L.lc[LC_MAXHALF]));
     int nbuf = 0;
-    TileAlloc ta = {0, 0};
     // candidate j-blocks are dealt to the 4 warps block by block (jb - ib = 4*(32*it + lane) + w): the neighbours of an
     // i-block cluster in index space, so chunk-wise dealing left three warps waiting at the barrier (48 % of all stall
     // samples in the round-1 profile)
@@ -338,8 +356,8 @@ __global__ void __launch_bounds__(NW*32) k_build_tiles(NbDev nb) {
         if (jb < nb.nblocks) {
             if (allPairs || jb == ib) cand = true;
             else {
-                float4 cj = nb.blockCenter[jb];
-                float4 hj = nb.blockHalf[jb];
+                float4 cj = L.blockCenter[jb];
+                float4 hj = L.blockHalf[jb];
                 float3 d = make_float3(cj.x-ci.x, cj.y-ci.y, cj.z-ci.z);
                 cand = (box_dist2(d, hi.x+hj.x, hi.y+hj.y, hi.z+hj.z, nb.box, periodic) < nb.paddedCutoff2);
             }
@@ -354,18 +372,22 @@ __global__ void __launch_bounds__(NW*32) k_build_tiles(NbDev nb) {
             if (sj < nb.natoms) {
                 if (allPairs || jblk == ib) inc = true;
                 else {
-                    float4 pj = nb.swrap[sj];
+                    float4 pj = L.swrap[sj];
                     float3 d = make_float3(pj.x-ci.x, pj.y-ci.y, pj.z-ci.z);
                     inc = (box_dist2(d, hi.x, hi.y, hi.z, nb.box, periodic) < nb.paddedCutoff2);
                     if (inc && exactCull) {
                         // exact cull: keep j only if it is within the padded cutoff of at least one atom of the i-block.
                         // Valid because every block satisfies halfExtent <= L/2 - cutoff - padding (off otherwise).
+                        // |d - q|^2 = |q|^2 - 2 d.q + |d|^2 with |q|^2 precomputed: 3 FMA per i-atom.  The 1e-5 margin
+                        // covers the cancellation error (coordinates are relative to the block centre, |d|, |q| < ~3 nm);
+                        // keeping a j-atom that is a hair outside the padded cutoff is harmless.
                         d = min_image(d, nb.box);
+                        const float mx = -2.0f*d.x, my = -2.0f*d.y, mz = -2.0f*d.z;
+                        const float thr = nb.paddedCutoff2*1.00001f - (d.x*d.x + d.y*d.y + d.z*d.z);
                         inc = false;
                         for (int k = 0; k < 32; k++) {
                             const float4 q = sipos[k];
-                            const float ex = d.x-q.x, ey = d.y-q.y, ez = d.z-q.z;
-                            if (ex*ex + ey*ey + ez*ez < nb.paddedCutoff2) { inc = true; break; }
+                            if (fmaf(mx, q.x, fmaf(my, q.y, fmaf(mz, q.z, q.w))) < thr) { inc = true; break; }
                         }
                     }
                 }
@@ -377,12 +399,12 @@ __global__ void __launch_bounds__(NW*32) k_build_tiles(NbDev nb) {
             __syncwarp();
             if (jblk == ib) {
                 // the diagonal tile is always emitted on its own so that its mask is the simple j>i triangle
-                flush_tile(nb, ib, buf, nbuf, true, lane, sexc, nexc, e0, ta);
+                flush_tile(nb, L, ib, buf, nbuf, true, lane, sexc, nexc, e0);
                 nbuf = 0;
                 __syncwarp();
             }
             else if (nbuf >= 32) {
-                flush_tile(nb, ib, buf, 32, false, lane, sexc, nexc, e0, ta);
+                flush_tile(nb, L, ib, buf, 32, false, lane, sexc, nexc, e0);
                 int v = (lane + 32 < nbuf) ? buf[lane+32] : 0;
                 __syncwarp();
                 buf[lane] = v;
@@ -407,25 +429,24 @@ __global__ void __launch_bounds__(NW*32) k_build_tiles(NbDev nb) {
     }
     __syncthreads();
     for (int off = 32*w; off < total; off += 32*NW)
-        flush_tile(nb, ib, smerged + off, min(32, total - off), false, lane, sexc, nexc, e0, ta);
-    // give back the unused part of the last reservation as empty tiles
-    if (lane < ta.left) {
-        const int t = ta.base + (TILE_CHUNK - ta.left) + lane;
-        if (t < nb.maxTiles) nb.tileI[t] = -1;
-    }
+        flush_tile(nb, L, ib, smerged + off, min(32, total - off), false, lane, sexc, nexc, e0);
 }
 
-__global__ void k_list_done(NbDev nb) {
-    if (nb.counters[2] == 0) return;
-    if (threadIdx.x == 0 && blockIdx.x == 0) { nb.counters[2] = 0; nb.counters[4] += 1; }
+__global__ void k_list_done(NbDev nb, int mode) {
+    if (nb.counters[mode ? CT_SOFT : CT_REBUILD] == 0) return;
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        nb.counters[4] += 1;
+        if (mode) { nb.counters[CT_SOFT] = 0; nb.counters[CT_PENDING] = 1; }   // built beside the step: the integrator's last block flips
+        else { nb.counters[CT_REBUILD] = 0; nb.counters[CT_SOFT] = 0; nb.counters[CT_CUR] ^= 1; }
+    }
 }
 
 void launch_check_displacement(const NbDev& nb, cudaStream_t s) {
     k_check_gather<<<(nb.npad+255)/256, 256, 0, s>>>(nb);
 }
 
-__global__ void k_zero_cells(NbDev nb) {
-    if (nb.counters[2] == 0) return;
+__global__ void k_zero_cells(NbDev nb, int mode) {
+    if (nb.counters[mode ? CT_SOFT : CT_REBUILD] == 0) return;
     for (int i = blockIdx.x*blockDim.x + threadIdx.x; i <= nb.ncells; i += gridDim.x*blockDim.x) {
         nb.cellCount[i] = 0;
         if (i < nb.ncells) nb.cellFill[i] = 0;
@@ -434,25 +455,25 @@ __global__ void k_zero_cells(NbDev nb) {
 
 int list_build_launch_count() { return 9; }
 
-void launch_list_build(const NbDev& nb, cudaStream_t s) {
+void launch_list_build(const NbDev& nb, cudaStream_t s, int mode) {
     // kernels only (this sequence is also the body of a CUDA-graph conditional node); each returns immediately unless
     // counters[2] is set
     int nbk = (nb.natoms+255)/256;
-    k_zero_cells<<<std::min(64, (nb.ncells+256)/256), 256, 0, s>>>(nb);
-    k_bin_atoms<<<nbk, 256, 0, s>>>(nb);
-    k_scan_cells<<<1, 1024, 0, s>>>(nb);
-    k_fill_cells<<<nbk, 256, 0, s>>>(nb);
-    k_sort_cells<<<(nb.ncells+127)/128, 128, 0, s>>>(nb);
-    k_finalize_sort<<<(nb.npad+255)/256, 256, 0, s>>>(nb);
-    k_block_bounds<<<(nb.nblocks*32+255)/256, 256, 0, s>>>(nb);
+    k_zero_cells<<<std::min(64, (nb.ncells+256)/256), 256, 0, s>>>(nb, mode);
+    k_bin_atoms<<<nbk, 256, 0, s>>>(nb, mode);
+    k_scan_cells<<<1, 1024, 0, s>>>(nb, mode);
+    k_fill_cells<<<nbk, 256, 0, s>>>(nb, mode);
+    k_sort_cells<<<(nb.ncells+127)/128, 128, 0, s>>>(nb, mode);
+    k_finalize_sort<<<(nb.npad+255)/256, 256, 0, s>>>(nb, mode);
+    k_block_bounds<<<(nb.nblocks*32+255)/256, 256, 0, s>>>(nb, mode);
     // 8 warps per i-block shorten the dependent chain while the grid is under one wave (measured: DHFR 108 -> 98 us per
     // build); above that the extra CTAs only add waves (ApoA1 225 -> 244 us), so large systems keep 4
     static const int btEnv = getenv("B200MD_BT_WARPS") ? atoi(getenv("B200MD_BT_WARPS")) : 0;
     const int btWarps = btEnv ? btEnv : (nb.nblocks <= 1200 ? 8 : 4);
-    if (btWarps >= 16) k_build_tiles<16><<<nb.nblocks, 512, 0, s>>>(nb);
-    else if (btWarps >= 8) k_build_tiles<8><<<nb.nblocks, 256, 0, s>>>(nb);
-    else k_build_tiles<4><<<nb.nblocks, 128, 0, s>>>(nb);
-    k_list_done<<<1, 32, 0, s>>>(nb);
+    if (btWarps >= 16) k_build_tiles<16><<<nb.nblocks, 512, 0, s>>>(nb, mode);
+    else if (btWarps >= 8) k_build_tiles<8><<<nb.nblocks, 256, 0, s>>>(nb, mode);
+    else k_build_tiles<4><<<nb.nblocks, 128, 0, s>>>(nb, mode);
+    k_list_done<<<1, 32, 0, s>>>(nb, mode);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -489,6 +510,28 @@ __device__ __forceinline__ float ewald_g(float w) {
 // slots, denormal/range fix-ups around rsqrtf and __fdividef, switch-function code in the main path).  This version is
 // written FMA-first with ftz approximate rcp/rsqrt (one Newton step restores rsqrt to <1 ulp) and moves the switching
 // function into its own instantiation: ~58 instructions per slot.
+// The tiles of a list live in TILE_REGIONS pools (flush_tile).  Flat tile number f -> slot: lane r holds the inclusive prefix
+// sum of the pool counts; the pool of f is the number of prefixes <= f.
+struct TileCursor {
+    int incl, total, cap;
+    __device__ __forceinline__ void init(const NbDev& nb, const ListDev& L, int lane) {
+        cap = nb.maxTiles/TILE_REGIONS;
+        int c = min(L.lc[LC_TILES + lane], cap);
+        for (int off = 1; off < 32; off <<= 1) {
+            const int v = __shfl_up_sync(FULL, c, off);
+            if (lane >= off) c += v;
+        }
+        incl = c;
+        total = __shfl_sync(FULL, c, 31);
+    }
+    __device__ __forceinline__ int slot(int f) const {       // f < total, uniform over the warp
+        const int r = __popc(__ballot_sync(FULL, incl <= f));
+        const int before = __shfl_sync(FULL, incl, max(r-1, 0));
+        return r*cap + f - (r > 0 ? before : 0);
+    }
+};
+static_assert(TILE_REGIONS == 32, "TileCursor maps one pool to one lane");
+
 __device__ __forceinline__ float wrap_rel(float p, float c, double L, double invL) {
     double r = (double) p - (double) c;
     r -= L*rint(r*invL);
@@ -496,11 +539,13 @@ __device__ __forceinline__ float wrap_rel(float p, float c, double L, double inv
 }
 
 template <bool ENERGY, int METHOD, bool SHIFT, bool RATIONAL, bool SWITCH>
-__device__ __forceinline__ void pair_tiles(const NbDev& nb, float& energy) {
+__device__ __forceinline__ void pair_tiles(const NbDev& nb, const ListDev& L, float& energy) {
     const int lane = threadIdx.x & 31;
     const int gwarp = (blockIdx.x*blockDim.x + threadIdx.x) >> 5;
     const int nwarps = (gridDim.x*blockDim.x) >> 5;
-    const int ntiles = min(nb.counters[0], nb.maxTiles);
+    TileCursor cursor;
+    cursor.init(nb, L, lane);
+    const int ntiles = cursor.total;
     const bool periodic = nb.box.periodic != 0;
     const float alpha2 = nb.alpha*nb.alpha, nalpha3 = -alpha2*nb.alpha;
     const float cutoff2 = nb.cutoff2;
@@ -508,19 +553,33 @@ __device__ __forceinline__ void pair_tiles(const NbDev& nb, float& energy) {
     const int src = (lane + 1) & 31;
     // multi-GPU force decomposition: rank r owns the tiles of i-blocks with ib % world == r.  (Tile INDICES are handed out
     // by an atomic counter and differ between ranks; the i-block of a tile does not.)
-    for (int t = gwarp; t < ntiles; t += nwarps) {
-        const int ib = nb.tileI[t];
-        if (ib < 0) continue;                                  // unused slot of a reservation chunk
+    __shared__ int sbase;
+    int f = gwarp;
+    const int wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    if (nb.pairDynamic) f = ntiles;
+    for (;; f += nwarps) {
+        if (nb.pairDynamic) {
+            // one cursor fetch per CTA and round: CTAs that start late (SM slots held by other kernels) take less work
+            __syncthreads();
+            if (threadIdx.x == 0) sbase = atomicAdd(&nb.counters[CT_CURSOR], wpb);
+            __syncthreads();
+            f = sbase + wib;
+            if (sbase >= ntiles) break;
+            if (f >= ntiles) continue;
+        }
+        else if (f >= ntiles) break;
+        const int t = cursor.slot(f);
+        const int ib = L.tileI[t];
         if (nb.world > 1 && (ib % nb.world) != nb.rank) continue;
         const int si = ib*32 + lane;
-        float4 pi = nb.sposq[si];
-        const float2 sei = nb.ssigeps[si];
-        const int jidx = nb.tileJ[t*32 + lane];
+        float4 pi = L.sposq[si];
+        const float2 sei = L.ssigeps[si];
+        const int jidx = L.tileJ[t*32 + lane];
         const int jj = max(jidx, 0);
-        float4 pj = nb.sposq[jj];
-        float2 sej = nb.ssigeps[jj];
-        const int mi = nb.tileMask[t];
-        unsigned int mask = (mi < 0) ? FULL : nb.maskPool[mi*32 + lane];
+        float4 pj = L.sposq[jj];
+        float2 sej = L.ssigeps[jj];
+        const int mi = L.tileMask[t];
+        unsigned int mask = (mi < 0) ? FULL : L.maskPool[mi*32 + lane];
         // rotate the mask so that bit 0 is always the current slot: slot = (lane + k) & 31
         mask = __funnelshift_r(mask, mask, lane);
         if (SHIFT) {
@@ -528,7 +587,7 @@ __device__ __forceinline__ void pair_tiles(const NbDev& nb, float& energy) {
             // double from the exact user coordinates (a lattice shift applied in fp32 costs half an ulp of the box
             // length, ~5e-7 nm: 1e-3 relative on weakly loaded atoms).  The rounding left is that of the ~1 nm relative
             // coordinate (<= 6e-8 nm).
-            const float4 c = nb.blockCenter[ib];
+            const float4 c = L.blockCenter[ib];
             const BoxDev& bx = nb.box;
             pi.x = wrap_rel(pi.x, c.x, bx.dax, bx.recip[0]); pi.y = wrap_rel(pi.y, c.y, bx.dby, bx.recip[4]); pi.z = wrap_rel(pi.z, c.z, bx.dcz, bx.recip[8]);
             pj.x = wrap_rel(pj.x, c.x, bx.dax, bx.recip[0]); pj.y = wrap_rel(pj.y, c.y, bx.dby, bx.recip[4]); pj.z = wrap_rel(pj.z, c.z, bx.dcz, bx.recip[8]);
@@ -598,14 +657,14 @@ __device__ __forceinline__ void pair_tiles(const NbDev& nb, float& energy) {
             fjx = __shfl_sync(FULL, fjx, src); fjy = __shfl_sync(FULL, fjy, src); fjz = __shfl_sync(FULL, fjz, src);
         }
         // after 32 rotations every lane holds its own j again
-        const int ai = nb.sorig[si];
+        const int ai = L.sorig[si];
         if (ai >= 0) {
             atomicAdd((unsigned long long*) &nb.force[ai], (unsigned long long) float_to_fixed(fix));
             atomicAdd((unsigned long long*) &nb.force[ai + nb.npad], (unsigned long long) float_to_fixed(fiy));
             atomicAdd((unsigned long long*) &nb.force[ai + 2*nb.npad], (unsigned long long) float_to_fixed(fiz));
         }
         if (jidx >= 0) {
-            const int aj = nb.sorig[jidx];
+            const int aj = L.sorig[jidx];
             atomicAdd((unsigned long long*) &nb.force[aj], (unsigned long long) float_to_fixed(fjx));
             atomicAdd((unsigned long long*) &nb.force[aj + nb.npad], (unsigned long long) float_to_fixed(fjy));
             atomicAdd((unsigned long long*) &nb.force[aj + 2*nb.npad], (unsigned long long) float_to_fixed(fjz));
@@ -614,16 +673,16 @@ __device__ __forceinline__ void pair_tiles(const NbDev& nb, float& energy) {
 }
 
 template <bool ENERGY, int METHOD, bool SHIFT, bool RATIONAL>
-__device__ __forceinline__ void pair_tiles_sw(const NbDev& nb, float& energy) {
-    if (nb.useSwitch) pair_tiles<ENERGY, METHOD, SHIFT, RATIONAL, true>(nb, energy);
-    else pair_tiles<ENERGY, METHOD, SHIFT, RATIONAL, false>(nb, energy);
+__device__ __forceinline__ void pair_tiles_sw(const NbDev& nb, const ListDev& L, float& energy) {
+    if (nb.useSwitch) pair_tiles<ENERGY, METHOD, SHIFT, RATIONAL, true>(nb, L, energy);
+    else pair_tiles<ENERGY, METHOD, SHIFT, RATIONAL, false>(nb, L, energy);
 }
 
 template <bool ENERGY, int METHOD>
 __global__ void __launch_bounds__(256) k_pair(NbDev nb) {
     float energy = 0.f;
-    // counters[7]: max block half extent (float bits) recorded at list build
-    const float maxHalf = __int_as_float(nb.counters[7]);
+    const ListDev& L = nb.list[nb.counters[CT_CUR] & 1];
+    const float maxHalf = __int_as_float(L.lc[LC_MAXHALF]);       // max block half extent recorded at list build
     const BoxDev& b = nb.box;
     const float minL = fminf(b.ax, fminf(b.by, b.cz));
     const bool shiftOK = b.periodic && !b.triclinic && (0.5f*minL - nb.cutoff - 2.0f*sqrtf(nb.halfPad2) >= maxHalf);
@@ -631,12 +690,12 @@ __global__ void __launch_bounds__(256) k_pair(NbDev nb) {
     // (it cost 1e-4 relative on the 894-ion fixture); the exp-based erfc has a RELATIVE error, so it is the default.
     const bool rational = (METHOD == B200MD_NB_PME) && (nb.alpha*nb.alpha*nb.cutoff2 < PME_G_WMAX) && nb.useRational;
     if (shiftOK) {
-        if (rational) pair_tiles_sw<ENERGY, METHOD, true, true>(nb, energy);
-        else pair_tiles_sw<ENERGY, METHOD, true, false>(nb, energy);
+        if (rational) pair_tiles_sw<ENERGY, METHOD, true, true>(nb, L, energy);
+        else pair_tiles_sw<ENERGY, METHOD, true, false>(nb, L, energy);
     }
     else {
-        if (rational) pair_tiles_sw<ENERGY, METHOD, false, true>(nb, energy);
-        else pair_tiles_sw<ENERGY, METHOD, false, false>(nb, energy);
+        if (rational) pair_tiles_sw<ENERGY, METHOD, false, true>(nb, L, energy);
+        else pair_tiles_sw<ENERGY, METHOD, false, false>(nb, L, energy);
     }
     if (ENERGY) {
         for (int off = 16; off > 0; off >>= 1) energy += __shfl_xor_sync(FULL, energy, off);
@@ -649,7 +708,11 @@ static void launch_pair_m(const NbDev& nb, cudaStream_t s) {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    dim3 grid(sms*4), block(256);
+    // B200MD_PAIR_WAVES=M: M waves of short-lived CTAs instead of one wave of persistent ones, so that SM slots are handed
+    // back while the kernel runs (the reciprocal-space kernels on the high-priority stream need them)
+    static const int waves = getenv("B200MD_PAIR_WAVES") ? std::max(1, atoi(getenv("B200MD_PAIR_WAVES"))) : 1;
+    static const int perSm = getenv("B200MD_PAIR_CTAS_PER_SM") ? std::max(1, atoi(getenv("B200MD_PAIR_CTAS_PER_SM"))) : 4;
+    dim3 grid(sms*perSm*waves), block(256);
     switch (nb.method) {
         case B200MD_NB_PME: k_pair<ENERGY, B200MD_NB_PME><<<grid, block, 0, s>>>(nb); break;
         case B200MD_NB_NOCUTOFF: k_pair<ENERGY, B200MD_NB_NOCUTOFF><<<grid, block, 0, s>>>(nb); break;
@@ -663,22 +726,25 @@ void launch_pair(const NbDev& nb, bool energy, cudaStream_t s) {
 
 // diagnostic: number of pairs inside the true cutoff that the list evaluates (tile efficiency accounting)
 __global__ void k_count_pairs(NbDev nb) {
+    const ListDev& L = nb.list[nb.counters[CT_CUR] & 1];
     const int lane = threadIdx.x & 31;
     const int gwarp = (blockIdx.x*blockDim.x + threadIdx.x) >> 5;
     const int nwarps = (gridDim.x*blockDim.x) >> 5;
-    const int ntiles = min(nb.counters[0], nb.maxTiles);
+    TileCursor cursor;
+    cursor.init(nb, L, lane);
+    const int ntiles = cursor.total;
+    if (gwarp == 0 && lane == 0) L.lc[LC_USED] = ntiles;
     int count = 0;
-    for (int t = gwarp; t < ntiles; t += nwarps) {
-        if (nb.tileI[t] < 0) continue;
-        if (lane == 0) atomicAdd(&nb.counters[9], 1);          // tiles actually in use
-        const int si = nb.tileI[t]*32 + lane;
-        const float4 pi = nb.sposq[si];
-        const int mi = nb.tileMask[t];
-        const unsigned int mask = (mi < 0) ? FULL : nb.maskPool[mi*32 + lane];
+    for (int f = gwarp; f < ntiles; f += nwarps) {
+        const int t = cursor.slot(f);
+        const int si = L.tileI[t]*32 + lane;
+        const float4 pi = L.sposq[si];
+        const int mi = L.tileMask[t];
+        const unsigned int mask = (mi < 0) ? FULL : L.maskPool[mi*32 + lane];
         for (int k = 0; k < 32; k++) {
-            int jidx = nb.tileJ[t*32 + k];
+            int jidx = L.tileJ[t*32 + k];
             if (jidx < 0 || !((mask >> k) & 1u)) continue;
-            float4 pj = nb.sposq[jidx];
+            float4 pj = L.sposq[jidx];
             float3 d = make_float3(pj.x-pi.x, pj.y-pi.y, pj.z-pi.z);
             if (nb.box.periodic) d = min_image(d, nb.box);
             if (d.x*d.x + d.y*d.y + d.z*d.z < nb.cutoff2) count++;
@@ -690,6 +756,5 @@ __global__ void k_count_pairs(NbDev nb) {
 
 void launch_count_pairs(const NbDev& nb, cudaStream_t s) {
     cudaMemsetAsync(&nb.counters[5], 0, sizeof(int), s);
-    cudaMemsetAsync(&nb.counters[9], 0, sizeof(int), s);
     k_count_pairs<<<148*4, 256, 0, s>>>(nb);
 }

@@ -8,7 +8,11 @@ from openmm_b200.engine import TERM_NB_DIRECT, TERM_NB_RECIP, TERM_ALL
 mode = sys.argv[1]
 names = sys.argv[2:] or ["dhfr"]
 for name in names:
-    d = systems.SystemDesc.load(os.path.join("data", name + ".npz")).rounded()
+    if os.path.exists(os.path.join("data", name + ".npz")):
+        d = systems.SystemDesc.load(os.path.join("data", name + ".npz")).rounded()
+    else:
+        import bench
+        d = bench.load_workload(name)
     eng = Engine(d)
     if mode == "parity":
         from oracle import omm
@@ -22,12 +26,13 @@ for name in names:
     else:
         eng.set_integrator(systems.INT_LANGEVIN, 0.002, 300.0, 1.0, 7, 1e-5)
         stream = torch.cuda.ExternalStream(eng.stream())
-        eng.step(1000); eng.synchronize()
+        nst = 2000 if d.natoms < 200000 else 200
+        eng.step(nst//2); eng.synchronize()
         best = 1e9
         for rep in range(3):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(stream); eng.step(2000); e1.record(stream); torch.cuda.synchronize()
-            best = min(best, 1e3*e0.elapsed_time(e1)/2000)
+            e0.record(stream); eng.step(nst); e1.record(stream); torch.cuda.synchronize()
+            best = min(best, 1e3*e0.elapsed_time(e1)/nst)
         st = eng.stats()
         ph = {k: round(1e3*eng.time_phase(k, 20), 2) for k in ["pair", "pme_spread", "pme_fft_conv", "pme_gather", "bonded", "integrate", "list_build"]} if mode == "timeph" else {}
         print("%s %.1f us/step %.1f ns/day builds %d tiles %d %s env BT=%s PAD=%s" % (name, best, 172800.0/best, st.get("list_builds", -1), st.get("num_tiles", -1), ph,
