@@ -781,6 +781,19 @@ extern "C" int b200md_checkpoint_load(b200md_ctx* ctx, const void* buf, int64_t 
     API_END(ctx)
 }
 
+// Multi-GPU role split (replicated atoms): with PME and world > 1 the LAST rank computes reciprocal space for all atoms and
+// nothing else; the other world-1 ranks share the direct-space tiles (by i-block: list construction AND tile kernel) and the
+// bonded terms.  Returns the rank's view of the sharding.
+static bool role_split(const b200md_ctx* c) { return c->world > 1 && c->comm && c->nb.method == B200MD_NB_PME && c->haveNb; }
+static NbDev role_nb(const b200md_ctx* c) {
+    NbDev nb = c->nb;
+    if (role_split(c)) {
+        if (c->rank == c->world - 1) { nb.rank = 0; nb.world = 1; }
+        else nb.world = c->world - 1;
+    }
+    return nb;
+}
+
 // ---------------------------------------------------------------- force evaluation
 // Enqueue one force evaluation on the stream (no host sync).  Returns the number of kernels launched.
 static int enqueue_forces(b200md_ctx* c, int terms, bool energy, bool forcesAlreadyZero = false, bool inStep = false) {
@@ -794,12 +807,12 @@ static int enqueue_forces(b200md_ctx* c, int terms, bool energy, bool forcesAlre
     // other world-1 ranks share the direct-space tiles (by i-block) and the bonded terms.  The two halves of the force
     // field thus overlap on different GPUs, there is no charge-grid collective, and one int64 all-reduce of the force buffer
     // per step joins them.  (With PME and world > 1 only; otherwise every rank takes a share of everything.)
-    const bool split = c->world > 1 && c->comm && c->nb.method == B200MD_NB_PME && c->haveNb;
+    const bool split = role_split(c);
     const int pmeRank = c->world - 1;
     NbDev nbSave = c->nb;
     if (split) {
-        if (c->rank == pmeRank) { direct = false; c->nb.rank = 0; c->nb.world = 1; }
-        else { recip = false; c->nb.world = c->world - 1; }
+        if (c->rank == pmeRank) direct = false; else recip = false;
+        c->nb = role_nb(c);
     }
     struct Restore { b200md_ctx* c; NbDev saved; ~Restore() { unsigned long long h = c->nb.condHandle; c->nb = saved; c->nb.condHandle = h; } } restore{c, nbSave};
     // Reciprocal space (spread -> FFT/convolution -> gather, in USER atom order: independent of the neighbour list) and
@@ -1028,9 +1041,12 @@ extern "C" int b200md_step(b200md_ctx* ctx, int nsteps) {
     if (c->listDirty && c->haveNb) {
         // the state was changed from outside: bring the neighbour list up to date before the step graphs, whose tile
         // kernel trusts the current list (kernels gated on counters[CT_REBUILD], which the setter raised)
-        launch_check_displacement(c->nb, c->stream);
-        launch_list_build(c->nb, c->stream, 0);
-        c->kernelLaunches += 1 + list_build_launch_count();
+        if (!(role_split(c) && c->rank == c->world - 1)) {      // the reciprocal-space rank keeps no list
+            const NbDev nb = role_nb(c);
+            launch_check_displacement(nb, c->stream);
+            launch_list_build(nb, c->stream, 0);
+            c->kernelLaunches += 1 + list_build_launch_count();
+        }
         c->listDirty = false;
     }
     if (!c->stepStateValid) {
@@ -1151,6 +1167,7 @@ extern "C" int b200md_time_phase(b200md_ctx* ctx, int phase, int reps, double* m
     require(ctx->finalized, "time_phase before finalize");
     b200md_ctx* c = ctx;
     cudaStream_t s = c->stream;
+    const NbDev nbv = role_nb(c);        // the sharding the step graphs use
     cudaEvent_t e0, e1;
     CUDA_CHECK(cudaEventCreate(&e0)); CUDA_CHECK(cudaEventCreate(&e1));
     const int one = 1;
@@ -1173,13 +1190,13 @@ extern "C" int b200md_time_phase(b200md_ctx* ctx, int phase, int reps, double* m
         if (phase == 5) CUDA_CHECK(cudaMemcpyAsync(&c->counters.p[2], &one, sizeof(int), cudaMemcpyHostToDevice, s));
         CUDA_CHECK(cudaEventRecord(e0, s));
         switch (phase) {
-            case 0: launch_pair(c->nb, false, s); break;
-            case 1: launch_pme_spread(c->nb, c->pme, s); break;
-            case 2: launch_pme_fft_conv(c->nb, c->pme, false, s); break;
-            case 3: launch_pme_gather(c->nb, c->pme, s); break;
-            case 4: launch_integrate(c->nb, c->units, c->integ, s); break;
-            case 5: launch_list_build(c->nb, s); break;
-            case 6: launch_bonded(c->nb, c->bd, B200MD_TERM_ALL, false, s); break;
+            case 0: launch_pair(nbv, false, s); break;
+            case 1: launch_pme_spread(nbv, c->pme, s); break;
+            case 2: launch_pme_fft_conv(nbv, c->pme, false, s); break;
+            case 3: launch_pme_gather(nbv, c->pme, s); break;
+            case 4: launch_integrate(nbv, c->units, c->integ, s); break;
+            case 5: launch_list_build(nbv, s); break;
+            case 6: launch_bonded(nbv, c->bd, B200MD_TERM_ALL, false, s); break;
             default: throw std::runtime_error("unknown phase");
         }
         CUDA_CHECK(cudaEventRecord(e1, s));

@@ -309,6 +309,7 @@ __device__ void flush_tile(const NbDev& nb, const ListDev& L, int ib, const int*
 template <int NW>
 __global__ void __launch_bounds__(NW*32) k_build_tiles(NbDev nb, int mode) {
     if (nb.counters[mode ? CT_SOFT : CT_REBUILD] == 0) return;
+    if (nb.world > 1 && ((int) blockIdx.x % nb.world) != nb.rank) return;     // multi-GPU: tiles of this rank's i-blocks only
     const ListDev& L = nb.list[(nb.counters[CT_CUR] & 1) ^ 1];      // the list under construction
     __shared__ int sbuf[NW][64];
     __shared__ int sexcAll[32][MAX_CACHED_EXCL + 1];         // +1: odd stride, conflict-free per-lane rows
