@@ -1155,7 +1155,7 @@ extern "C" int b200md_get_stats(b200md_ctx* ctx, b200md_stats* out) {
         const int* cur = lc + LC_STRIDE*(h[CT_CUR] & 1);
         int masks = 0;
         for (int r = 0; r < TILE_REGIONS; r++) masks += cur[LC_MASKS + r];
-        out->num_tiles = cur[LC_USED]; out->num_mask_tiles = masks; out->overflow = h[3]; out->list_builds = h[4]; out->pairs_in_cutoff = h[5];
+        out->num_tiles = cur[LC_USED]; out->num_mask_tiles = masks; out->overflow = h[3]; out->list_builds = h[4]; out->pairs_in_cutoff = h[5]; out->stale_list_steps = h[CT_STALE];
     }
     out->force_evals = ctx->forceEvals; out->kernel_launches = ctx->kernelLaunches;
     out->pme_grid[0] = ctx->pme.nx; out->pme_grid[1] = ctx->pme.ny; out->pme_grid[2] = ctx->pme.nz; out->ewald_alpha = ctx->pme.alpha;
