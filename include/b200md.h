@@ -172,6 +172,20 @@ int b200md_fft3d_r2c(int device, int nx, int ny, int nz, const float* in, float*
 int b200md_fft3d_c2r(int device, int nx, int ny, int nz, const float* in, float* out);
 void* b200md_cuda_stream(b200md_ctx* ctx);
 
+/* ---------------------------------------------------------------------------------------------------
+ * Stand-alone reciprocal-space PME: the narrow drop-in behind the reference's
+ * CalcPmeReciprocalForceKernel (olla/include/openmm/kernels.h:1493-1557), the hook through which the CPU platform
+ * (CpuKernels.cpp:620-690) and the CUDA platform (CudaKernels.cpp:746-760, UseCpuPme) outsource reciprocal space to
+ * plugins/cpupme.  plugin/libOpenMMB200Pme.so registers a kernel of that name that forwards to these two calls.
+ *   create: CalcPmeReciprocalForceKernel::initialize(gridx, gridy, gridz, numParticles, alpha, deterministic);
+ *           every grid dimension must factor into radices <= 13 (the caller rounds up, as cpupme does);
+ *   exec:   beginComputation + finishComputation: posq = [natoms][4] floats (x, y, z, charge in e: IO::getPosq),
+ *           box = the three periodic box vectors row by row, force4 = [natoms][4] floats (IO::setForce layout, 4th
+ *           element untouched), *energy = reciprocal-space energy WITHOUT the Ewald self term (as cpupme returns it).
+ * Destroy with b200md_destroy.                                                                       */
+int b200md_pme_create(b200md_ctx** out, int device, int natoms, int nx, int ny, int nz, double alpha);
+int b200md_pme_exec(b200md_ctx* ctx, const float* posq, const double box[9], int include_energy, float* force4, double* energy);
+
 #ifdef __cplusplus
 }
 #endif

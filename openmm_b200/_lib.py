@@ -68,6 +68,8 @@ SIGNATURES = {
     "b200md_time_phase": (C.c_int, [_P, C.c_int, C.c_int, _D]),
     "b200md_fft3d_r2c": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, _F, _F]),
     "b200md_fft3d_c2r": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, _F, _F]),
+    "b200md_pme_create": (C.c_int, [C.POINTER(_P), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double]),
+    "b200md_pme_exec": (C.c_int, [_P, _F, _D, C.c_int, _F, _D]),
     "b200md_cuda_stream": (_P, [_P]),
 }
 

@@ -61,6 +61,7 @@ struct b200md_ctx {
     cudaEvent_t evFork = nullptr, evJoin = nullptr, evListFork = nullptr, evListJoin = nullptr;
     bool asyncList = false;             // B200MD_ASYNC_LIST=1: build the successor list beside the step (see enqueue_forces)
     bool specPair = true;               // step graphs: the tile kernel does not wait for a rebuild IF node (needs asyncList)
+    bool pmeOnly = false;               // b200md_pme_create: reciprocal space only, no neighbour list is ever built
     bool listDirty = true;              // state changed from outside: rebuild synchronously before the next step graph
     double softFrac = 0.7;
     float softPad2 = 3e38f;
@@ -81,7 +82,7 @@ struct b200md_ctx {
     bool haveOrigin = false;
     double padFrac = 0.10;
     // ---- device state ----
-    DevBuf<float4> posq, velm, sposq[2], swrap[2], refPos, atomShift, blockCenter[2], blockHalf[2];
+    DevBuf<float4> posq, velm, sposq[2], swrap[2], refPos, atomShift, blockCenter[2], blockHalf[2], superCenter[2], superHalf[2];
     DevBuf<float2> sigeps, ssigeps[2];
     DevBuf<long long> force;
     DevBuf<double> energy, cmScratch;
@@ -297,8 +298,8 @@ static void setup_cells(b200md_ctx* c) {
         std::vector<int> rank;
         cell_order(nc, rank);
         c->cellRank.upload(rank);
-        c->cellCount.alloc(ncells + 1);
-        c->cellFill.alloc(ncells);
+        c->cellCount.alloc(ncells + 1); c->cellCount.zero();     // every list build leaves them zeroed again (k_block_bounds)
+        c->cellFill.alloc(ncells); c->cellFill.zero();
         c->nb.ncells = ncells;
         for (int d = 0; d < 3; d++) c->nb.ncell[d] = nc[d];
         c->nb.cellRank = c->cellRank.p; c->nb.cellCount = c->cellCount.p; c->nb.cellFill = c->cellFill.p;
@@ -529,6 +530,8 @@ extern "C" int b200md_finalize(b200md_ctx* ctx) {
         c->sorig[l].alloc(NP); c->sorig[l].zero(); c->blockCenter[l].alloc(c->nblocks); c->blockHalf[l].alloc(c->nblocks);
         ListDev& L = c->nb.list[l];
         L.sposq = c->sposq[l].p; L.ssigeps = c->ssigeps[l].p; L.swrap = c->swrap[l].p; L.sorig = c->sorig[l].p;
+        c->superCenter[l].alloc((c->nblocks + 31)/32); c->superHalf[l].alloc((c->nblocks + 31)/32);
+        L.superCenter = c->superCenter[l].p; L.superHalf = c->superHalf[l].p;
         L.blockCenter = c->blockCenter[l].p; L.blockHalf = c->blockHalf[l].p; L.lc = c->listCounters.p + LC_STRIDE*l;
     }
     c->force.alloc((size_t) 3*NP); c->force.zero();
@@ -593,6 +596,7 @@ extern "C" int b200md_finalize(b200md_ctx* ctx) {
             poolCap = std::min(poolCap, 1.25*est/TILE_REGIONS + 64);     // + slack for the imbalance between pools
         }
         poolCap = std::min(poolCap, 16.0e6/TILE_REGIONS);
+        if (c->pmeOnly) poolCap = 1;
         nb.maxTiles = ((int) poolCap + 1)*TILE_REGIONS;
         for (int l = 0; l < 2; l++) {
             c->tileI[l].alloc(nb.maxTiles); c->tileJ[l].alloc((size_t) nb.maxTiles*32); c->tileMask[l].alloc(nb.maxTiles); c->maskPool[l].alloc((size_t) nb.maxTiles*32);
@@ -1138,6 +1142,48 @@ extern "C" int b200md_comm_init(b200md_ctx* ctx, int rank, int world, const void
     rc = g_nccl.AllReduce(warm.p, warm.p, 64, NCCL_INT64, NCCL_SUM, ctx->comm, ctx->stream);
     if (rc != 0) throw std::runtime_error("ncclAllReduce warm-up failed");
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    API_END(ctx)
+}
+
+// ---------------------------------------------------------------- stand-alone reciprocal space (CalcPmeReciprocalForceKernel)
+extern "C" int b200md_pme_create(b200md_ctx** out, int device, int natoms, int nx, int ny, int nz, double alpha) {
+    int rc = b200md_create(out, device, natoms);
+    if (rc != 0) return rc;
+    b200md_ctx* c = *out;
+    c->pmeOnly = true;
+    std::vector<double> one(natoms, 1.0), zero(natoms, 0.0);
+    b200md_nonbonded_desc d = b200md_nonbonded_desc{};
+    d.method = B200MD_NB_PME; d.cutoff = 0.01; d.ewald_alpha = alpha; d.grid[0] = nx; d.grid[1] = ny; d.grid[2] = nz;
+    rc = b200md_set_masses(c, one.data());
+    if (rc == 0) rc = b200md_set_nonbonded(c, &d, zero.data(), one.data(), zero.data());
+    return rc;          // finalised at the first exec, when the box is known
+}
+
+extern "C" int b200md_pme_exec(b200md_ctx* ctx, const float* posq, const double box[9], int include_energy, float* force4, double* energy) {
+    if (!ctx) return -1;
+    if (!ctx->finalized || std::memcmp(box, ctx->boxA, 3*sizeof(double)) || std::memcmp(box+3, ctx->boxB, 3*sizeof(double)) || std::memcmp(box+6, ctx->boxC, 3*sizeof(double))) {
+        int rc = b200md_set_box(ctx, box, box+3, box+6);
+        if (rc == 0 && !ctx->finalized) rc = b200md_finalize(ctx);
+        if (rc != 0) return rc;
+    }
+    API_BEGIN(ctx)
+    require(ctx->pmeOnly, "b200md_pme_exec on a context that was not made by b200md_pme_create");
+    b200md_ctx* c = ctx;
+    const float sk = (float) std::sqrt(B200MD_ONE_4PI_EPS0);
+    std::vector<float4> h(c->npad, make_float4(0, 0, 0, 0));
+    for (int i = 0; i < c->natoms; i++) h[i] = make_float4(posq[4*i], posq[4*i+1], posq[4*i+2], posq[4*i+3]*sk);
+    CUDA_CHECK(cudaMemcpyAsync(c->posq.p, h.data(), sizeof(float4)*c->npad, cudaMemcpyHostToDevice, c->stream));
+    c->kernelLaunches += enqueue_forces(c, B200MD_TERM_NB_RECIP, include_energy != 0);
+    c->forceEvals++;
+    c->hforce.resize((size_t) 3*c->npad);
+    double he[B200MD_NUM_ENERGY] = {0};
+    CUDA_CHECK(cudaMemcpyAsync(c->hforce.data(), c->force.p, sizeof(long long)*3*c->npad, cudaMemcpyDeviceToHost, c->stream));
+    if (include_energy) CUDA_CHECK(cudaMemcpyAsync(he, c->energy.p, sizeof(he), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    const double s = 1.0/B200MD_FORCE_SCALE;
+    for (int i = 0; i < c->natoms; i++)
+        for (int k = 0; k < 3; k++) force4[4*i+k] = (float) (s*(double) c->hforce[(size_t) k*c->npad + i]);
+    if (energy) *energy = include_energy ? he[EN_RECIP] : 0.0;
     API_END(ctx)
 }
 

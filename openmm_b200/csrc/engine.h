@@ -49,6 +49,8 @@ struct ListDev {
     int* sorig;                  // sorted slot -> user atom (-1 for padding)
     float4* blockCenter;
     float4* blockHalf;
+    float4* superCenter;         // bounding boxes of superblocks of 32 consecutive blocks (first level of the candidate search)
+    float4* superHalf;
     int* tileI;                  // [maxTiles]
     int* tileJ;                  // [maxTiles*32]
     int* tileMask;               // [maxTiles] index into maskPool or -1
