@@ -846,7 +846,10 @@ static int enqueue_forces(b200md_ctx* c, int terms, bool energy, bool forcesAlre
         const cudaGraphNode_t* deps = nullptr;
         size_t ndeps = 0;
         CUDA_CHECK(cudaStreamGetCaptureInfo_v2(s, &cap, nullptr, &graph, &deps, &ndeps));
-        if (cap == cudaStreamCaptureStatusActive && c->useCond) {
+        // With the two-launch list build a NOT-taken rebuild costs ~4 us of gated kernels in front of the tile kernel, an IF
+        // node ~15 us: the IF nodes are kept for the 7-launch build and for the side-stream successor build only.
+        const bool wantCond = c->useCond && (!list_build_merged() || (inStep && c->asyncList && c->softPad2 < c->nb.halfPad2));
+        if (cap == cudaStreamCaptureStatusActive && wantCond) {
             // the rebuild kernels live in an IF node of the step graph: zero launches on the (usual) steps without a rebuild
             // Inside a step, a second IF node builds the SUCCESSOR list on a side stream as soon as some atom has used up
             // softFrac of its allowance: the current list is still valid for this step's forces, the new one takes over when
@@ -932,6 +935,7 @@ static void check_flags(b200md_ctx* c) {
     int h[8];
     CUDA_CHECK(cudaMemcpyAsync(h, c->counters.p, sizeof(int)*8, cudaMemcpyDeviceToHost, c->stream));
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    if (h[3] == 2) throw std::runtime_error("B200 platform: neighbour-list construction timed out at a grid barrier (k_list_prep)");
     if (h[3]) throw std::runtime_error("B200 platform: neighbour-list tile capacity exceeded (" + std::to_string(c->nb.maxTiles) + " tiles)");
 }
 

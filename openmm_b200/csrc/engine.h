@@ -62,7 +62,8 @@ struct ListDev {
 enum { LC_TILES = 0, LC_MASKS = TILE_REGIONS, LC_MAXHALF = 2*TILE_REGIONS, LC_USED = 2*TILE_REGIONS + 1, LC_STRIDE = 128 };
 
 // indices into NbDev::counters
-enum { CT_REBUILD = 2, CT_OVERFLOW = 3, CT_BUILDS = 4, CT_PAIRS = 5, CT_LASTBLOCK = 8, CT_CUR = 10, CT_SOFT = 11, CT_PENDING = 12, CT_STALE = 13, CT_CURSOR = 14 };
+enum { CT_REBUILD = 2, CT_OVERFLOW = 3, CT_BUILDS = 4, CT_PAIRS = 5, CT_LASTBLOCK = 8, CT_CUR = 10, CT_SOFT = 11, CT_PENDING = 12, CT_STALE = 13, CT_CURSOR = 14,
+       CT_BTDONE = 7, CT_BAR = 9, CT_BAREXIT = 15 };      // k_build_tiles completion count; grid barrier of k_list_prep
 
 struct NbDev {
     BoxDev box;
@@ -175,6 +176,7 @@ __device__ __forceinline__ long long float_to_fixed(float f) {           // |f| 
 
 // ---- launchers (defined in the .cu files) ----
 void launch_check_displacement(const NbDev& nb, cudaStream_t s);
+bool list_build_merged();        // list build = 2 gated launches (k_list_prep with grid barriers + k_build_tiles); B200MD_LIST_MERGED=0: 7
 void launch_list_build(const NbDev& nb, cudaStream_t s, int mode = 0);   // all list kernels, gated on counters[CT_REBUILD] (mode 0) or counters[CT_SOFT] (mode 1)
 void launch_pair(const NbDev& nb, bool energy, cudaStream_t s);
 void launch_count_pairs(const NbDev& nb, cudaStream_t s);

@@ -115,10 +115,7 @@ __global__ void __launch_bounds__(256) k_check_gather(NbDev nb) {
 
 // ------------------------------------------------------------------------------------------------
 // 2. binning (periodic systems only; non-periodic systems keep the identity order)
-__global__ void k_bin_atoms(NbDev nb, int mode) {
-    if (nb.counters[mode ? CT_SOFT : CT_REBUILD] == 0) return;
-    int a = blockIdx.x*blockDim.x + threadIdx.x;
-    if (a >= nb.natoms) return;
+__device__ __forceinline__ void bin_atom(const NbDev& nb, int a) {
     float4 p = nb.posq[a];
     int key = 0;
     float4 shift = make_float4(0, 0, 0, 0);
@@ -149,11 +146,14 @@ __global__ void k_bin_atoms(NbDev nb, int mode) {
     nb.atomShift[a] = shift;
     atomicAdd(&nb.cellCount[key], 1);
 }
+__global__ void k_bin_atoms(NbDev nb, int mode) {
+    if (nb.counters[mode ? CT_SOFT : CT_REBUILD] == 0) return;
+    int a = blockIdx.x*blockDim.x + threadIdx.x;
+    if (a < nb.natoms) bin_atom(nb, a);
+}
 
 // exclusive scan of cellCount[0..ncells) into cellCount (in place), single block
-__global__ void k_scan_cells(NbDev nb, int mode) {
-    if (nb.counters[mode ? CT_SOFT : CT_REBUILD] == 0) return;
-    __shared__ int partial[1024];
+__device__ void scan_cells_block(const NbDev& nb, int* partial) {      // one CTA, partial[blockDim.x] in shared memory
     int n = nb.ncells;
     int per = (n + blockDim.x - 1)/blockDim.x;
     int begin = threadIdx.x*per, end = min(begin+per, n);
@@ -176,21 +176,24 @@ __global__ void k_scan_cells(NbDev nb, int mode) {
     }
     if (threadIdx.x == 0) nb.cellCount[n] = nb.natoms;
 }
-
-__global__ void k_fill_cells(NbDev nb, int mode) {
+__global__ void k_scan_cells(NbDev nb, int mode) {
     if (nb.counters[mode ? CT_SOFT : CT_REBUILD] == 0) return;
-    int a = blockIdx.x*blockDim.x + threadIdx.x;
-    if (a >= nb.natoms) return;
+    __shared__ int partial[1024];
+    scan_cells_block(nb, partial);
+}
+
+__device__ __forceinline__ void fill_atom(const NbDev& nb, int a) {
     int key = nb.atomCell[a];
     int slot = nb.cellCount[key] + atomicAdd(&nb.cellFill[key], 1);
     nb.tmpSorted[slot] = a;
 }
-
-__global__ void k_finalize_sort(NbDev nb, int mode) {
+__global__ void k_fill_cells(NbDev nb, int mode) {
     if (nb.counters[mode ? CT_SOFT : CT_REBUILD] == 0) return;
-    const ListDev& L = nb.list[(nb.counters[CT_CUR] & 1) ^ 1];      // the list under construction
-    int s = blockIdx.x*blockDim.x + threadIdx.x;
-    if (s >= nb.npad) return;
+    int a = blockIdx.x*blockDim.x + threadIdx.x;
+    if (a < nb.natoms) fill_atom(nb, a);
+}
+
+__device__ __forceinline__ void finalize_slot(const NbDev& nb, const ListDev& L, int s) {
     if (s < nb.natoms) {
         int a = s;
         if (nb.box.periodic) {
@@ -218,6 +221,12 @@ __global__ void k_finalize_sort(NbDev nb, int mode) {
         L.ssigeps[s] = make_float2(0, 0);
         // position is filled by k_block_bounds with a copy of a real atom of the same block
     }
+}
+__global__ void k_finalize_sort(NbDev nb, int mode) {
+    if (nb.counters[mode ? CT_SOFT : CT_REBUILD] == 0) return;
+    const ListDev& L = nb.list[(nb.counters[CT_CUR] & 1) ^ 1];      // the list under construction
+    int s = blockIdx.x*blockDim.x + threadIdx.x;
+    if (s < nb.npad) finalize_slot(nb, L, s);
 }
 
 // one warp per block of 32 sorted atoms: axis-aligned bounding box (findBlockBounds, findInteractingBlocks.cu:7-52)
@@ -269,6 +278,105 @@ __global__ void __launch_bounds__(1024) k_block_bounds(NbDev nb, int mode) {
         nb.cellCount[i] = 0;
         if (i < nb.ncells) nb.cellFill[i] = 0;
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// The five kernels above as ONE launch with software grid barriers between the phases.  Why: a rebuild is needed every
+// ~4th step only, and what the other steps pay for it is what a NOT-taken rebuild costs in front of the tile kernel: ~15 us
+// of latency for a CUDA-graph IF node, or ~2 us per gated kernel that only reads the flag and returns.  Two gated launches
+// (this one and k_build_tiles) cost ~4 us.  The grid is sized to be co-resident (<= 2 CTAs of 256 threads per SM); CTAs
+// that find no free slot yet (the charge spreading runs beside it) join late, the others wait for them at the first
+// barrier, and every wait is bounded (a time-out raises the sticky error flag instead of hanging the device).
+__device__ __forceinline__ void grid_barrier(const NbDev& nb, int target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(&nb.counters[CT_BAR], 1);
+        long spins = 0;
+        while (*((volatile int*) &nb.counters[CT_BAR]) < target) {
+            __nanosleep(32);
+            if (++spins > (1L << 20)) { nb.counters[CT_OVERFLOW] = 2; break; }
+        }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+__device__ void list_prep_phases(const NbDev& nb, const ListDev& L, int* partial) {
+    const int G = gridDim.x;
+    const int gtid = blockIdx.x*blockDim.x + threadIdx.x, gthreads = G*blockDim.x;
+    const int lane = threadIdx.x & 31, gwarp = gtid >> 5, gwarps = gthreads >> 5;
+    // 1. binning
+    for (int a = gtid; a < nb.natoms; a += gthreads) bin_atom(nb, a);
+    grid_barrier(nb, G);
+    // 2. exclusive scan of the cell counts (one CTA)
+    if (blockIdx.x == 0) scan_cells_block(nb, partial);
+    grid_barrier(nb, 2*G);
+    // 3. atoms into their cells
+    for (int a = gtid; a < nb.natoms; a += gthreads) fill_atom(nb, a);
+    grid_barrier(nb, 3*G);
+    // 4. deterministic in-cell order, sorted copies
+    for (int s = gtid; s < nb.npad; s += gthreads) finalize_slot(nb, L, s);
+    grid_barrier(nb, 4*G);
+    // 5. block bounding boxes (one warp per block); the binning counters are consumed: zero them for the next build
+    for (int b = gwarp; b < nb.nblocks; b += gwarps) {
+        const int s = b*32 + lane;
+        const int sl = min(s, nb.natoms-1);
+        const float4 p = L.swrap[sl];
+        if (s >= nb.natoms) { L.swrap[s] = make_float4(p.x, p.y, p.z, 0.f); L.sposq[s] = make_float4(p.x, p.y, p.z, 0.f); }
+        float lox = p.x, hix = p.x, loy = p.y, hiy = p.y, loz = p.z, hiz = p.z;
+        for (int off = 16; off > 0; off >>= 1) {
+            lox = fminf(lox, __shfl_xor_sync(FULL, lox, off)); hix = fmaxf(hix, __shfl_xor_sync(FULL, hix, off));
+            loy = fminf(loy, __shfl_xor_sync(FULL, loy, off)); hiy = fmaxf(hiy, __shfl_xor_sync(FULL, hiy, off));
+            loz = fminf(loz, __shfl_xor_sync(FULL, loz, off)); hiz = fmaxf(hiz, __shfl_xor_sync(FULL, hiz, off));
+        }
+        if (lane == 0) {
+            L.blockCenter[b] = make_float4(0.5f*(lox+hix), 0.5f*(loy+hiy), 0.5f*(loz+hiz), 0);
+            L.blockHalf[b] = make_float4(0.5f*(hix-lox), 0.5f*(hiy-loy), 0.5f*(hiz-loz), 0);
+            atomicMax(&L.lc[LC_MAXHALF], __float_as_int(0.5f*fmaxf(hix-lox, fmaxf(hiy-loy, hiz-loz))));
+        }
+    }
+    for (int i = gtid; i <= nb.ncells; i += gthreads) {
+        nb.cellCount[i] = 0;
+        if (i < nb.ncells) nb.cellFill[i] = 0;
+    }
+    if (gtid < TILE_REGIONS) { L.lc[LC_TILES + gtid] = 0; L.lc[LC_MASKS + gtid] = 0; }
+    grid_barrier(nb, 5*G);
+    // 6. superblock boxes (one warp per 32 blocks)
+    const int nsuper = (nb.nblocks + 31) >> 5;
+    for (int sb = gwarp; sb < nsuper; sb += gwarps) {
+        const int b = sb*32 + lane;
+        float lox = 3e38f, hix = -3e38f, loy = 3e38f, hiy = -3e38f, loz = 3e38f, hiz = -3e38f;
+        if (b < nb.nblocks) {
+            const float4 c = L.blockCenter[b], h = L.blockHalf[b];
+            lox = c.x - h.x; hix = c.x + h.x; loy = c.y - h.y; hiy = c.y + h.y; loz = c.z - h.z; hiz = c.z + h.z;
+        }
+        for (int off = 16; off > 0; off >>= 1) {
+            lox = fminf(lox, __shfl_xor_sync(FULL, lox, off)); hix = fmaxf(hix, __shfl_xor_sync(FULL, hix, off));
+            loy = fminf(loy, __shfl_xor_sync(FULL, loy, off)); hiy = fmaxf(hiy, __shfl_xor_sync(FULL, hiy, off));
+            loz = fminf(loz, __shfl_xor_sync(FULL, loz, off)); hiz = fmaxf(hiz, __shfl_xor_sync(FULL, hiz, off));
+        }
+        if (lane == 0) {
+            L.superCenter[sb] = make_float4(0.5f*(lox+hix), 0.5f*(loy+hiy), 0.5f*(loz+hiz), 0);
+            L.superHalf[sb] = make_float4(0.5f*(hix-lox), 0.5f*(hiy-loy), 0.5f*(hiz-loz), 0);
+        }
+    }
+}
+// the last CTA to leave re-arms the barrier for the next build
+__device__ __forceinline__ void grid_barrier_exit(const NbDev& nb) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(&nb.counters[CT_BAREXIT], 1) == (int) gridDim.x - 1) { nb.counters[CT_BAR] = 0; nb.counters[CT_BAREXIT] = 0; }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_list_prep(NbDev nb, int mode) {
+    if (nb.counters[mode ? CT_SOFT : CT_REBUILD] == 0) return;
+    const ListDev& L = nb.list[(nb.counters[CT_CUR] & 1) ^ 1];      // the list under construction
+    __shared__ int partial[256];
+    list_prep_phases(nb, L, partial);
+    grid_barrier_exit(nb);
 }
 
 #define MAX_CACHED_EXCL 24
@@ -327,24 +435,44 @@ __device__ void flush_tile(const NbDev& nb, const ListDev& L, int ib, const int*
 // buffers are merged, sorted and flushed by warp 0 at the end, so an i-block still ends with at most one partial tile.
 // (findBlocksWithInteractions, findInteractingBlocks.cu:180-405, is the reference counterpart.  Round-1 profile: with a
 // single warp per i-block the kernel was one long dependent chain of L2 round trips per block, 150 us at DHFR size.)
+// end of a list build: the new list becomes current at once (mode 0) or when the integrator has finished (mode 1)
+__device__ __forceinline__ void list_done(const NbDev& nb, int mode) {
+    nb.counters[CT_BUILDS] += 1;
+    if (mode) { nb.counters[CT_SOFT] = 0; nb.counters[CT_PENDING] = 1; }   // built beside the step: the integrator's last block flips
+    else { nb.counters[CT_REBUILD] = 0; nb.counters[CT_SOFT] = 0; nb.counters[CT_CUR] ^= 1; }
+}
+// fused variant: the last CTA of k_build_tiles to finish closes the build (saves the k_list_done launch)
+__device__ __forceinline__ void list_block_done(const NbDev& nb, int mode, int fused) {
+    if (!fused) return;
+    __threadfence();
+    if (atomicAdd(&nb.counters[CT_BTDONE], 1) == (int) gridDim.x - 1) {
+        nb.counters[CT_BTDONE] = 0;
+        list_done(nb, mode);
+    }
+}
+
+// shared-memory working set of one i-block under construction (one group of NW warps)
 template <int NW>
-__global__ void __launch_bounds__(NW*32) k_build_tiles(NbDev nb, int mode) {
-    if (nb.counters[mode ? CT_SOFT : CT_REBUILD] == 0) return;
-    if (nb.world > 1 && ((int) blockIdx.x % nb.world) != nb.rank) return;     // multi-GPU: tiles of this rank's i-blocks only
-    const ListDev& L = nb.list[(nb.counters[CT_CUR] & 1) ^ 1];      // the list under construction
-    __shared__ int sbuf[NW][64];
-    __shared__ int sexcAll[32][MAX_CACHED_EXCL + 1];         // +1: odd stride, conflict-free per-lane rows
-    __shared__ float4 sipos[32];                             // the i-block's atoms, relative to the block centre
-    __shared__ int sleft[NW];
-    __shared__ int sbList[SB_MAX];                           // superblocks within range of this i-block
-    __shared__ int sbCount;
-    __shared__ int smerged[NW*32];
-    const int w = threadIdx.x >> 5;
-    const int lane = threadIdx.x & 31;
-    const int ib = blockIdx.x;
-    int* buf = sbuf[w];
+struct BuildSmem {
+    int sbuf[NW][64];
+    int sexcAll[32][MAX_CACHED_EXCL + 1];         // +1: odd stride, conflict-free per-lane rows
+    float4 sipos[32];                             // the i-block's atoms, relative to the block centre
+    int sleft[NW];
+    int sbList[SB_MAX];                           // superblocks within range of this i-block
+    int sbCount;
+    int smerged[NW*32];
+};
+// barrier over the NW warps that build one i-block (a named barrier, so that several groups could share a CTA)
+__device__ __forceinline__ void group_sync(int barId, int nthreads) {
+    asm volatile("bar.sync %0, %1;" :: "r"(barId), "r"(nthreads) : "memory");
+}
+
+// All tiles of i-block ib, by a group of NW warps (w = warp within the group).
+template <int NW>
+__device__ void build_tiles_iblock(const NbDev& nb, const ListDev& L, int ib, int w, int lane, BuildSmem<NW>& S, int barId) {
+    int* buf = S.sbuf[w];
     // this lane's exclusion partners, translated to sorted indices ONCE per i-block
-    int* sexc = sexcAll[lane];
+    int* sexc = S.sexcAll[lane];
     int nexc = 0, e0 = 0;
     {
         const int si = ib*32 + lane;
@@ -361,9 +489,9 @@ __global__ void __launch_bounds__(NW*32) k_build_tiles(NbDev nb, int mode) {
     if (w == 0) {
         const float4 p = L.swrap[ib*32 + lane];            // padding slots hold a copy of a real atom of the block
         const float qx = p.x-ci.x, qy = p.y-ci.y, qz = p.z-ci.z;
-        sipos[lane] = make_float4(qx, qy, qz, qx*qx + qy*qy + qz*qz);
+        S.sipos[lane] = make_float4(qx, qy, qz, qx*qx + qy*qy + qz*qz);
     }
-    __syncthreads();
+    group_sync(barId, NW*32);
     const bool periodic = nb.box.periodic != 0;
     const bool allPairs = (nb.method == B200MD_NB_NOCUTOFF);
     // same condition as the pair kernel's SHIFT mode (counters[7] = max block half extent of THIS build)
@@ -380,7 +508,7 @@ __global__ void __launch_bounds__(NW*32) k_build_tiles(NbDev nb, int mode) {
     const int nsuper = (nb.nblocks + 31) >> 5;
     for (int chunk = ib >> 5; chunk < nsuper; chunk += SB_MAX) {
     const int chunkEnd = min(chunk + SB_MAX, nsuper);
-    __syncthreads();
+    group_sync(barId, NW*32);
     if (w == 0) {
         int cnt = 0;
         for (int s0 = chunk; s0 < chunkEnd; s0 += 32) {
@@ -396,16 +524,16 @@ __global__ void __launch_bounds__(NW*32) k_build_tiles(NbDev nb, int mode) {
                 }
             }
             const unsigned int m = __ballot_sync(FULL, ok);
-            if (ok) sbList[cnt + __popc(m & ((1u << lane) - 1u))] = sb;
+            if (ok) S.sbList[cnt + __popc(m & ((1u << lane) - 1u))] = sb;
             cnt += __popc(m);
         }
-        if (lane == 0) sbCount = cnt;
+        if (lane == 0) S.sbCount = cnt;
     }
-    __syncthreads();
-    const int nvirt = sbCount*32;
+    group_sync(barId, NW*32);
+    const int nvirt = S.sbCount*32;
     for (int it = 0; w + NW*32*it < nvirt; it++) {
         const int v = w + NW*(32*it + lane);
-        const int jb = (v < nvirt) ? sbList[v >> 5]*32 + (v & 31) : nb.nblocks;
+        const int jb = (v < nvirt) ? S.sbList[v >> 5]*32 + (v & 31) : nb.nblocks;
         bool cand = false;
         if (jb < nb.nblocks && jb >= ib) {
             if (allPairs || jb == ib) cand = true;
@@ -421,7 +549,7 @@ __global__ void __launch_bounds__(NW*32) k_build_tiles(NbDev nb, int mode) {
             int b = __ffs(bits) - 1;
             bits &= bits - 1;
             const int vb = w + NW*(32*it + b);
-            int jblk = sbList[vb >> 5]*32 + (vb & 31);
+            int jblk = S.sbList[vb >> 5]*32 + (vb & 31);
             int sj = jblk*32 + lane;
             bool inc = false;
             if (sj < nb.natoms) {
@@ -441,7 +569,7 @@ __global__ void __launch_bounds__(NW*32) k_build_tiles(NbDev nb, int mode) {
                         const float thr = nb.paddedCutoff2*1.00001f - (d.x*d.x + d.y*d.y + d.z*d.z);
                         inc = false;
                         for (int k = 0; k < 32; k++) {
-                            const float4 q = sipos[k];
+                            const float4 q = S.sipos[k];
                             if (fmaf(mx, q.x, fmaf(my, q.y, fmaf(mz, q.z, q.w))) < thr) { inc = true; break; }
                         }
                     }
@@ -469,57 +597,81 @@ __global__ void __launch_bounds__(NW*32) k_build_tiles(NbDev nb, int mode) {
         }
     }
     }   // superblock chunks
-    // merge the four partial buffers (each ascending, < 32 entries): rank sort into smerged, flush by warp 0
-    if (lane == 0) sleft[w] = nbuf;
-    __syncthreads();
+    // merge the four partial buffers (each ascending, < 32 entries): rank sort into S.smerged, flush by warp 0
+    if (lane == 0) S.sleft[w] = nbuf;
+    group_sync(barId, NW*32);
     int total = 0;
-    for (int q = 0; q < NW; q++) total += sleft[q];
+    for (int q = 0; q < NW; q++) total += S.sleft[q];
     if (lane < nbuf) {
         const int v = buf[lane];
         int rank = 0;
         for (int q = 0; q < NW; q++) {
-            const int nq = sleft[q];
-            for (int k = 0; k < nq; k++) rank += (sbuf[q][k] < v);
+            const int nq = S.sleft[q];
+            for (int k = 0; k < nq; k++) rank += (S.sbuf[q][k] < v);
         }
-        smerged[rank] = v;                 // sorted indices are unique, so ranks are a permutation
+        S.smerged[rank] = v;                 // sorted indices are unique, so ranks are a permutation
     }
-    __syncthreads();
+    group_sync(barId, NW*32);
     for (int off = 32*w; off < total; off += 32*NW)
-        flush_tile(nb, L, ib, smerged + off, min(32, total - off), false, lane, sexc, nexc, e0);
+        flush_tile(nb, L, ib, S.smerged + off, min(32, total - off), false, lane, sexc, nexc, e0);
+    group_sync(barId, NW*32);          // the group's shared memory is reused by its next i-block
+}
+
+template <int NW>
+__global__ void __launch_bounds__(NW*32) k_build_tiles(NbDev nb, int mode, int fused) {
+    if (nb.counters[mode ? CT_SOFT : CT_REBUILD] == 0) return;
+    if (nb.world > 1 && ((int) blockIdx.x % nb.world) != nb.rank) {           // multi-GPU: tiles of this rank's i-blocks only
+        if (threadIdx.x == 0) list_block_done(nb, mode, fused);
+        return;
+    }
+    const ListDev& L = nb.list[(nb.counters[CT_CUR] & 1) ^ 1];      // the list under construction
+    __shared__ BuildSmem<NW> S;
+    build_tiles_iblock<NW>(nb, L, blockIdx.x, threadIdx.x >> 5, threadIdx.x & 31, S, 1);
+    if (threadIdx.x == 0) list_block_done(nb, mode, fused);
 }
 
 __global__ void k_list_done(NbDev nb, int mode) {
     if (nb.counters[mode ? CT_SOFT : CT_REBUILD] == 0) return;
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
-        nb.counters[4] += 1;
-        if (mode) { nb.counters[CT_SOFT] = 0; nb.counters[CT_PENDING] = 1; }   // built beside the step: the integrator's last block flips
-        else { nb.counters[CT_REBUILD] = 0; nb.counters[CT_SOFT] = 0; nb.counters[CT_CUR] ^= 1; }
-    }
+    if (threadIdx.x == 0 && blockIdx.x == 0) list_done(nb, mode);
 }
 
 void launch_check_displacement(const NbDev& nb, cudaStream_t s) {
     k_check_gather<<<(nb.npad+255)/256, 256, 0, s>>>(nb);
 }
 
-int list_build_launch_count() { return 7; }
+// B200MD_LIST_MERGED=0: the six separate kernels instead of k_list_prep + k_build_tiles
+bool list_build_merged() {
+    static const bool m = getenv("B200MD_LIST_MERGED") ? atoi(getenv("B200MD_LIST_MERGED")) != 0 : true;
+    return m;
+}
+int list_build_launch_count() { return list_build_merged() ? 2 : 7; }
 
 void launch_list_build(const NbDev& nb, cudaStream_t s, int mode) {
     // kernels only (this sequence is also the body of a CUDA-graph conditional node); each returns immediately unless
-    // counters[2] is set
-    int nbk = (nb.natoms+255)/256;
-    k_bin_atoms<<<nbk, 256, 0, s>>>(nb, mode);
-    k_scan_cells<<<1, 1024, 0, s>>>(nb, mode);
-    k_fill_cells<<<nbk, 256, 0, s>>>(nb, mode);
-    k_finalize_sort<<<(nb.npad+255)/256, 256, 0, s>>>(nb, mode);
-    k_block_bounds<<<(nb.nblocks+31)/32, 1024, 0, s>>>(nb, mode);
+    // its flag (counters[CT_REBUILD] / counters[CT_SOFT]) is set
+    const int merged = list_build_merged() ? 1 : 0;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (merged) {
+        k_list_prep<<<std::max(1, std::min((nb.npad + 255)/256, 2*sms)), 256, 0, s>>>(nb, mode);
+    }
+    else {
+        int nbk = (nb.natoms+255)/256;
+        k_bin_atoms<<<nbk, 256, 0, s>>>(nb, mode);
+        k_scan_cells<<<1, 1024, 0, s>>>(nb, mode);
+        k_fill_cells<<<nbk, 256, 0, s>>>(nb, mode);
+        k_finalize_sort<<<(nb.npad+255)/256, 256, 0, s>>>(nb, mode);
+        k_block_bounds<<<(nb.nblocks+31)/32, 1024, 0, s>>>(nb, mode);
+    }
     // 8 warps per i-block shorten the dependent chain while the grid is under one wave (measured: DHFR 108 -> 98 us per
     // build); above that the extra CTAs only add waves (ApoA1 225 -> 244 us), so large systems keep 4
     static const int btEnv = getenv("B200MD_BT_WARPS") ? atoi(getenv("B200MD_BT_WARPS")) : 0;
     const int btWarps = btEnv ? btEnv : (nb.nblocks <= 1200 ? 8 : 4);
-    if (btWarps >= 16) k_build_tiles<16><<<nb.nblocks, 512, 0, s>>>(nb, mode);
-    else if (btWarps >= 8) k_build_tiles<8><<<nb.nblocks, 256, 0, s>>>(nb, mode);
-    else k_build_tiles<4><<<nb.nblocks, 128, 0, s>>>(nb, mode);
-    k_list_done<<<1, 32, 0, s>>>(nb, mode);
+    if (btWarps >= 16) k_build_tiles<16><<<nb.nblocks, 512, 0, s>>>(nb, mode, merged);
+    else if (btWarps >= 8) k_build_tiles<8><<<nb.nblocks, 256, 0, s>>>(nb, mode, merged);
+    else k_build_tiles<4><<<nb.nblocks, 128, 0, s>>>(nb, mode, merged);
+    if (!merged) k_list_done<<<1, 32, 0, s>>>(nb, mode);
 }
 
 // ------------------------------------------------------------------------------------------------
