@@ -106,7 +106,8 @@ int b200md_update_bonded_params(b200md_ctx* ctx, int kind, int n, const double* 
 int b200md_set_box(b200md_ctx* ctx, const double a[3], const double b[3], const double c[3]);
 int b200md_get_box(b200md_ctx* ctx, double a[3], double b[3], double c[3]);
 int b200md_set_positions(b200md_ctx* ctx, const double* xyz);
-int b200md_get_positions(b200md_ctx* ctx, double* xyz);
+int b200md_get_positions(b200md_ctx* ctx, double* xyz);   /* continuous (unwrapped) trajectory, like the Reference platform's:
+                                                             * internal molecule wrapping is undone ("Long runs") */
 int b200md_set_velocities(b200md_ctx* ctx, const double* xyz);
 int b200md_get_velocities(b200md_ctx* ctx, double* xyz);
 int b200md_get_forces(b200md_ctx* ctx, double* xyz);        /* forces of the last b200md_compute */

@@ -86,7 +86,7 @@ struct b200md_ctx {
     DevBuf<float2> sigeps, ssigeps[2];
     DevBuf<long long> force;
     DevBuf<double> energy, cmScratch;
-    DevBuf<int> sorig[2], sortedOf, cellRank, cellCount, cellFill, atomCell, tmpSorted, tileI[2], tileJ[2], tileMask[2], listCounters, counters, exclStart, exclList;
+    DevBuf<int> molStart, molAtoms, cellOffset, sorig[2], sortedOf, cellRank, cellCount, cellFill, atomCell, tmpSorted, tileI[2], tileJ[2], tileMask[2], listCounters, counters, exclStart, exclList;
     DevBuf<unsigned int> maskPool[2];
     DevBuf<unsigned long long> stepCounter;
     DevBuf<unsigned int> blocksDone;
@@ -122,6 +122,7 @@ struct b200md_ctx {
     void* comm = nullptr;
     int rank = 0, world = 1;
     std::vector<float4> hbuf4;
+    std::vector<int> hoffset;
     std::vector<long long> hforce;
 };
 
@@ -622,6 +623,35 @@ extern "C" int b200md_finalize(b200md_ctx* ctx) {
     }
     upload_params(c);
     build_units(c);
+    // ---- molecules (connected components of bonds, angles, torsions, constraints and exceptions) for the wrap at list
+    // builds; off for non-periodic systems and with more than one rank (every rank would have to wrap in the same step,
+    // and the reciprocal-space rank builds no list) ----
+    c->cellOffset.alloc((size_t) 3*NP); c->cellOffset.zero();
+    nb.cellOffset = c->cellOffset.p; nb.nmol = 0; nb.molStart = nullptr; nb.molAtoms = nullptr;
+    if ((nb.method == B200MD_NB_CUTOFF_PERIODIC || nb.method == B200MD_NB_PME) && c->world == 1 && !c->pmeOnly && !getenv("B200MD_NO_WRAP")) {
+        std::vector<int> parent(N);
+        for (int i = 0; i < N; i++) parent[i] = i;
+        auto find = [&](int x) { while (parent[x] != x) { parent[x] = parent[parent[x]]; x = parent[x]; } return x; };
+        auto join = [&](int a, int b) { a = find(a); b = find(b); if (a != b) parent[std::max(a, b)] = std::min(a, b); };
+        for (size_t i = 0; i < c->bondI.size(); i++) join(c->bondI[i], c->bondJ[i]);
+        for (size_t i = 0; i < c->angI.size(); i++) { join(c->angI[i], c->angJ[i]); join(c->angJ[i], c->angK[i]); }
+        for (size_t i = 0; i < c->torI.size(); i++) { join(c->torI[i], c->torJ[i]); join(c->torJ[i], c->torK[i]); join(c->torK[i], c->torL[i]); }
+        for (size_t i = 0; i < c->conI.size(); i++) join(c->conI[i], c->conJ[i]);
+        for (size_t i = 0; i < c->excI.size(); i++) join(c->excI[i], c->excJ[i]);
+        std::vector<int> molOf(N), count;
+        std::map<int, int> id;
+        for (int i = 0; i < N; i++) {
+            const int r = find(i);
+            auto it = id.find(r);
+            if (it == id.end()) { it = id.insert(std::make_pair(r, (int) count.size())).first; count.push_back(0); }
+            molOf[i] = it->second; count[it->second]++;
+        }
+        std::vector<int> start(count.size() + 1, 0), fill(count.size(), 0), atoms(N);
+        for (size_t m = 0; m < count.size(); m++) start[m+1] = start[m] + count[m];
+        for (int i = 0; i < N; i++) atoms[start[molOf[i]] + fill[molOf[i]]++] = i;      // ascending inside a molecule: the first atom is its anchor
+        c->molStart.upload(start); c->molAtoms.upload(atoms);
+        nb.nmol = (int) count.size(); nb.molStart = c->molStart.p; nb.molAtoms = c->molAtoms.p;
+    }
     if (nb.method == B200MD_NB_PME) setup_pme(c, c->nbdesc.grid[0], c->nbdesc.grid[1], c->nbdesc.grid[2], c->nbdesc.ewald_alpha);
     c->finalized = true;
     apply_box(c);
@@ -691,6 +721,7 @@ extern "C" int b200md_set_positions(b200md_ctx* ctx, const double* x) {
         invalidate_graph(ctx);
     }
     CUDA_CHECK(cudaMemcpyAsync(ctx->posq.p, ctx->hbuf4.data(), sizeof(float4)*ctx->npad, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_CHECK(cudaMemsetAsync(ctx->cellOffset.p, 0, sizeof(int)*3*ctx->npad, ctx->stream));
     const int one = 1;
     CUDA_CHECK(cudaMemcpyAsync(&ctx->counters.p[2], &one, sizeof(int), cudaMemcpyHostToDevice, ctx->stream)); ctx->listDirty = true;
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
@@ -702,6 +733,20 @@ extern "C" int b200md_get_positions(b200md_ctx* ctx, double* x) {
     CUDA_CHECK(cudaMemcpyAsync(ctx->hbuf4.data(), ctx->posq.p, sizeof(float4)*ctx->npad, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     for (int i = 0; i < ctx->natoms; i++) { x[3*i] = ctx->hbuf4[i].x; x[3*i+1] = ctx->hbuf4[i].y; x[3*i+2] = ctx->hbuf4[i].z; }
+    if (ctx->nb.nmol > 0) {
+        // undo the internal molecule wrapping: the caller sees the continuous trajectory, like the Reference platform's
+        const int NP = ctx->npad;
+        ctx->hoffset.resize((size_t) 3*NP);
+        CUDA_CHECK(cudaMemcpy(ctx->hoffset.data(), ctx->cellOffset.p, sizeof(int)*3*NP, cudaMemcpyDeviceToHost));
+        for (int i = 0; i < ctx->natoms; i++) {
+            const int kx = ctx->hoffset[i], ky = ctx->hoffset[i + NP], kz = ctx->hoffset[i + 2*NP];
+            if (kx | ky | kz) {
+                x[3*i]   += kx*ctx->boxA[0] + ky*ctx->boxB[0] + kz*ctx->boxC[0];
+                x[3*i+1] += ky*ctx->boxB[1] + kz*ctx->boxC[1];
+                x[3*i+2] += kz*ctx->boxC[2];
+            }
+        }
+    }
     API_END(ctx)
 }
 extern "C" int b200md_set_velocities(b200md_ctx* ctx, const double* v) {
@@ -748,36 +793,38 @@ extern "C" int b200md_synchronize(b200md_ctx* ctx) {
 struct CkptHeader { char magic[8]; int version; int natoms; double time; int64_t stepCount; double box[9]; unsigned long long rngStep; };
 extern "C" int64_t b200md_checkpoint_save(b200md_ctx* ctx, void* buf, int64_t cap) {
     if (!ctx) return -1;
-    const int64_t need = sizeof(CkptHeader) + 2*sizeof(float4)*(int64_t) ctx->npad;
+    const int64_t need = sizeof(CkptHeader) + 2*sizeof(float4)*(int64_t) ctx->npad + 3*sizeof(int)*(int64_t) ctx->npad;
     if (!buf) return need;
     try {
         CUDA_CHECK(cudaSetDevice(ctx->device));
         require(cap >= need, "checkpoint buffer too small");
         CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
         CkptHeader h; memset(&h, 0, sizeof(h));
-        memcpy(h.magic, "B200MDCK", 8); h.version = 1; h.natoms = ctx->natoms; h.time = ctx->time; h.stepCount = ctx->stepCount;
+        memcpy(h.magic, "B200MDCK", 8); h.version = 2; h.natoms = ctx->natoms; h.time = ctx->time; h.stepCount = ctx->stepCount;
         for (int i = 0; i < 3; i++) { h.box[i] = ctx->boxA[i]; h.box[3+i] = ctx->boxB[i]; h.box[6+i] = ctx->boxC[i]; }
         CUDA_CHECK(cudaMemcpy(&h.rngStep, ctx->stepCounter.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost));
         char* p = (char*) buf;
         memcpy(p, &h, sizeof(h)); p += sizeof(h);
         CUDA_CHECK(cudaMemcpy(p, ctx->posq.p, sizeof(float4)*ctx->npad, cudaMemcpyDeviceToHost)); p += sizeof(float4)*ctx->npad;
-        CUDA_CHECK(cudaMemcpy(p, ctx->velm.p, sizeof(float4)*ctx->npad, cudaMemcpyDeviceToHost));
+        CUDA_CHECK(cudaMemcpy(p, ctx->velm.p, sizeof(float4)*ctx->npad, cudaMemcpyDeviceToHost)); p += sizeof(float4)*ctx->npad;
+        CUDA_CHECK(cudaMemcpy(p, ctx->cellOffset.p, sizeof(int)*3*ctx->npad, cudaMemcpyDeviceToHost));
         return need;
     } catch (std::exception& e) { ctx->err = e.what(); return -1; }
 }
 extern "C" int b200md_checkpoint_load(b200md_ctx* ctx, const void* buf, int64_t size) {
     API_BEGIN(ctx)
     ctx->stepStateValid = false;
-    const int64_t need = sizeof(CkptHeader) + 2*sizeof(float4)*(int64_t) ctx->npad;
+    const int64_t need = sizeof(CkptHeader) + 2*sizeof(float4)*(int64_t) ctx->npad + 3*sizeof(int)*(int64_t) ctx->npad;
     require(size >= need, "checkpoint blob too small");
     CkptHeader h; memcpy(&h, buf, sizeof(h));
-    require(memcmp(h.magic, "B200MDCK", 8) == 0 && h.version == 1 && h.natoms == ctx->natoms, "checkpoint blob does not match this context");
+    require(memcmp(h.magic, "B200MDCK", 8) == 0 && h.version == 2 && h.natoms == ctx->natoms, "checkpoint blob does not match this context");
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     ctx->time = h.time; ctx->stepCount = h.stepCount;
     for (int i = 0; i < 3; i++) { ctx->boxA[i] = h.box[i]; ctx->boxB[i] = h.box[3+i]; ctx->boxC[i] = h.box[6+i]; }
     const char* p = (const char*) buf + sizeof(h);
     CUDA_CHECK(cudaMemcpy(ctx->posq.p, p, sizeof(float4)*ctx->npad, cudaMemcpyHostToDevice)); p += sizeof(float4)*ctx->npad;
-    CUDA_CHECK(cudaMemcpy(ctx->velm.p, p, sizeof(float4)*ctx->npad, cudaMemcpyHostToDevice));
+    CUDA_CHECK(cudaMemcpy(ctx->velm.p, p, sizeof(float4)*ctx->npad, cudaMemcpyHostToDevice)); p += sizeof(float4)*ctx->npad;
+    CUDA_CHECK(cudaMemcpy(ctx->cellOffset.p, p, sizeof(int)*3*ctx->npad, cudaMemcpyHostToDevice));
     CUDA_CHECK(cudaMemcpy(ctx->stepCounter.p, &h.rngStep, sizeof(unsigned long long), cudaMemcpyHostToDevice));
     if (ctx->haveBox) apply_box(ctx);
     const int one = 1;

@@ -100,6 +100,13 @@ struct NbDev {
     // exclusions, CSR in user order
     const int* exclStart;
     const int* exclList;
+    // whole molecules that have diffused more than one box length out of the primary cell are moved back by lattice vectors
+    // at list builds (fp32 coordinates lose ~1e-7 nm of resolution per nm of magnitude: a water walks ~100 nm per
+    // microsecond); cellOffset remembers the lattice vectors so that the user keeps seeing a continuous trajectory
+    int nmol;                    // 0: wrapping off (non-periodic, or more than one rank)
+    const int* molStart;         // CSR over molAtoms
+    const int* molAtoms;
+    int* cellOffset;             // [3][npad] lattice vector counts to ADD when reporting positions
     float halfPad2;              // (padding/2)^2: beyond this displacement the current list is invalid
     float softPad2;              // displacement^2 at which the successor list is built beside the step (3e38: never)
     // multi-GPU sharding of the tile list / PME atoms

@@ -114,6 +114,43 @@ __global__ void __launch_bounds__(256) k_check_gather(NbDev nb) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// 1b. molecule wrapping (first phase of a list build).  The user's coordinates are never wrapped by the reference
+// (getState without enforcePeriodicBox returns a continuous trajectory), but fp32 coordinates must stay small: a molecule
+// whose first atom is more than one box length outside the primary cell is moved back by whole lattice vectors, all its
+// atoms together (bonded terms and constraints use no minimum image), and cellOffset records the move.  Molecules within
+// one box length are left alone, so a freshly set structure keeps its exact coordinates.
+__device__ __forceinline__ void wrap_molecule(const NbDev& nb, int m) {
+    const int begin = nb.molStart[m], end = nb.molStart[m+1];
+    const float4 p = nb.posq[nb.molAtoms[begin]];
+    const double* R = nb.box.recip;
+    const double px = p.x - nb.origin[0], py = p.y - nb.origin[1], pz = p.z - nb.origin[2];
+    const double f[3] = {px*R[0] + py*R[3] + pz*R[6], px*R[1] + py*R[4] + pz*R[7], px*R[2] + py*R[5] + pz*R[8]};
+    int k[3];
+    bool move = false;
+    for (int d = 0; d < 3; d++) {
+        const double w = floor(f[d]);
+        k[d] = (w >= 2.0 || w <= -2.0) ? (int) w : 0;          // NaN compares false: no move
+        move |= (k[d] != 0);
+    }
+    if (!move) return;
+    const BoxDev& b = nb.box;
+    const double sx = -(k[0]*(double) b.dax + k[1]*(double) b.bx + k[2]*(double) b.cx);
+    const double sy = -(k[1]*(double) b.dby + k[2]*(double) b.cy);
+    const double sz = -(k[2]*(double) b.dcz);
+    for (int t = begin; t < end; t++) {
+        const int a = nb.molAtoms[t];
+        const float4 q = nb.posq[a];
+        nb.posq[a] = make_float4((float) ((double) q.x + sx), (float) ((double) q.y + sy), (float) ((double) q.z + sz), q.w);
+        nb.cellOffset[a] += k[0]; nb.cellOffset[a + nb.npad] += k[1]; nb.cellOffset[a + 2*nb.npad] += k[2];
+    }
+}
+__global__ void k_wrap_molecules(NbDev nb, int mode) {
+    if (nb.counters[mode ? CT_SOFT : CT_REBUILD] == 0) return;
+    const int m = blockIdx.x*blockDim.x + threadIdx.x;
+    if (m < nb.nmol) wrap_molecule(nb, m);
+}
+
+// ------------------------------------------------------------------------------------------------
 // 2. binning (periodic systems only; non-periodic systems keep the identity order)
 __device__ __forceinline__ void bin_atom(const NbDev& nb, int a) {
     float4 p = nb.posq[a];
@@ -306,18 +343,25 @@ __device__ void list_prep_phases(const NbDev& nb, const ListDev& L, int* partial
     const int G = gridDim.x;
     const int gtid = blockIdx.x*blockDim.x + threadIdx.x, gthreads = G*blockDim.x;
     const int lane = threadIdx.x & 31, gwarp = gtid >> 5, gwarps = gthreads >> 5;
+    // 0. molecules that have walked away come home (rare; the barrier is skipped when wrapping is off)
+    int base = 0;
+    if (nb.nmol > 0) {
+        for (int m = gtid; m < nb.nmol; m += gthreads) wrap_molecule(nb, m);
+        grid_barrier(nb, G);
+        base = G;
+    }
     // 1. binning
     for (int a = gtid; a < nb.natoms; a += gthreads) bin_atom(nb, a);
-    grid_barrier(nb, G);
+    grid_barrier(nb, base + G);
     // 2. exclusive scan of the cell counts (one CTA)
     if (blockIdx.x == 0) scan_cells_block(nb, partial);
-    grid_barrier(nb, 2*G);
+    grid_barrier(nb, base + 2*G);
     // 3. atoms into their cells
     for (int a = gtid; a < nb.natoms; a += gthreads) fill_atom(nb, a);
-    grid_barrier(nb, 3*G);
+    grid_barrier(nb, base + 3*G);
     // 4. deterministic in-cell order, sorted copies
     for (int s = gtid; s < nb.npad; s += gthreads) finalize_slot(nb, L, s);
-    grid_barrier(nb, 4*G);
+    grid_barrier(nb, base + 4*G);
     // 5. block bounding boxes (one warp per block); the binning counters are consumed: zero them for the next build
     for (int b = gwarp; b < nb.nblocks; b += gwarps) {
         const int s = b*32 + lane;
@@ -341,7 +385,7 @@ __device__ void list_prep_phases(const NbDev& nb, const ListDev& L, int* partial
         if (i < nb.ncells) nb.cellFill[i] = 0;
     }
     if (gtid < TILE_REGIONS) { L.lc[LC_TILES + gtid] = 0; L.lc[LC_MASKS + gtid] = 0; }
-    grid_barrier(nb, 5*G);
+    grid_barrier(nb, base + 5*G);
     // 6. superblock boxes (one warp per 32 blocks)
     const int nsuper = (nb.nblocks + 31) >> 5;
     for (int sb = gwarp; sb < nsuper; sb += gwarps) {
@@ -658,6 +702,7 @@ void launch_list_build(const NbDev& nb, cudaStream_t s, int mode) {
     }
     else {
         int nbk = (nb.natoms+255)/256;
+        if (nb.nmol > 0) k_wrap_molecules<<<(nb.nmol+255)/256, 256, 0, s>>>(nb, mode);
         k_bin_atoms<<<nbk, 256, 0, s>>>(nb, mode);
         k_scan_cells<<<1, 1024, 0, s>>>(nb, mode);
         k_fill_cells<<<nbk, 256, 0, s>>>(nb, mode);
