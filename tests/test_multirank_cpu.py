@@ -98,3 +98,50 @@ def test_round_robin_sharding_is_a_partition():
         for r in range(world):
             cover[r*per:min(N, (r+1)*per)] += 1
         assert (cover == 1).all()
+
+
+def _role_worker(rank, world, port, out):
+    """DESIGN.md section 5 at world 2: rank 0 = direct space + bonded terms + exclusion correction, rank 1 = reciprocal space
+    for all atoms (what engine.cu:role_split / role_nb arrange), joined by one int64 all-reduce of the force buffer."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from openmm_b200 import systems
+    from oracle import port as orc
+    desc = systems.water_box(3, cutoff=0.45, rigid=False).rounded()
+    L = orc.lib()
+    n = desc.natoms
+    pos, q = orc._d(desc.positions), orc._d(desc.charges)
+    box = orc._d(desc.box).reshape(9)
+    alpha, nx, ny, nz = desc.pme_parameters()
+    f = np.zeros((n, 3))
+    e = 0.0
+    if rank == world - 1:
+        e += L.orc_pme_reciprocal(n, orc._dp(pos), orc._dp(q), orc._dp(box), alpha, nx, ny, nz, orc._dp(f))
+        e += L.orc_self_energy(n, orc._dp(q), alpha)
+    else:
+        fd, ed, parts = orc.forces_energy(desc, pme=(alpha, nx, ny, nz))
+        # everything but reciprocal space and the self term
+        fr = np.zeros((n, 3))
+        er = L.orc_pme_reciprocal(n, orc._dp(pos), orc._dp(q), orc._dp(box), alpha, nx, ny, nz, orc._dp(fr))
+        f, e = fd - fr, ed - er - parts["self"]
+    fixed = torch.from_numpy(np.rint(f*SCALE).astype(np.int64))
+    dist.all_reduce(fixed)
+    et = torch.tensor([e], dtype=torch.float64)
+    dist.all_reduce(et)
+    if rank == 0:
+        np.save(out, np.concatenate([fixed.numpy().astype(np.float64).ravel()/SCALE, et.numpy()]))
+    dist.destroy_process_group()
+
+
+def test_role_split_direct_rank_plus_reciprocal_rank_world2(tmp_path):
+    from openmm_b200 import systems
+    from oracle import port as orc
+    out = str(tmp_path/"role.npy")
+    port = 31500 + (os.getpid() % 2000)
+    mp.spawn(_role_worker, args=(2, port, out), nprocs=2, join=True)
+    got = np.load(out)
+    desc = systems.water_box(3, cutoff=0.45, rigid=False).rounded()
+    f, e, _ = orc.forces_energy(desc)
+    assert np.abs(got[:-1].reshape(desc.natoms, 3) - f).max() < 1e-6      # int64 rounding of two partial sums + one subtraction
+    assert abs(got[-1] - e) < 1e-9*abs(e)
