@@ -6,10 +6,12 @@
 // coulombLennardJones.cc:1-116.  Arithmetic follows ReferenceLJCoulombIxn::calculateEwaldIxn
 // (ReferenceLJCoulombIxn.cpp:373-460) and calculateOneIxn for the cutoff / no-cutoff methods.
 //
-// Design (not the reference's): atoms are fully re-sorted on the device along a space-filling curve of
-// binning cells every time the list is rebuilt; the nonbonded kernels work on the sorted copy (sposq) while
-// integration/bonded code keeps the user's order.  Exclusion masks are generated on the fly while tiles are
-// emitted, so there is no static "exclusion tile" set and no host involvement.
+// Design (not the reference's): atoms are fully re-sorted on the device along a blocked-serpentine order of binning
+// cells every time the list is rebuilt; the tile kernel works on the sorted copy (ListDev::sposq, exact user coordinates)
+// while integration/bonded code keeps the user's order.  Exclusion masks are generated on the fly while tiles are
+// emitted, so there is no static "exclusion tile" set and no host involvement.  There are two complete lists
+// (NbDev::list[2]): a build always fills the one that is not current and flips counters[CT_CUR] on the device.
+// A build is two launches, k_list_prep and k_build_tiles, that return at once unless counters[CT_REBUILD] is raised.
 #include "engine.h"
 #include "../../include/b200md.h"
 #include <algorithm>
@@ -538,7 +540,7 @@ __device__ void build_tiles_iblock(const NbDev& nb, const ListDev& L, int ib, in
     group_sync(barId, NW*32);
     const bool periodic = nb.box.periodic != 0;
     const bool allPairs = (nb.method == B200MD_NB_NOCUTOFF);
-    // same condition as the pair kernel's SHIFT mode (counters[7] = max block half extent of THIS build)
+    // same condition as the pair kernel's SHIFT mode (lc[LC_MAXHALF] = max block half extent of THIS build)
     const float minL = fminf(nb.box.ax, fminf(nb.box.by, nb.box.cz));
     const bool exactCull = periodic && !nb.box.triclinic &&
                            (0.5f*minL - nb.cutoff - 2.0f*sqrtf(nb.halfPad2) >= __int_as_float(L.lc[LC_MAXHALF]));
