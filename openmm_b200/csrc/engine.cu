@@ -522,6 +522,7 @@ extern "C" int b200md_finalize(b200md_ctx* ctx) {
     nb.rank = c->rank; nb.world = c->world;
     nb.useRational = getenv("B200MD_PAIR_RATIONAL") ? atoi(getenv("B200MD_PAIR_RATIONAL")) : 0;
     nb.pairDynamic = getenv("B200MD_PAIR_DYNAMIC") ? atoi(getenv("B200MD_PAIR_DYNAMIC")) : 0;
+    nb.packCull = getenv("B200MD_BT_PACK") ? atoi(getenv("B200MD_BT_PACK")) : 1;
     // ---- state arrays ----
     c->posq.alloc(NP); c->posq.zero(); c->velm.alloc(NP); c->velm.zero();
     c->refPos.alloc(NP); c->refPos.zero(); c->atomShift.alloc(NP); c->sigeps.alloc(NP);

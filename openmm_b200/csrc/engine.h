@@ -117,6 +117,7 @@ struct NbDev {
     // CUDA-graph conditional node that holds the list-rebuild kernels (0 = none: rebuild kernels are gated on counters[2])
     unsigned long long condHandle;
     unsigned long long condAsync;   // second IF node: build of the successor list on a side stream
+    int packCull;                // k_build_tiles: exact cull on full warps (B200MD_BT_PACK)
     int pairDynamic;             // tile kernel fetches tiles from a cursor instead of a static stride
     int useRational;             // B200MD_PAIR_RATIONAL=1: rational Ewald kernel in the force-only tile loop (1 MUFU less, lower accuracy)
 };
