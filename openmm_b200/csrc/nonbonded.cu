@@ -334,7 +334,7 @@ __device__ __forceinline__ void grid_barrier(const NbDev& nb, int target) {
         long spins = 0;
         while (*((volatile int*) &nb.counters[CT_BAR]) < target) {
             __nanosleep(32);
-            if (++spins > (1L << 20)) { nb.counters[CT_OVERFLOW] = 2; break; }
+            if (++spins > (1L << 23)) { nb.counters[CT_OVERFLOW] = 2; break; }
         }
         __threadfence();
     }
