@@ -25,6 +25,13 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 
 
+# what the inputs are: the real benchmark structures where the reference ships them (built here by the reference's own
+# forcefield.py, tools/make_benchmark_systems.py), synthetic water boxes otherwise; velocities are always synthetic
+DATA_NOTE = {"dhfr": "real DHFR benchmark system of the reference (5dfr_solv-cube_equil.pdb, amber99sb+tip3p via the reference's forcefield.py); synthetic velocities",
+             "apoa1": "real ApoA1 benchmark system of the reference (apoa1.pdb, amber14+lipid17+tip3p via the reference's forcefield.py); synthetic velocities",
+             "water24k": "synthetic", "water1m": "synthetic"}
+
+
 def load_workload(name):
     from openmm_b200 import systems
     if name == "water24k":
@@ -102,7 +109,7 @@ def run_reference(args, rank, world):
     nsday = args.dt*1e-3*md*args.steps*86400/sec
     line = {"impl": "reference", "metric": "ns/day", "value": nsday, "unit": "ns/day", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3*sec/args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "config": {"workload": args.workload, "atoms": d.natoms, "md_steps_per_step": md, "dt_fs": args.dt*1e3,
+            "data": DATA_NOTE.get(args.workload, "synthetic"), "config": {"workload": args.workload, "atoms": d.natoms, "md_steps_per_step": md, "dt_fs": args.dt*1e3,
                                             "platform": "reference CPU platform (platforms/cpu), reference PME (no FFTW)", "pme_grid": list(d.pme_parameters()[1:])},
             "cpu_baseline": {"value": nsday, "unit": "ns/day", "cores": cores, "kind": "reference", "sample": "%d x %d MD steps" % (args.steps, md)},
             "e2e": {"value": nsday, "unit": "ns/day", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
@@ -230,7 +237,7 @@ def main():
     phases = {ph: round(eng.time_phase(ph, 30)*1e3, 2) for ph in ("pair", "pme_spread", "pme_fft_conv", "pme_gather", "bonded", "integrate", "list_build")}
     flops = T*1024*60.0
     line = {"metric": "ns/day", "value": nsday, "unit": "ns/day", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms/args.steps,
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": DATA_NOTE.get(args.workload, "synthetic"),
             "config": {"workload": args.workload, "atoms": d.natoms, "md_steps_per_step": md, "dt_fs": args.dt*1e3, "integrator": "Langevin 300K 1/ps + SETTLE/SHAKE (HBonds)",
                        "cutoff_nm": d.cutoff, "pme_grid": st["pme_grid"], "parallelism": ("replicated atoms: %d direct-space ranks + 1 PME rank, int64 force all-reduce" % (world-1)) if world > 1 else "single GPU",
                        "l2": "256 MiB buffer written between timed iterations (inside the timed region)", "us_per_md_step": 1e3*ms/(args.steps*md)},
