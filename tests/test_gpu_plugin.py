@@ -98,7 +98,7 @@ def test_plugin_checkpoint(omm):
 
 REFERENCE_TEST_BINARIES = ["TestB200NonbondedForce", "TestB200Ewald", "TestB200Settle", "TestB200LangevinIntegrator", "TestB200LangevinMiddleIntegrator",
                            "TestB200VerletIntegrator", "TestB200HarmonicBondForce", "TestB200HarmonicAngleForce", "TestB200PeriodicTorsionForce",
-                           "TestB200CMMotionRemover"]
+                           "TestB200CMMotionRemover", "TestB200LocalEnergyMinimizer"]
 
 
 @pytest.mark.parametrize("name", REFERENCE_TEST_BINARIES)
