@@ -341,7 +341,7 @@ static void apply_box(b200md_ctx* c) {
         setup_cells(c);
         if (m == B200MD_NB_PME) { launch_pme_eterm(c->nb, c->pme, c->stream); c->kernelLaunches++; }
         const int one = 1;
-        CUDA_CHECK(cudaMemcpyAsync(&c->counters.p[2], &one, sizeof(int), cudaMemcpyHostToDevice, c->stream)); c->listDirty = true;
+        CUDA_CHECK(cudaMemcpyAsync(&c->counters.p[CT_REBUILD], &one, sizeof(int), cudaMemcpyHostToDevice, c->stream)); c->listDirty = true;
         CUDA_CHECK(cudaStreamSynchronize(c->stream));
         invalidate_graph(c);
     }
@@ -672,7 +672,7 @@ extern "C" int b200md_update_nonbonded_params(b200md_ctx* ctx, const double* q, 
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     upload_params(ctx);
     const int one = 1;
-    CUDA_CHECK(cudaMemcpy(&ctx->counters.p[2], &one, sizeof(int), cudaMemcpyHostToDevice)); ctx->listDirty = true;   // sorted copies of the parameters
+    CUDA_CHECK(cudaMemcpy(&ctx->counters.p[CT_REBUILD], &one, sizeof(int), cudaMemcpyHostToDevice)); ctx->listDirty = true;   // sorted copies of the parameters
     invalidate_graph(ctx);
     API_END(ctx)
 }
@@ -724,7 +724,7 @@ extern "C" int b200md_set_positions(b200md_ctx* ctx, const double* x) {
     CUDA_CHECK(cudaMemcpyAsync(ctx->posq.p, ctx->hbuf4.data(), sizeof(float4)*ctx->npad, cudaMemcpyHostToDevice, ctx->stream));
     CUDA_CHECK(cudaMemsetAsync(ctx->cellOffset.p, 0, sizeof(int)*3*ctx->npad, ctx->stream));
     const int one = 1;
-    CUDA_CHECK(cudaMemcpyAsync(&ctx->counters.p[2], &one, sizeof(int), cudaMemcpyHostToDevice, ctx->stream)); ctx->listDirty = true;
+    CUDA_CHECK(cudaMemcpyAsync(&ctx->counters.p[CT_REBUILD], &one, sizeof(int), cudaMemcpyHostToDevice, ctx->stream)); ctx->listDirty = true;
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     API_END(ctx)
 }
@@ -829,7 +829,7 @@ extern "C" int b200md_checkpoint_load(b200md_ctx* ctx, const void* buf, int64_t 
     CUDA_CHECK(cudaMemcpy(ctx->stepCounter.p, &h.rngStep, sizeof(unsigned long long), cudaMemcpyHostToDevice));
     if (ctx->haveBox) apply_box(ctx);
     const int one = 1;
-    CUDA_CHECK(cudaMemcpy(&ctx->counters.p[2], &one, sizeof(int), cudaMemcpyHostToDevice)); ctx->listDirty = true;
+    CUDA_CHECK(cudaMemcpy(&ctx->counters.p[CT_REBUILD], &one, sizeof(int), cudaMemcpyHostToDevice)); ctx->listDirty = true;
     API_END(ctx)
 }
 
@@ -983,8 +983,8 @@ static void check_flags(b200md_ctx* c) {
     int h[8];
     CUDA_CHECK(cudaMemcpyAsync(h, c->counters.p, sizeof(int)*8, cudaMemcpyDeviceToHost, c->stream));
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
-    if (h[3] == 2) throw std::runtime_error("B200 platform: neighbour-list construction timed out at a grid barrier (k_list_prep)");
-    if (h[3]) throw std::runtime_error("B200 platform: neighbour-list tile capacity exceeded (" + std::to_string(c->nb.maxTiles) + " tiles)");
+    if (h[CT_OVERFLOW] == 2) throw std::runtime_error("B200 platform: neighbour-list construction timed out at a grid barrier (k_list_prep)");
+    if (h[CT_OVERFLOW]) throw std::runtime_error("B200 platform: neighbour-list tile capacity exceeded (" + std::to_string(c->nb.maxTiles) + " tiles)");
 }
 
 extern "C" int b200md_compute(b200md_ctx* ctx, int terms, int want_forces, double* energy) {
@@ -1253,7 +1253,7 @@ extern "C" int b200md_get_stats(b200md_ctx* ctx, b200md_stats* out) {
         const int* cur = lc + LC_STRIDE*(h[CT_CUR] & 1);
         int masks = 0;
         for (int r = 0; r < TILE_REGIONS; r++) masks += cur[LC_MASKS + r];
-        out->num_tiles = cur[LC_USED]; out->num_mask_tiles = masks; out->overflow = h[3]; out->list_builds = h[4]; out->pairs_in_cutoff = h[5]; out->stale_list_steps = h[CT_STALE];
+        out->num_tiles = cur[LC_USED]; out->num_mask_tiles = masks; out->overflow = h[CT_OVERFLOW]; out->list_builds = h[CT_BUILDS]; out->pairs_in_cutoff = h[CT_PAIRS]; out->stale_list_steps = h[CT_STALE];
     }
     out->force_evals = ctx->forceEvals; out->kernel_launches = ctx->kernelLaunches;
     out->pme_grid[0] = ctx->pme.nx; out->pme_grid[1] = ctx->pme.ny; out->pme_grid[2] = ctx->pme.nz; out->ewald_alpha = ctx->pme.alpha;
@@ -1285,7 +1285,7 @@ extern "C" int b200md_time_phase(b200md_ctx* ctx, int phase, int reps, double* m
             CUDA_CHECK(cudaMemcpyAsync(c->posq.p, savePos.p, sizeof(float4)*c->npad, cudaMemcpyDeviceToDevice, s));
             CUDA_CHECK(cudaMemcpyAsync(c->velm.p, saveVel.p, sizeof(float4)*c->npad, cudaMemcpyDeviceToDevice, s));
         }
-        if (phase == 5) CUDA_CHECK(cudaMemcpyAsync(&c->counters.p[2], &one, sizeof(int), cudaMemcpyHostToDevice, s));
+        if (phase == 5) CUDA_CHECK(cudaMemcpyAsync(&c->counters.p[CT_REBUILD], &one, sizeof(int), cudaMemcpyHostToDevice, s));
         CUDA_CHECK(cudaEventRecord(e0, s));
         switch (phase) {
             case 0: launch_pair(nbv, false, s); break;

@@ -114,7 +114,7 @@ struct NbDev {
     // origin of the primary periodic cell used for binning (chosen at set_positions so that a structure centred anywhere,
     // e.g. a PDB centred on 0, is binned WITHOUT lattice shifts: a shift costs one fp32 rounding of the coordinate)
     double origin[3];
-    // CUDA-graph conditional node that holds the list-rebuild kernels (0 = none: rebuild kernels are gated on counters[2])
+    // CUDA-graph conditional node that holds the list-rebuild kernels (0 = none: rebuild kernels are gated on counters[CT_REBUILD])
     unsigned long long condHandle;
     unsigned long long condAsync;   // second IF node: build of the successor list on a side stream
     int packCull;                // k_build_tiles: exact cull on full warps (B200MD_BT_PACK)

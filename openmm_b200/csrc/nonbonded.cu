@@ -89,11 +89,11 @@ __global__ void __launch_bounds__(256) k_check_gather(NbDev nb) {
         __syncthreads();
         if (threadIdx.x == 0) {
             __threadfence();
-            last = (atomicAdd(&nb.counters[8], 1) == (int) gridDim.x - 1);
+            last = (atomicAdd(&nb.counters[CT_LASTBLOCK], 1) == (int) gridDim.x - 1);
         }
         __syncthreads();
         if (last && threadIdx.x == 0) {
-            nb.counters[8] = 0;
+            nb.counters[CT_LASTBLOCK] = 0;
             __threadfence();
             const int hard = *((volatile int*) &nb.counters[CT_REBUILD]);
             const int soft = *((volatile int*) &nb.counters[CT_SOFT]);
@@ -1055,10 +1055,10 @@ __global__ void k_count_pairs(NbDev nb) {
         }
     }
     for (int off = 16; off > 0; off >>= 1) count += __shfl_xor_sync(FULL, count, off);
-    if (lane == 0 && count) atomicAdd(&nb.counters[5], count);
+    if (lane == 0 && count) atomicAdd(&nb.counters[CT_PAIRS], count);
 }
 
 void launch_count_pairs(const NbDev& nb, cudaStream_t s) {
-    cudaMemsetAsync(&nb.counters[5], 0, sizeof(int), s);
+    cudaMemsetAsync(&nb.counters[CT_PAIRS], 0, sizeof(int), s);
     k_count_pairs<<<148*4, 256, 0, s>>>(nb);
 }
