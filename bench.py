@@ -122,7 +122,10 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default=os.environ.get("B200MD_WORKLOAD", "dhfr"))
+    ap.add_argument("--workload", default=os.environ.get("B200MD_WORKLOAD"),
+                    help="dhfr (default on 1 GPU: BASELINE.json configs[1]), apoa1 (default on N > 1 GPUs: configs[3]), water24k, water1m")
+    ap.add_argument("--via", default="plugin", choices=["plugin", "cabi"],
+                    help="e2e leg: through the OpenMM Platform plugin (Context + LangevinIntegrator.step) or through the bare C-ABI")
     ap.add_argument("--md-steps", type=int, default=500)
     ap.add_argument("--ref-md-steps", type=int, default=10)
     ap.add_argument("--dt", type=float, default=0.002)
@@ -131,6 +134,8 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.workload is None:
+        args.workload = "dhfr" if max(world, args.gpus) == 1 else "apoa1"
     if args.impl == "reference":
         return run_reference(args, rank, world)
 
@@ -196,20 +201,45 @@ def main():
         ms = float(t.item())
     nsday = args.dt*1e-3*md*args.steps*86400/(ms*1e-3)
 
-    # ---- end to end through the C-ABI with HOST buffers: upload state, run, read back positions + energy ----
+    # ---- end to end with HOST buffers: upload the state, run, read back positions + velocities + energy ----
+    # --via plugin (default, single GPU): through the reference's public API -- Context.setPositions/setVelocities,
+    # LangevinIntegrator.step(md), Context.getState -- on the B200 Platform plugin (plugin/libOpenMMB200.so loaded into the
+    # unmodified libOpenMM.so as its host application); --via cabi (and N > 1): the same calls on the bare C-ABI.
     x = eng.get_positions()
     v = eng.get_velocities()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        eng.set_positions(x)
-        eng.set_velocities(v)
-        eng.step(md)
-        x = eng.get_positions()
-        v = eng.get_velocities()
-    e_final = eng.compute()
-    barrier()
-    e2e_sec = time.perf_counter() - t0
+    via = args.via if world == 1 else "cabi"
+    e2e_launches = 0
+    if via == "plugin":
+        from oracle import omm                # the host application (reference libOpenMM.so + ctypes shim); compute is the plugin's
+        omm.load_plugin(os.path.join(ROOT, "plugin", "libOpenMMB200.so"))
+        sim = omm.Simulation(d, "B200", integrator=(systems.INT_LANGEVIN, 300.0, 1.0, args.dt), seed=7, constraint_tol=1e-5, pme=d.pme_parameters(),
+                             props="DeviceIndex=%d" % local)
+        assert sim.platform() == "B200"
+        sim.set_positions(x); sim.set_velocities(v)
+        sim.step(md)                          # captures the step graph outside the timed region
+        sim.state(energy=True)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            sim.set_positions(x)
+            sim.set_velocities(v)
+            sim.step(md)
+            st = sim.state(positions=True, velocities=True)
+            x, v = st["positions"], st["velocities"]
+        e_final = sim.state(energy=True)["potential"]
+        e2e_sec = time.perf_counter() - t0
+        sim.close()
+    else:
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            eng.set_positions(x)
+            eng.set_velocities(v)
+            eng.step(md)
+            x = eng.get_positions()
+            v = eng.get_velocities()
+        e_final = eng.compute()
+        barrier()
+        e2e_sec = time.perf_counter() - t0
     if world > 1:
         t = torch.tensor([e2e_sec])
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -229,9 +259,11 @@ def main():
     alg_bytes = T*(32*4 + 4 + 4) + X*32*4 + NP*(16 + 8) + NP*24       # tiles (j list, i block, mask idx) + masks + posq/sigeps read + force write
     peak, peak_src = peaks()
     achieved = alg_bytes/(pair_ms*1e-3)/1e9
-    traffic = None          # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel
-    tpath = os.path.join(ROOT, "profiles", "r01_final_k_pair_summary.json")
-    if args.workload == "dhfr" and os.path.exists(tpath):
+    # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel ON THIS WORKLOAD
+    # (tools/summarize_profile.py writes profiles/r02_<workload>_k_pair_summary.json); null when no capture exists
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r02_%s_k_pair_summary.json" % args.workload)
+    if os.path.exists(tpath):
         tj = json.load(open(tpath))
         traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
     phases = {ph: round(eng.time_phase(ph, 30)*1e3, 2) for ph in ("pair", "pme_spread", "pme_fft_conv", "pme_gather", "bonded", "integrate", "list_build")}
@@ -243,12 +275,14 @@ def main():
                        "l2": "256 MiB buffer written between timed iterations (inside the timed region)", "us_per_md_step": 1e3*ms/(args.steps*md)},
             "clocks": sampler.summary(),
             "e2e": {"value": e2e_nsday, "unit": "ns/day", "h2d_bytes_per_step": 2*nbytes, "d2h_bytes_per_step": 2*nbytes + 8,
-                    "note": "per bench step: set_positions+set_velocities from host doubles, %d MD steps, get_positions+get_velocities; final energy %.1f" % (md, e_final)},
+                    "via": "OpenMM Platform plugin: Context.setPositions/setVelocities + LangevinIntegrator.step + Context.getState (libOpenMMB200.so)" if via == "plugin" else "C-ABI (b200md_set_positions/.../b200md_step)",
+                    "note": "per bench step: positions+velocities from host doubles, %d MD steps, positions+velocities back; final energy %.1f" % (md, e_final)},
             "gpu_launches": int(st1["kernel_launches"] - st0["kernel_launches"]),
             "roofline": {"kernel": "k_pair (direct-space 32x32 tile kernel)", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved/peak,
                          "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": pair_ms,
                          "tiles": T, "pairs_in_cutoff": st["pairs_in_cutoff"], "tile_fill": st["pairs_in_cutoff"]/(T*1024.0),
-                         "fp32_tflops_algorithmic": flops/(pair_ms*1e-3)/1e12,
+                         "fp32_tflops_all_slots": flops/(pair_ms*1e-3)/1e12,       # 60 flop x every evaluated slot, in or out of the cutoff
+                         "fp32_tflops_useful_pairs": st["pairs_in_cutoff"]*60.0/(pair_ms*1e-3)/1e12,
                          "note": "compute (FP32/SFU) bound kernel: arithmetic intensity ~%.0f flop/B; see DESIGN.md" % (flops/alg_bytes)},
             "phases_us": phases, "list_builds_in_timed_region": int(st1["list_builds"] - st0["list_builds"])}
     if not args.no_cpu_baseline:

@@ -83,9 +83,20 @@ int b200md_set_angles(b200md_ctx* ctx, int n, const int* p1, const int* p2, cons
 /* CalcPeriodicTorsionForceKernel::initialize (kernels.h:429), E = k (1+cos(n phi - phase)).          */
 int b200md_set_torsions(b200md_ctx* ctx, int n, const int* p1, const int* p2, const int* p3, const int* p4,
                         const int* periodicity, const double* phase, const double* k);
+/* Force group (Force::getForceGroup, openmmapi/include/openmm/Force.h) of every bond / angle / torsion, so that
+ * several Force objects of one class may live in different groups (ContextImpl::calcForcesAndEnergy,
+ * ContextImpl.cpp:293-308; tests/TestLocalEnergyMinimizer.h:234 testForceGroups).  kind 0 bonds, 1 angles, 2 torsions;
+ * default group 0.  group[i] | 0x80 marks a term of a Force with usesPeriodicBoundaryConditions(): its
+ * difference vectors take the minimum image (ReferenceForce::getDeltaRPeriodic, ReferenceForce.cpp:90-101).          */
+int b200md_set_bonded_groups(b200md_ctx* ctx, int kind, int n, const int* group);
 /* System::getConstraintParameters; supported topologies: 3-atom rigid molecules (SETTLE,
  * ReferenceConstraints.cpp:69-146) and X-H_n clusters, n<=3 (SHAKE, common IntegrationUtilities.cpp:204-277). */
 int b200md_set_constraints(b200md_ctx* ctx, int n, const int* p1, const int* p2, const double* distance);
+/* Dry run of the constraint classification, without a context or a device: 0 if every constraint is supported, else -1
+ * with the reason in msg.  Platform::contextCreated calls it so that an unsupported System is refused THERE, where
+ * ContextImpl can still fall back to another platform (ContextImpl.cpp:152-166).                                      */
+int b200md_check_constraints(int natoms, const double* mass, int n, const int* p1, const int* p2, const double* distance,
+                             char* msg, int msglen);
 /* RemoveCMMotionKernel (kernels.h:1464-1483); frequency <= 0 disables.                               */
 int b200md_set_cm_remover(b200md_ctx* ctx, int frequency);
 /* RemoveCMMotionKernel::execute (kernels.h:1483): subtract the centre-of-mass velocity now.          */
@@ -124,6 +135,9 @@ int b200md_checkpoint_load(b200md_ctx* ctx, const void* buf, int64_t size);
  * neighbour list if any atom moved more than half the padding, evaluate the selected terms.
  * energy (may be NULL) receives the potential energy of the selected terms.                          */
 int b200md_compute(b200md_ctx* ctx, int terms, int want_forces, double* energy);
+/* the same with the `groups` bit mask of CalcForcesAndEnergyKernel::beginComputation (kernels.h:96): a bond / angle /
+ * torsion is evaluated iff its class is in `terms` AND bit (its force group) of bonded_group_mask is set.            */
+int b200md_compute_groups(b200md_ctx* ctx, int terms, unsigned int bonded_group_mask, int want_forces, double* energy);
 
 /* ---------------------------------------------------------------------------------------------------
  * Integrate*StepKernel::initialize/execute/computeKineticEnergy (kernels.h:1033-1060, 1160-1220),

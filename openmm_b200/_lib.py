@@ -3,7 +3,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200md.so")
+LIB_PATH = os.environ.get("B200MD_LIB", os.path.join(_HERE, "libb200md.so"))      # B200MD_LIB: experiment builds (csrc/Makefile `dbl`)
 
 
 class NonbondedDesc(C.Structure):
@@ -36,7 +36,9 @@ SIGNATURES = {
     "b200md_set_bonds": (C.c_int, [_P, C.c_int, _I, _I, _D, _D]),
     "b200md_set_angles": (C.c_int, [_P, C.c_int, _I, _I, _I, _D, _D]),
     "b200md_set_torsions": (C.c_int, [_P, C.c_int, _I, _I, _I, _I, _I, _D, _D]),
+    "b200md_set_bonded_groups": (C.c_int, [_P, C.c_int, C.c_int, _I]),
     "b200md_set_constraints": (C.c_int, [_P, C.c_int, _I, _I, _D]),
+    "b200md_check_constraints": (C.c_int, [C.c_int, _D, C.c_int, _I, _I, _D, C.c_char_p, C.c_int]),
     "b200md_set_cm_remover": (C.c_int, [_P, C.c_int]),
     "b200md_remove_cm_motion": (C.c_int, [_P]),
     "b200md_finalize": (C.c_int, [_P]),
@@ -55,6 +57,7 @@ SIGNATURES = {
     "b200md_checkpoint_save": (C.c_int64, [_P, _P, C.c_int64]),
     "b200md_checkpoint_load": (C.c_int, [_P, _P, C.c_int64]),
     "b200md_compute": (C.c_int, [_P, C.c_int, C.c_int, _D]),
+    "b200md_compute_groups": (C.c_int, [_P, C.c_int, C.c_uint, C.c_int, _D]),
     "b200md_set_integrator": (C.c_int, [_P, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int, C.c_double]),
     "b200md_step": (C.c_int, [_P, C.c_int]),
     "b200md_integrate_only": (C.c_int, [_P]),

@@ -44,10 +44,13 @@ __global__ void __launch_bounds__(128) k_bonded(NbDev nb, BondedDev bd, int term
     const int gid = nb.rank + nb.world*(blockIdx.x*blockDim.x + threadIdx.x);
     double eB = 0, eA = 0, eT = 0, eE = 0;
     int i = gid;
-    if (i < nB) {
+    // group byte of a bonded term: bits 0-4 force group, bit 7 = the Force uses periodic boundary conditions
+    // (usesPeriodicBoundaryConditions: every difference vector takes the minimum image, ReferenceBondIxn / getDeltaRPeriodic)
+    if (i < nB && ((bd.groupMask >> (bd.bondGroup[i] & 31)) & 1u)) {
         const int2 at = bd.bondAtoms[i];
         const double2 pr = bd.bondParams[i];
         D3 d = sub(nb.posq[at.x], nb.posq[at.y]);
+        if (bd.bondGroup[i] & 0x80) d = min_image_d(d, nb.box);
         const double r = sqrt(dot(d, d));
         const double dr = r - pr.x;
         eB = 0.5*pr.y*dr*dr;
@@ -56,11 +59,12 @@ __global__ void __launch_bounds__(128) k_bonded(NbDev nb, BondedDev bd, int term
         add_force(nb, at.y, scale(d, -s));
     }
     i -= nB;
-    if (i >= 0 && i < nA) {
+    if (i >= 0 && i < nA && ((bd.groupMask >> (bd.angleGroup[i] & 31)) & 1u)) {
         const int4 at = bd.angleAtoms[i];
         const double2 pr = bd.angleParams[i];
         D3 v0 = sub(nb.posq[at.y], nb.posq[at.x]);
         D3 v1 = sub(nb.posq[at.y], nb.posq[at.z]);
+        if (bd.angleGroup[i] & 0x80) { v0 = min_image_d(v0, nb.box); v1 = min_image_d(v1, nb.box); }
         D3 cp = cross(v0, v1);
         double rp = sqrt(dot(cp, cp));
         rp = fmax(rp, 1e-6);
@@ -78,12 +82,13 @@ __global__ void __launch_bounds__(128) k_bonded(NbDev nb, BondedDev bd, int term
         add_force(nb, at.y, {-f1.x-f3.x, -f1.y-f3.y, -f1.z-f3.z});
     }
     i -= nA;
-    if (i >= 0 && i < nT) {
+    if (i >= 0 && i < nT && ((bd.groupMask >> (bd.torsionGroup[i] & 31)) & 1u)) {
         const int4 at = bd.torsionAtoms[i];
         const double4 pr = bd.torsionParams[i];   // k, phase, n
         D3 v0 = sub(nb.posq[at.x], nb.posq[at.y]);
         D3 v1 = sub(nb.posq[at.z], nb.posq[at.y]);
         D3 v2 = sub(nb.posq[at.z], nb.posq[at.w]);
+        if (bd.torsionGroup[i] & 0x80) { v0 = min_image_d(v0, nb.box); v1 = min_image_d(v1, nb.box); v2 = min_image_d(v2, nb.box); }
         D3 cp0 = cross(v0, v1), cp1 = cross(v1, v2);
         const double n0 = dot(cp0, cp0), n1 = dot(cp1, cp1);
         double c = dot(cp0, cp1)/sqrt(n0*n1);

@@ -75,6 +75,7 @@ struct b200md_ctx {
     std::vector<int> bondI, bondJ; std::vector<double> bondR0, bondK;
     std::vector<int> angI, angJ, angK; std::vector<double> angT0, angKK;
     std::vector<int> torI, torJ, torK, torL, torN; std::vector<double> torPhase, torKK;
+    std::vector<unsigned char> bondGroup, angGroup, torGroup;       // force group of every bonded element (default 0)
     std::vector<int> conI, conJ; std::vector<double> conD;
     int cmFreq = 0;
     double boxA[3] = {0, 0, 0}, boxB[3] = {0, 0, 0}, boxC[3] = {0, 0, 0};
@@ -99,6 +100,7 @@ struct b200md_ctx {
     DevBuf<int2> bondAtoms, excAtoms; DevBuf<double2> bondParams, angleParams;
     DevBuf<int4> angleAtoms, torsionAtoms, unitAtoms; DevBuf<double4> torsionParams, excParams;
     DevBuf<int> unitType; DevBuf<float4> unitParams;
+    DevBuf<unsigned char> bondGroupDev, angGroupDev, torGroupDev;
     NbDev nb{};
     PmeDev pme{};
     BondedDev bd{};
@@ -130,6 +132,7 @@ struct b200md_ctx {
 #define API_END(ctx) } catch (std::exception& e) { (ctx)->err = e.what(); return -1; } return 0;
 
 static void require(bool cond, const char* msg) { if (!cond) throw std::runtime_error(msg); }
+static void check_flags(b200md_ctx* c);
 
 extern "C" const char* b200md_version(void) { return "b200md 0.1 (sm_100a)"; }
 extern "C" const char* b200md_last_error(const b200md_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
@@ -238,6 +241,15 @@ extern "C" int b200md_set_torsions(b200md_ctx* ctx, int n, const int* p1, const 
     require(!ctx->finalized, "set_torsions after finalize");
     ctx->torI.assign(p1, p1+n); ctx->torJ.assign(p2, p2+n); ctx->torK.assign(p3, p3+n); ctx->torL.assign(p4, p4+n);
     ctx->torN.assign(per, per+n); ctx->torPhase.assign(ph, ph+n); ctx->torKK.assign(k, k+n);
+    API_END(ctx)
+}
+extern "C" int b200md_set_bonded_groups(b200md_ctx* ctx, int kind, int n, const int* group) {
+    API_BEGIN(ctx)
+    require(!ctx->finalized, "set_bonded_groups after finalize");
+    require(kind >= 0 && kind <= 2, "set_bonded_groups: kind must be 0 (bonds), 1 (angles) or 2 (torsions)");
+    std::vector<unsigned char>& g = kind == 0 ? ctx->bondGroup : (kind == 1 ? ctx->angGroup : ctx->torGroup);
+    g.resize(n);
+    for (int i = 0; i < n; i++) { require(group[i] >= 0 && (group[i] & ~0x80) < 32, "force group out of range"); g[i] = (unsigned char) group[i]; }
     API_END(ctx)
 }
 extern "C" int b200md_set_constraints(b200md_ctx* ctx, int n, const int* p1, const int* p2, const double* d) {
@@ -387,13 +399,16 @@ static void upload_params(b200md_ctx* c) {
     c->selfEnergy = self;
 }
 
-static void build_units(b200md_ctx* c) {
-    const int N = c->natoms;
-    const int nc = (int) c->conI.size();
+// Integration units: SETTLE waters, X-H_n SHAKE clusters, free atoms.  Pure host function so that the plugin can run it
+// as a dry run from Platform::contextCreated (b200md_check_constraints) before anything is allocated.
+static bool classify_units(int N, const double* mass, const std::vector<int>& conI, const std::vector<int>& conJ, const std::vector<double>& conD,
+                           std::vector<int4>& ua2, std::vector<int>& ut2, std::vector<float4>& up2, std::string& err) {
+    const int nc = (int) conI.size();
     std::vector<std::vector<std::pair<int, double> > > adj(N);
     for (int k = 0; k < nc; k++) {
-        adj[c->conI[k]].push_back(std::make_pair(c->conJ[k], c->conD[k]));
-        adj[c->conJ[k]].push_back(std::make_pair(c->conI[k], c->conD[k]));
+        if (conI[k] < 0 || conI[k] >= N || conJ[k] < 0 || conJ[k] >= N || conI[k] == conJ[k]) { err = "constraint with an illegal particle index"; return false; }
+        adj[conI[k]].push_back(std::make_pair(conJ[k], conD[k]));
+        adj[conJ[k]].push_back(std::make_pair(conI[k], conD[k]));
     }
     std::vector<int> assigned(N, 0);
     std::vector<int4> ua; std::vector<int> ut; std::vector<float4> up;
@@ -411,7 +426,7 @@ static void build_units(b200md_ctx* c) {
         else if (dab == dbd) { apex = b; o1 = a; o2 = d; d1 = dab; d2 = dad; }
         else if (dad == dbd) { apex = d; o1 = a; o2 = b; d1 = dad; d2 = dab; }
         else continue;
-        if (c->mass[apex] == 0 || c->mass[o1] == 0 || c->mass[o2] == 0) continue;
+        if (mass[apex] == 0 || mass[o1] == 0 || mass[o2] == 0) continue;
         assigned[a] = assigned[b] = assigned[d] = 1;
         order.push_back(std::make_pair(std::min(a, std::min(b, d)), (int) ua.size()));
         ua.push_back(make_int4(apex, o1, o2, -1)); ut.push_back(1); up.push_back(make_float4(d1, d2, 0.f, 0.f));
@@ -424,7 +439,7 @@ static void build_units(b200md_ctx* c) {
         if (adj[a].size() == 1 && adj[adj[a][0].first].size() == 1) {
             // isolated pair: the heavier atom is the centre, ties -> lower index
             int b = adj[a][0].first;
-            if (c->mass[b] > c->mass[a] || (c->mass[b] == c->mass[a] && b < a)) centre = false;
+            if (mass[b] > mass[a] || (mass[b] == mass[a] && b < a)) centre = false;
         }
         if (!centre) continue;
         int at[4] = {a, -1, -1, -1}; float dd[3] = {0, 0, 0};
@@ -434,19 +449,40 @@ static void build_units(b200md_ctx* c) {
         ua.push_back(make_int4(at[0], at[1], at[2], at[3])); ut.push_back(2); up.push_back(make_float4(dd[0], dd[1], dd[2], 0.f));
     }
     for (int a = 0; a < N; a++) {
-        if (!assigned[a] && !adj[a].empty())
-            throw std::runtime_error("B200 platform: unsupported constraint topology (only rigid 3-atom molecules and X-H_n clusters; general CCMA constraints are not implemented)");
+        if (!assigned[a] && !adj[a].empty()) {
+            err = "unsupported constraint topology (only rigid 3-atom molecules and X-H_n clusters; general CCMA constraints are not implemented)";
+            return false;
+        }
         if (!assigned[a]) {
             order.push_back(std::make_pair(a, (int) ua.size()));
             ua.push_back(make_int4(a, -1, -1, -1)); ut.push_back(0); up.push_back(make_float4(0, 0, 0, 0));
         }
     }
     std::sort(order.begin(), order.end());
-    std::vector<int4> ua2(ua.size()); std::vector<int> ut2(ua.size()); std::vector<float4> up2(ua.size());
+    ua2.resize(ua.size()); ut2.resize(ua.size()); up2.resize(ua.size());
     for (size_t k = 0; k < order.size(); k++) { ua2[k] = ua[order[k].second]; ut2[k] = ut[order[k].second]; up2[k] = up[order[k].second]; }
+    return true;
+}
+
+static void build_units(b200md_ctx* c) {
+    std::vector<int4> ua2; std::vector<int> ut2; std::vector<float4> up2;
+    std::string err;
+    if (!classify_units(c->natoms, c->mass.data(), c->conI, c->conJ, c->conD, ua2, ut2, up2, err)) throw std::runtime_error("B200 platform: " + err);
     c->unitAtoms.upload(ua2); c->unitType.upload(ut2); c->unitParams.upload(up2);
     c->units.nunits = (int) ua2.size();
     c->units.unitAtoms = c->unitAtoms.p; c->units.unitType = c->unitType.p; c->units.unitParams = c->unitParams.p;
+}
+
+// dry run of the constraint classification (no context, no device): 0 = every constraint is supported
+extern "C" int b200md_check_constraints(int natoms, const double* mass, int n, const int* p1, const int* p2, const double* d, char* msg, int msglen) {
+    try {
+        std::vector<int> ci(p1, p1+n), cj(p2, p2+n); std::vector<double> cd(d, d+n);
+        std::vector<int4> ua; std::vector<int> ut; std::vector<float4> up;
+        std::string err;
+        if (classify_units(natoms, mass, ci, cj, cd, ua, ut, up, err)) return 0;
+        if (msg && msglen > 0) { strncpy(msg, err.c_str(), msglen-1); msg[msglen-1] = 0; }
+        return -1;
+    } catch (std::exception& e) { if (msg && msglen > 0) { strncpy(msg, e.what(), msglen-1); msg[msglen-1] = 0; } return -1; }
 }
 
 // B-spline moduli (pme_calculate_bsplines_moduli, ReferencePME.cpp:98-193)
@@ -510,6 +546,44 @@ static void setup_pme(b200md_ctx* c, int nx, int ny, int nz, double alpha) {
     }
 }
 
+
+// ---------------------------------------------------------------- tile pools
+// Capacity of ONE of the TILE_REGIONS slot pools.  The first guess assumes a homogeneous density; prepare_list() measures
+// the pools after every list build that follows a change of the state from outside and grows them (slabs, droplets,
+// vacuum around a solute and box changes are then handled instead of raising "capacity exceeded").
+static int initial_pool_capacity(const b200md_ctx* c) {
+    const int nbk = c->nblocks, N = c->natoms;
+    const double rc = c->nbdesc.cutoff;
+    // worst case (every block pair interacts): i-block ib emits at most nbk - ib + 2 tiles (its j-blocks, the diagonal
+    // tile on its own, one partial tile); pool 0 holds the smallest ib and is the fullest
+    double poolCap = 0;
+    for (int ib = 0; ib < nbk; ib += TILE_REGIONS) poolCap += nbk - ib + 2;
+    if (c->nb.method != B200MD_NB_NOCUTOFF && c->haveBox) {
+        const double vol = c->boxA[0]*c->boxB[1]*c->boxC[2];
+        const double rp = rc*(1.0 + c->padFrac);
+        const double pairs = 0.5*N*(N/vol)*(4.0/3.0*M_PI*rp*rp*rp);
+        const double est = pairs/(1024.0*0.15) + 18.0*nbk;           // tiles at >= 15 % fill + partial tiles
+        poolCap = std::min(poolCap, 1.25*est/TILE_REGIONS + 64);     // + slack for the imbalance between pools
+    }
+    poolCap = std::min(poolCap, 16.0e6/TILE_REGIONS);
+    if (c->pmeOnly) poolCap = 1;
+    return (int) poolCap + 1;
+}
+static int worst_pool_capacity(const b200md_ctx* c) {
+    double cap = 0;
+    for (int ib = 0; ib < c->nblocks; ib += TILE_REGIONS) cap += c->nblocks - ib + 2;
+    return (int) std::min(cap, 2.0e9/TILE_REGIONS/32) + 1;
+}
+static void alloc_tile_pools(b200md_ctx* c, int poolCap) {
+    NbDev& nb = c->nb;
+    nb.maxTiles = poolCap*TILE_REGIONS;
+    for (int l = 0; l < 2; l++) {
+        c->tileI[l].alloc(nb.maxTiles); c->tileJ[l].alloc((size_t) nb.maxTiles*32); c->tileMask[l].alloc(nb.maxTiles); c->maskPool[l].alloc((size_t) nb.maxTiles*32);
+        ListDev& L = nb.list[l];
+        L.tileI = c->tileI[l].p; L.tileJ = c->tileJ[l].p; L.tileMask = c->tileMask[l].p; L.maskPool = c->maskPool[l].p;
+    }
+}
+
 extern "C" int b200md_finalize(b200md_ctx* ctx) {
     API_BEGIN(ctx)
     require(!ctx->finalized, "finalize called twice");
@@ -522,6 +596,7 @@ extern "C" int b200md_finalize(b200md_ctx* ctx) {
     nb.rank = c->rank; nb.world = c->world;
     nb.useRational = getenv("B200MD_PAIR_RATIONAL") ? atoi(getenv("B200MD_PAIR_RATIONAL")) : 0;
     nb.pairDynamic = getenv("B200MD_PAIR_DYNAMIC") ? atoi(getenv("B200MD_PAIR_DYNAMIC")) : 0;
+    { const double cc = getenv("B200MD_CLOSE_NM") ? atof(getenv("B200MD_CLOSE_NM")) : 0.32; nb.closeCut2 = (float) (cc*cc); }
     nb.packCull = getenv("B200MD_BT_PACK") ? atoi(getenv("B200MD_BT_PACK")) : 1;
     // ---- state arrays ----
     c->posq.alloc(NP); c->posq.zero(); c->velm.alloc(NP); c->velm.zero();
@@ -584,28 +659,7 @@ extern "C" int b200md_finalize(b200md_ctx* ctx) {
         nb.exclStart = c->exclStart.p; nb.exclList = c->exclList.p;
     }
     // ---- tile capacity: TILE_REGIONS equal slot pools, i-block ib allocates from pool ib % TILE_REGIONS (flush_tile) ----
-    {
-        const int nbk = c->nblocks;
-        // worst case (every block pair interacts): i-block ib emits at most nbk - ib + 2 tiles (its j-blocks, the diagonal
-        // tile on its own, one partial tile); pool 0 holds the smallest ib and is the fullest
-        double poolCap = 0;
-        for (int ib = 0; ib < nbk; ib += TILE_REGIONS) poolCap += nbk - ib + 2;
-        if (nb.method != B200MD_NB_NOCUTOFF && c->haveBox) {
-            const double vol = c->boxA[0]*c->boxB[1]*c->boxC[2];
-            const double rp = rc*(1.0 + c->padFrac);
-            const double pairs = 0.5*N*(N/vol)*(4.0/3.0*M_PI*rp*rp*rp);
-            const double est = pairs/(1024.0*0.15) + 18.0*nbk;           // tiles at >= 15 % fill + partial tiles
-            poolCap = std::min(poolCap, 1.25*est/TILE_REGIONS + 64);     // + slack for the imbalance between pools
-        }
-        poolCap = std::min(poolCap, 16.0e6/TILE_REGIONS);
-        if (c->pmeOnly) poolCap = 1;
-        nb.maxTiles = ((int) poolCap + 1)*TILE_REGIONS;
-        for (int l = 0; l < 2; l++) {
-            c->tileI[l].alloc(nb.maxTiles); c->tileJ[l].alloc((size_t) nb.maxTiles*32); c->tileMask[l].alloc(nb.maxTiles); c->maskPool[l].alloc((size_t) nb.maxTiles*32);
-            ListDev& L = nb.list[l];
-            L.tileI = c->tileI[l].p; L.tileJ = c->tileJ[l].p; L.tileMask = c->tileMask[l].p; L.maskPool = c->maskPool[l].p;
-        }
-    }
+    alloc_tile_pools(c, initial_pool_capacity(c));
     // ---- bonded ----
     {
         const int nbnd = (int) c->bondI.size(), na = (int) c->angI.size(), nt = (int) c->torI.size();
@@ -621,6 +675,12 @@ extern "C" int b200md_finalize(b200md_ctx* ctx) {
         c->bd.bondAtoms = c->bondAtoms.p; c->bd.bondParams = c->bondParams.p; c->bd.angleAtoms = c->angleAtoms.p; c->bd.angleParams = c->angleParams.p;
         c->bd.torsionAtoms = c->torsionAtoms.p; c->bd.torsionParams = c->torsionParams.p;
         c->bd.excPeriodic = c->nbdesc.exceptions_periodic;
+        require((c->bondGroup.empty() || (int) c->bondGroup.size() == nbnd) && (c->angGroup.empty() || (int) c->angGroup.size() == na) &&
+                (c->torGroup.empty() || (int) c->torGroup.size() == nt), "set_bonded_groups: group array length differs from the number of terms");
+        c->bondGroup.resize(std::max(nbnd, 1), 0); c->angGroup.resize(std::max(na, 1), 0); c->torGroup.resize(std::max(nt, 1), 0);
+        c->bondGroupDev.upload(c->bondGroup); c->angGroupDev.upload(c->angGroup); c->torGroupDev.upload(c->torGroup);
+        c->bd.bondGroup = c->bondGroupDev.p; c->bd.angleGroup = c->angGroupDev.p; c->bd.torsionGroup = c->torGroupDev.p;
+        c->bd.groupMask = 0xffffffffu;
     }
     upload_params(c);
     build_units(c);
@@ -629,7 +689,8 @@ extern "C" int b200md_finalize(b200md_ctx* ctx) {
     // and the reciprocal-space rank builds no list) ----
     c->cellOffset.alloc((size_t) 3*NP); c->cellOffset.zero();
     nb.cellOffset = c->cellOffset.p; nb.nmol = 0; nb.molStart = nullptr; nb.molAtoms = nullptr;
-    if ((nb.method == B200MD_NB_CUTOFF_PERIODIC || nb.method == B200MD_NB_PME) && c->world == 1 && !c->pmeOnly && !getenv("B200MD_NO_WRAP")) {
+    // (also off with B200MD_ASYNC_LIST=1: the side-stream build would move molecules while bonded / PME kernels read them)
+    if ((nb.method == B200MD_NB_CUTOFF_PERIODIC || nb.method == B200MD_NB_PME) && c->world == 1 && !c->pmeOnly && !c->asyncList && !getenv("B200MD_NO_WRAP")) {
         std::vector<int> parent(N);
         for (int i = 0; i < N; i++) parent[i] = i;
         auto find = [&](int x) { while (parent[x] != x) { parent[x] = parent[parent[x]]; x = parent[x]; } return x; };
@@ -655,7 +716,7 @@ extern "C" int b200md_finalize(b200md_ctx* ctx) {
     }
     if (nb.method == B200MD_NB_PME) setup_pme(c, c->nbdesc.grid[0], c->nbdesc.grid[1], c->nbdesc.grid[2], c->nbdesc.ewald_alpha);
     c->finalized = true;
-    apply_box(c);
+    try { apply_box(c); } catch (...) { c->finalized = false; throw; }      // e.g. box smaller than twice the cutoff: the caller may fix the box and finalize again
     c->integ.stepCounter = c->stepCounter.p;
     c->integ.fused = 0; c->integ.cmEveryStep = 0; c->integ.cmScratch = c->cmScratch.p; c->integ.blocksDone = c->blocksDone.p;
     API_END(ctx)
@@ -732,7 +793,7 @@ extern "C" int b200md_get_positions(b200md_ctx* ctx, double* x) {
     API_BEGIN(ctx)
     ctx->hbuf4.resize(ctx->npad);
     CUDA_CHECK(cudaMemcpyAsync(ctx->hbuf4.data(), ctx->posq.p, sizeof(float4)*ctx->npad, cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    check_flags(ctx);
     for (int i = 0; i < ctx->natoms; i++) { x[3*i] = ctx->hbuf4[i].x; x[3*i+1] = ctx->hbuf4[i].y; x[3*i+2] = ctx->hbuf4[i].z; }
     if (ctx->nb.nmol > 0) {
         // undo the internal molecule wrapping: the caller sees the continuous trajectory, like the Reference platform's
@@ -766,7 +827,7 @@ extern "C" int b200md_get_velocities(b200md_ctx* ctx, double* v) {
     API_BEGIN(ctx)
     ctx->hbuf4.resize(ctx->npad);
     CUDA_CHECK(cudaMemcpyAsync(ctx->hbuf4.data(), ctx->velm.p, sizeof(float4)*ctx->npad, cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    check_flags(ctx);
     for (int i = 0; i < ctx->natoms; i++) { v[3*i] = ctx->hbuf4[i].x; v[3*i+1] = ctx->hbuf4[i].y; v[3*i+2] = ctx->hbuf4[i].z; }
     API_END(ctx)
 }
@@ -787,6 +848,7 @@ extern "C" void* b200md_cuda_stream(b200md_ctx* ctx) { return ctx ? (void*) ctx-
 extern "C" int b200md_synchronize(b200md_ctx* ctx) {
     API_BEGIN(ctx)
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    check_flags(ctx);
     API_END(ctx)
 }
 
@@ -815,6 +877,7 @@ extern "C" int64_t b200md_checkpoint_save(b200md_ctx* ctx, void* buf, int64_t ca
 extern "C" int b200md_checkpoint_load(b200md_ctx* ctx, const void* buf, int64_t size) {
     API_BEGIN(ctx)
     ctx->stepStateValid = false;
+    require(ctx->finalized, "checkpoint_load before finalize");
     const int64_t need = sizeof(CkptHeader) + 2*sizeof(float4)*(int64_t) ctx->npad + 3*sizeof(int)*(int64_t) ctx->npad;
     require(size >= need, "checkpoint blob too small");
     CkptHeader h; memcpy(&h, buf, sizeof(h));
@@ -848,7 +911,7 @@ static NbDev role_nb(const b200md_ctx* c) {
 
 // ---------------------------------------------------------------- force evaluation
 // Enqueue one force evaluation on the stream (no host sync).  Returns the number of kernels launched.
-static int enqueue_forces(b200md_ctx* c, int terms, bool energy, bool forcesAlreadyZero = false, bool inStep = false) {
+static int enqueue_forces(b200md_ctx* c, int terms, bool energy, bool forcesAlreadyZero = false, bool inStep = false, unsigned int groupMask = 0xffffffffu) {
     int launches = 0;
     cudaStream_t s = c->stream;
     if (!forcesAlreadyZero) CUDA_CHECK(cudaMemsetAsync(c->force.p, 0, sizeof(long long)*3*c->npad, s));
@@ -964,7 +1027,7 @@ static int enqueue_forces(b200md_ctx* c, int terms, bool energy, bool forcesAlre
     int bterms = terms & (B200MD_TERM_BONDS | B200MD_TERM_ANGLES | B200MD_TERM_TORSIONS);
     if (c->haveNb) bterms |= terms & B200MD_TERM_NB_DIRECT;
     const int nbonded = c->bd.nbonds + c->bd.nangles + c->bd.ntorsions + c->bd.nexc;
-    if (bterms && nbonded > 0 && !(split && c->rank == pmeRank)) { launch_bonded(c->nb, c->bd, bterms, energy, s); launches++; }
+    if (bterms && nbonded > 0 && !(split && c->rank == pmeRank)) { BondedDev bd = c->bd; bd.groupMask = groupMask; launch_bonded(c->nb, bd, bterms, energy, s); launches++; }
     if (fork) CUDA_CHECK(cudaStreamWaitEvent(s, c->evJoin, 0));
     if (joinList) CUDA_CHECK(cudaStreamWaitEvent(s, c->evListJoin, 0));
     if (c->world > 1 && c->comm) {
@@ -979,21 +1042,70 @@ static int enqueue_forces(b200md_ctx* c, int terms, bool energy, bool forcesAlre
     return launches;
 }
 
+// Sticky device flags are read at EVERY point where the host synchronises with the stream anyway (energy reads, state
+// reads, b200md_synchronize), so a problem inside a run of b200md_step calls surfaces at the next state read instead of
+// silently dropping pair interactions.
 static void check_flags(b200md_ctx* c) {
+    if (!c->finalized) return;
     int h[8];
     CUDA_CHECK(cudaMemcpyAsync(h, c->counters.p, sizeof(int)*8, cudaMemcpyDeviceToHost, c->stream));
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
     if (h[CT_OVERFLOW] == 2) throw std::runtime_error("B200 platform: neighbour-list construction timed out at a grid barrier (k_list_prep)");
-    if (h[CT_OVERFLOW]) throw std::runtime_error("B200 platform: neighbour-list tile capacity exceeded (" + std::to_string(c->nb.maxTiles) + " tiles)");
+    if (h[CT_OVERFLOW]) throw std::runtime_error("B200 platform: neighbour-list tile capacity exceeded (" + std::to_string(c->nb.maxTiles) + " tiles) during the preceding steps; the trajectory since the last state read is invalid");
+}
+
+static bool role_split(const b200md_ctx* c);
+static NbDev role_nb(const b200md_ctx* c);
+static void invalidate_graph(b200md_ctx* c);
+
+// After the state was changed from outside (positions, box, parameters, checkpoint): build the list now, synchronously,
+// and size the tile pools from what the build actually used.  The step graphs trust the current list and never grow it.
+static void prepare_list(b200md_ctx* c) {
+    if (!c->listDirty || !c->haveNb) { c->listDirty = false; return; }
+    if (c->pmeOnly || (role_split(c) && c->rank == c->world - 1)) { c->listDirty = false; return; }    // keeps no list
+    for (int attempt = 0; attempt < 8; attempt++) {
+        const NbDev nb = role_nb(c);
+        launch_check_displacement(nb, c->stream);
+        launch_list_build(nb, c->stream, 0);
+        c->kernelLaunches += 1 + list_build_launch_count();
+        int h[16], lc[2*LC_STRIDE];
+        CUDA_CHECK(cudaMemcpyAsync(h, c->counters.p, sizeof(int)*16, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_CHECK(cudaMemcpyAsync(lc, c->listCounters.p, sizeof(lc), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        if (h[CT_OVERFLOW] == 2) throw std::runtime_error("B200 platform: neighbour-list construction timed out at a grid barrier (k_list_prep)");
+        const int* cur = lc + LC_STRIDE*(h[CT_CUR] & 1);
+        int worst = 0;
+        for (int r = 0; r < TILE_REGIONS; r++) worst = std::max(worst, cur[LC_TILES + r]);
+        const int cap = c->nb.maxTiles/TILE_REGIONS;
+        const bool overflow = h[CT_OVERFLOW] != 0;
+        if (!overflow && worst <= (int) (0.8*cap)) { c->listDirty = false; return; }
+        // grow: the counters keep counting past the capacity (flush_tile), so `worst` is the demand even after an overflow
+        const int want = std::min(worst_pool_capacity(c), std::max(2*cap, (int) (1.5*worst) + 64));
+        if (want <= cap) {
+            if (overflow) throw std::runtime_error("B200 platform: neighbour-list tile capacity exceeded and cannot grow (" + std::to_string(c->nb.maxTiles) + " tiles)");
+            c->listDirty = false; return;
+        }
+        alloc_tile_pools(c, want);
+        const int zero = 0, one = 1;
+        CUDA_CHECK(cudaMemcpy(&c->counters.p[CT_OVERFLOW], &zero, sizeof(int), cudaMemcpyHostToDevice));
+        CUDA_CHECK(cudaMemcpy(&c->counters.p[CT_REBUILD], &one, sizeof(int), cudaMemcpyHostToDevice));
+        invalidate_graph(c);
+    }
+    throw std::runtime_error("B200 platform: neighbour-list tile pools did not converge");
 }
 
 extern "C" int b200md_compute(b200md_ctx* ctx, int terms, int want_forces, double* energy) {
+    return b200md_compute_groups(ctx, terms, 0xffffffffu, want_forces, energy);
+}
+
+extern "C" int b200md_compute_groups(b200md_ctx* ctx, int terms, unsigned int bonded_group_mask, int want_forces, double* energy) {
     API_BEGIN(ctx)
     ctx->stepStateValid = false;
     (void) want_forces;
     require(ctx->finalized, "compute before finalize");
     const bool wantE = energy != nullptr;
-    ctx->kernelLaunches += enqueue_forces(ctx, terms, wantE);
+    prepare_list(ctx);
+    ctx->kernelLaunches += enqueue_forces(ctx, terms, wantE, false, false, bonded_group_mask);
     ctx->forceEvals++;
     if (wantE) {
         double h[B200MD_NUM_ENERGY];
@@ -1094,17 +1206,7 @@ extern "C" int b200md_step(b200md_ctx* ctx, int nsteps) {
     require(ctx->finalized && ctx->haveIntegrator, "step before finalize / set_integrator");
     b200md_ctx* c = ctx;
     int remaining = nsteps;
-    if (c->listDirty && c->haveNb) {
-        // the state was changed from outside: bring the neighbour list up to date before the step graphs, whose tile
-        // kernel trusts the current list (kernels gated on counters[CT_REBUILD], which the setter raised)
-        if (!(role_split(c) && c->rank == c->world - 1)) {      // the reciprocal-space rank keeps no list
-            const NbDev nb = role_nb(c);
-            launch_check_displacement(nb, c->stream);
-            launch_list_build(nb, c->stream, 0);
-            c->kernelLaunches += 1 + list_build_launch_count();
-        }
-        c->listDirty = false;
-    }
+    prepare_list(c);      // the state was changed from outside: the step graphs trust the current list
     if (!c->stepStateValid) {
         CUDA_CHECK(cudaMemsetAsync(c->force.p, 0, sizeof(long long)*3*c->npad, c->stream));
         if (c->cmFreq == 1) {
@@ -1154,7 +1256,7 @@ extern "C" int b200md_kinetic_energy(b200md_ctx* ctx, double* ke) {
     launch_kinetic_energy(ctx->nb, ctx->units, ctx->integ, shift, ctx->stream);
     ctx->kernelLaunches++;
     CUDA_CHECK(cudaMemcpyAsync(ke, ctx->energy.p + EN_KE, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    check_flags(ctx);
     API_END(ctx)
 }
 extern "C" int b200md_apply_constraints(b200md_ctx* ctx, double tol) {
@@ -1264,6 +1366,8 @@ extern "C" int b200md_time_phase(b200md_ctx* ctx, int phase, int reps, double* m
     API_BEGIN(ctx)
     require(ctx->finalized, "time_phase before finalize");
     b200md_ctx* c = ctx;
+    prepare_list(c);
+    c->stepStateValid = false;            // phases 0, 3, 6 accumulate into the force buffer, phase 5 flips the list
     cudaStream_t s = c->stream;
     const NbDev nbv = role_nb(c);        // the sharding the step graphs use
     cudaEvent_t e0, e1;

@@ -30,8 +30,13 @@ struct BoxDev {
 // precision of the spectral pipeline (charge grid -> FFT -> convolution -> potential grid); the input grid is int64
 // fixed point either way.  fp32 measured sufficient: the 1e-3 level recip force errors seen on ApoA1 came from lattice-
 // shifted fp32 coordinates, not from the transform (identical errors with a double pipeline).
+#ifdef B200MD_REAL_DOUBLE      // experiment build (make dbl -> libb200md_dbl.so): double spectral pipeline, for error attribution only
+typedef double real;
+typedef double2 real2;
+#else
 typedef float real;
 typedef float2 real2;
+#endif
 
 struct FftPlanDev {      // 1-D mixed-radix Stockham plan for one grid dimension
     int n;
@@ -119,6 +124,7 @@ struct NbDev {
     unsigned long long condAsync;   // second IF node: build of the successor list on a side stream
     int packCull;                // k_build_tiles: exact cull on full warps (B200MD_BT_PACK)
     int pairDynamic;             // tile kernel fetches tiles from a cursor instead of a static stride
+    float closeCut2;             // pairs closer than this (squared) are evaluated in double from the exact coordinates (0: off)
     int useRational;             // B200MD_PAIR_RATIONAL=1: rational Ewald kernel in the force-only tile loop (1 MUFU less, lower accuracy)
 };
 
@@ -142,6 +148,10 @@ struct BondedDev {
     const int4* torsionAtoms; const double4* torsionParams;     // (k, phase, n, 0)
     const int2* excAtoms; const double4* excParams;             // (qq14*ONE_4PI_EPS0, sigma, 4 eps, 0)
     int excPeriodic;
+    // force group of every bond / angle / torsion (several Force objects of one class may sit in different groups,
+    // ContextImpl::calcForcesAndEnergy groups, ContextImpl.cpp:293-308); an element is evaluated iff bit `group` of groupMask is set
+    const unsigned char* bondGroup; const unsigned char* angleGroup; const unsigned char* torsionGroup;
+    unsigned int groupMask;
 };
 
 // One integration unit = a SETTLE water, a SHAKE cluster (centre + <=3 H) or a free atom.

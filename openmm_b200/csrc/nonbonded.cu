@@ -840,8 +840,71 @@ __device__ __forceinline__ float wrap_rel(float p, float c, double L, double inv
     return (float) r;
 }
 
-template <bool ENERGY, int METHOD, bool SHIFT, bool RATIONAL, bool SWITCH>
-__device__ __forceinline__ void pair_tiles(const NbDev& nb, const ListDev& L, float& energy) {
+// ---- close pairs in double precision ----
+// fp32 pair arithmetic has a relative error of ~1.5e-7 and the coordinates relative to the block centre are rounded to
+// ~3e-8 nm.  On a hydrogen-bonded pair (|F| ~ 1,500 kJ/mol/nm, dF/dr ~ 16,000) that is 2-5e-4 kJ/mol/nm of absolute error
+// on BOTH atoms, which is what an atom with a small net force (a lipid tail atom next to a water, say) is measured
+// against in the reference's 1e-4 criterion.  Pairs closer than nb.closeCut (default 0.32 nm, ~4 % of the pairs inside the
+// cutoff) are therefore taken out of the fp32 loop: the lane notes (i lane, j slot) in a per-warp queue, and after the 32
+// rotations the warp evaluates the queued pairs in double from the EXACT user coordinates and adds the forces to the
+// fixed-point buffer directly.  ReferenceLJCoulombIxn.cpp:388-447 (PME) / :559-575 (cutoff) / calculateOneIxn restated.
+#define CLOSE_QCAP 96
+template <bool ENERGY, int METHOD, bool SWITCH>
+__device__ __forceinline__ void close_pair_double(const NbDev& nb, const ListDev& L, int si, int sj, double& energyD) {
+    const float4 a = L.sposq[si], b = L.sposq[sj];
+    const float2 sa = L.ssigeps[si], sb = L.ssigeps[sj];
+    double dx = (double) b.x - (double) a.x, dy = (double) b.y - (double) a.y, dz = (double) b.z - (double) a.z;
+    const BoxDev& bx = nb.box;
+    if (bx.periodic) {
+        if (bx.triclinic) {         // ReferenceForce::getDeltaRPeriodic order: c, b, a
+            double k = floor(dz*bx.recip[8] + 0.5);
+            dx -= k*(double) bx.cx; dy -= k*(double) bx.cy; dz -= k*bx.dcz;
+            k = floor(dy*bx.recip[4] + 0.5);
+            dx -= k*(double) bx.bx; dy -= k*bx.dby;
+            k = floor(dx*bx.recip[0] + 0.5);
+            dx -= k*bx.dax;
+        }
+        else {
+            dx -= bx.dax*rint(dx*bx.recip[0]); dy -= bx.dby*rint(dy*bx.recip[4]); dz -= bx.dcz*rint(dz*bx.recip[8]);
+        }
+    }
+    const double r2 = dx*dx + dy*dy + dz*dz;
+    const double invR = rsqrt(r2), invR2 = invR*invR, r = r2*invR;
+    const double qq = (double) a.w*(double) b.w;
+    double dEdR, e;
+    if (METHOD == B200MD_NB_PME) {
+        const double ar = (double) nb.alpha*r;
+        const double ec = erfc(ar), ex = exp(-ar*ar);
+        dEdR = qq*invR*invR2*(ec + 1.12837916709551257390*ar*ex);
+        e = qq*invR*ec;
+    }
+    else if (METHOD == B200MD_NB_NOCUTOFF) { dEdR = qq*invR*invR2; e = qq*invR; }
+    else { dEdR = qq*(invR*invR2 - 2.0*(double) nb.krf); e = qq*(invR + (double) nb.krf*r2 - (double) nb.crf); }
+    const double sig = (double) sa.x + (double) sb.x, eps = (double) sa.y*(double) sb.y;
+    const double s2 = sig*sig*invR2, s6 = s2*s2*s2;
+    double ljF = eps*s6*invR2*(12.0*s6 - 6.0), ljE = eps*s6*(s6 - 1.0);
+    if (SWITCH && r > (double) nb.switchDist) {
+        const double swInv = 1.0/((double) nb.cutoff - (double) nb.switchDist);
+        const double x = (r - (double) nb.switchDist)*swInv;
+        const double sw = 1.0 + x*x*x*(-10.0 + x*(15.0 - x*6.0));
+        const double dsw = x*x*(-30.0 + x*(60.0 - x*30.0))*swInv;
+        ljF = sw*ljF - ljE*dsw*invR;
+        ljE *= sw;
+    }
+    dEdR += ljF;
+    if (ENERGY) energyD += e + ljE;
+    const int ai = L.sorig[si], aj = L.sorig[sj];
+    const long long fx = __double2ll_rn(dx*dEdR*B200MD_FORCE_SCALE), fy = __double2ll_rn(dy*dEdR*B200MD_FORCE_SCALE), fz = __double2ll_rn(dz*dEdR*B200MD_FORCE_SCALE);
+    atomicAdd((unsigned long long*) &nb.force[ai], (unsigned long long) (-fx));
+    atomicAdd((unsigned long long*) &nb.force[ai + nb.npad], (unsigned long long) (-fy));
+    atomicAdd((unsigned long long*) &nb.force[ai + 2*nb.npad], (unsigned long long) (-fz));
+    atomicAdd((unsigned long long*) &nb.force[aj], (unsigned long long) fx);
+    atomicAdd((unsigned long long*) &nb.force[aj + nb.npad], (unsigned long long) fy);
+    atomicAdd((unsigned long long*) &nb.force[aj + 2*nb.npad], (unsigned long long) fz);
+}
+
+template <bool ENERGY, int METHOD, bool SHIFT, bool RATIONAL, bool SWITCH, bool CLOSE>
+__device__ __forceinline__ void pair_tiles(const NbDev& nb, const ListDev& L, float& energy, unsigned short* cq) {
     const int lane = threadIdx.x & 31;
     const int gwarp = (blockIdx.x*blockDim.x + threadIdx.x) >> 5;
     const int nwarps = (gridDim.x*blockDim.x) >> 5;
@@ -853,6 +916,9 @@ __device__ __forceinline__ void pair_tiles(const NbDev& nb, const ListDev& L, fl
     const float cutoff2 = nb.cutoff2;
     const float swInv = SWITCH ? 1.0f/(nb.cutoff - nb.switchDist) : 0.f;
     const int src = (lane + 1) & 31;
+    const float close2 = CLOSE ? nb.closeCut2 : 0.f;
+    const unsigned int ltMask = (1u << lane) - 1u;
+    double energyD = 0.0;
     // multi-GPU force decomposition: rank r owns the tiles of i-blocks with ib % world == r.  (Tile INDICES are handed out
     // by an atomic counter and differ between ranks; the i-block of a tile does not.)
     __shared__ int sbase;
@@ -895,13 +961,23 @@ __device__ __forceinline__ void pair_tiles(const NbDev& nb, const ListDev& L, fl
             pj.x = wrap_rel(pj.x, c.x, bx.dax, bx.recip[0]); pj.y = wrap_rel(pj.y, c.y, bx.dby, bx.recip[4]); pj.z = wrap_rel(pj.z, c.z, bx.dcz, bx.recip[8]);
         }
         float fix = 0.f, fiy = 0.f, fiz = 0.f, fjx = 0.f, fjy = 0.f, fjz = 0.f;
+        int qn = 0;
 #pragma unroll 4
         for (int k = 0; k < 32; k++) {
             float3 d = make_float3(pj.x-pi.x, pj.y-pi.y, pj.z-pi.z);
             if (!SHIFT && periodic) d = min_image(d, nb.box);
             const float r2raw = fmaf(d.z, d.z, fmaf(d.y, d.y, d.x*d.x));
-            const bool valid = (mask & 1u) && r2raw < cutoff2;
+            bool valid = (mask & 1u) && r2raw < cutoff2;
             mask >>= 1;
+            if (CLOSE) {
+                const bool isClose = valid && r2raw < close2;
+                const unsigned int cm = __ballot_sync(FULL, isClose);
+                if (cm) {           // warp-uniform; ~1 rotation in 8 at water density
+                    const int pos = qn + __popc(cm & ltMask);
+                    if (isClose && pos < CLOSE_QCAP) { cq[pos] = (unsigned short) (lane | (((lane + k) & 31) << 5)); valid = false; }
+                    qn = min(CLOSE_QCAP, qn + __popc(cm));
+                }
+            }
             const float r2 = valid ? r2raw : 1.0f;
             float y = rsqrt_approx(r2);
             y = y*fmaf(-0.5f*r2, y*y, 1.5f);             // Newton step: F ~ invR^3 needs a <1 ulp invR
@@ -958,6 +1034,14 @@ __device__ __forceinline__ void pair_tiles(const NbDev& nb, const ListDev& L, fl
             sej.x = __shfl_sync(FULL, sej.x, src); sej.y = __shfl_sync(FULL, sej.y, src);
             fjx = __shfl_sync(FULL, fjx, src); fjy = __shfl_sync(FULL, fjy, src); fjz = __shfl_sync(FULL, fjz, src);
         }
+        if (CLOSE && qn > 0) {
+            __syncwarp();
+            for (int e = lane; e < qn; e += 32) {
+                const int code = cq[e];
+                close_pair_double<ENERGY, METHOD, SWITCH>(nb, L, ib*32 + (code & 31), L.tileJ[t*32 + (code >> 5)], energyD);
+            }
+            __syncwarp();
+        }
         // after 32 rotations every lane holds its own j again
         const int ai = L.sorig[si];
         if (ai >= 0) {
@@ -972,17 +1056,26 @@ __device__ __forceinline__ void pair_tiles(const NbDev& nb, const ListDev& L, fl
             atomicAdd((unsigned long long*) &nb.force[aj + 2*nb.npad], (unsigned long long) float_to_fixed(fjz));
         }
     }
+    if (ENERGY && CLOSE && energyD != 0.0) atomicAdd(&nb.energy[EN_NB], energyD);
 }
 
 template <bool ENERGY, int METHOD, bool SHIFT, bool RATIONAL>
-__device__ __forceinline__ void pair_tiles_sw(const NbDev& nb, const ListDev& L, float& energy) {
-    if (nb.useSwitch) pair_tiles<ENERGY, METHOD, SHIFT, RATIONAL, true>(nb, L, energy);
-    else pair_tiles<ENERGY, METHOD, SHIFT, RATIONAL, false>(nb, L, energy);
+__device__ __forceinline__ void pair_tiles_sw(const NbDev& nb, const ListDev& L, float& energy, unsigned short* cq) {
+    if (nb.closeCut2 > 0.f) {
+        if (nb.useSwitch) pair_tiles<ENERGY, METHOD, SHIFT, false, true, true>(nb, L, energy, cq);
+        else pair_tiles<ENERGY, METHOD, SHIFT, false, false, true>(nb, L, energy, cq);
+    }
+    else {
+        if (nb.useSwitch) pair_tiles<ENERGY, METHOD, SHIFT, RATIONAL, true, false>(nb, L, energy, cq);
+        else pair_tiles<ENERGY, METHOD, SHIFT, RATIONAL, false, false>(nb, L, energy, cq);
+    }
 }
 
 template <bool ENERGY, int METHOD>
 __global__ void __launch_bounds__(256) k_pair(NbDev nb) {
     float energy = 0.f;
+    __shared__ unsigned short closeQ[8][CLOSE_QCAP];       // per-warp queue of close pairs: i lane | j slot << 5
+    unsigned short* cq = closeQ[threadIdx.x >> 5];
     const ListDev& L = nb.list[nb.counters[CT_CUR] & 1];
     const float maxHalf = __int_as_float(L.lc[LC_MAXHALF]);       // max block half extent recorded at list build
     const BoxDev& b = nb.box;
@@ -992,12 +1085,12 @@ __global__ void __launch_bounds__(256) k_pair(NbDev nb) {
     // (it cost 1e-4 relative on the 894-ion fixture); the exp-based erfc has a RELATIVE error, so it is the default.
     const bool rational = (METHOD == B200MD_NB_PME) && (nb.alpha*nb.alpha*nb.cutoff2 < PME_G_WMAX) && nb.useRational;
     if (shiftOK) {
-        if (rational) pair_tiles_sw<ENERGY, METHOD, true, true>(nb, L, energy);
-        else pair_tiles_sw<ENERGY, METHOD, true, false>(nb, L, energy);
+        if (rational) pair_tiles_sw<ENERGY, METHOD, true, true>(nb, L, energy, cq);
+        else pair_tiles_sw<ENERGY, METHOD, true, false>(nb, L, energy, cq);
     }
     else {
-        if (rational) pair_tiles_sw<ENERGY, METHOD, false, true>(nb, L, energy);
-        else pair_tiles_sw<ENERGY, METHOD, false, false>(nb, L, energy);
+        if (rational) pair_tiles_sw<ENERGY, METHOD, false, true>(nb, L, energy, cq);
+        else pair_tiles_sw<ENERGY, METHOD, false, false>(nb, L, energy, cq);
     }
     if (ENERGY) {
         for (int off = 16; off > 0; off >>= 1) energy += __shfl_xor_sync(FULL, energy, off);
