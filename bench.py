@@ -161,6 +161,22 @@ def main():
         comm = (rank, world, bytes(uid.numpy().tobytes()))
 
     d = load_workload(args.workload)
+    # N > 1: the SAME workload on ONE GPU, measured by rank 0 in this very run, so that a scaling efficiency can be formed on a
+    # like-for-like basis (the driver's own N=1 run uses the N=1 default workload, DHFR)
+    n1 = None
+    if world > 1:
+        if rank == 0:
+            e1 = Engine(d, device=local)
+            e1.set_integrator(systems.INT_LANGEVIN, args.dt, 300.0, 1.0, 7, 1e-5)
+            e1.step(300 + args.md_steps); e1.synchronize()
+            s1 = torch.cuda.ExternalStream(e1.stream(), device=local)
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record(s1); e1.step(2*args.md_steps); a1.record(s1); e1.synchronize()
+            ms1 = a0.elapsed_time(a1)/2
+            n1 = {"workload": args.workload, "n_gpus": 1, "value": args.dt*1e-3*args.md_steps*86400/(ms1*1e-3), "unit": "ns/day", "us_per_md_step": 1e3*ms1/args.md_steps,
+                  "note": "same workload, single-GPU engine, rank 0 of this run, %d MD steps device-timed" % (2*args.md_steps)}
+            e1.close()
+        dist.all_reduce(torch.zeros(1))
     eng = Engine(d, device=local, comm=comm)
     eng.set_integrator(systems.INT_LANGEVIN, args.dt, 300.0, 1.0, 7, 1e-5)
     stream = torch.cuda.ExternalStream(eng.stream(), device=local)
@@ -271,7 +287,10 @@ def main():
     line = {"metric": "ns/day", "value": nsday, "unit": "ns/day", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms/args.steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": DATA_NOTE.get(args.workload, "synthetic"),
             "config": {"workload": args.workload, "atoms": d.natoms, "md_steps_per_step": md, "dt_fs": args.dt*1e3, "integrator": "Langevin 300K 1/ps + SETTLE/SHAKE (HBonds)",
-                       "cutoff_nm": d.cutoff, "pme_grid": st["pme_grid"], "parallelism": ("replicated atoms: %d direct-space ranks + 1 PME rank, int64 force all-reduce" % (world-1)) if world > 1 else "single GPU",
+                       "cutoff_nm": d.cutoff, "pme_grid": st["pme_grid"], "parallelism": ("owner decomposition over %d ranks, peer-memory data plane: tiles by i-block, forces reduced to the owners and positions "
+                                       "published by the integrate kernel through NVLink stores, x-slab-decomposed PME FFT with the transposes fused into the FFT kernels' stores; "
+                                       "no NCCL call on the step path" % world) if world > 1 and os.environ.get("B200MD_MGPU", "p2p") != "nccl" else
+                                      (("replicated atoms: %d direct-space ranks + 1 PME rank, int64 force all-reduce (NCCL)" % (world-1)) if world > 1 else "single GPU"),
                        "l2": "256 MiB buffer written between timed iterations (inside the timed region)", "us_per_md_step": 1e3*ms/(args.steps*md)},
             "clocks": sampler.summary(),
             "e2e": {"value": e2e_nsday, "unit": "ns/day", "h2d_bytes_per_step": 2*nbytes, "d2h_bytes_per_step": 2*nbytes + 8,
@@ -285,6 +304,9 @@ def main():
                          "fp32_tflops_useful_pairs": st["pairs_in_cutoff"]*60.0/(pair_ms*1e-3)/1e12,
                          "note": "compute (FP32/SFU) bound kernel: arithmetic intensity ~%.0f flop/B; see DESIGN.md" % (flops/alg_bytes)},
             "phases_us": phases, "list_builds_in_timed_region": int(st1["list_builds"] - st0["list_builds"])}
+    if n1 is not None:
+        line["single_gpu_same_workload"] = n1
+        line["speedup_vs_single_gpu_same_workload"] = nsday/n1["value"]
     if not args.no_cpu_baseline:
         try:
             from oracle import omm

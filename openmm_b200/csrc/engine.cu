@@ -14,11 +14,16 @@
 static std::string g_create_error;
 
 template <class T> struct DevBuf {
-    T* p = nullptr; size_t n = 0;
-    void alloc(size_t count) { free(); n = count; if (count) CUDA_CHECK(cudaMalloc(&p, count*sizeof(T))); }
+    T* p = nullptr; size_t n = 0; bool owned = true;
+    // attach: the buffer lives inside the multi-GPU window (peers store into it); alloc() then only checks the size
+    void attach(void* ptr, size_t count) { free(); p = (T*) ptr; n = count; owned = false; }
+    void alloc(size_t count) {
+        if (!owned) { if (count > n) throw std::runtime_error("window buffer too small"); return; }
+        free(); n = count; if (count) CUDA_CHECK(cudaMalloc(&p, count*sizeof(T)));
+    }
     void upload(const std::vector<T>& v) { if (v.size() > n) alloc(v.size()); if (!v.empty()) CUDA_CHECK(cudaMemcpy(p, v.data(), v.size()*sizeof(T), cudaMemcpyHostToDevice)); }
     void zero() { if (n) CUDA_CHECK(cudaMemset(p, 0, n*sizeof(T))); }
-    void free() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    void free() { if (p && owned) cudaFree(p); p = nullptr; n = 0; owned = true; }
     ~DevBuf() { free(); }
 };
 
@@ -30,6 +35,7 @@ struct NcclApi {
     int (*GetUniqueId)(void*) = nullptr;
     int (*CommInitRank)(void**, int, NcclUid, int) = nullptr;
     int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
     int (*CommDestroy)(void*) = nullptr;
     const char* (*GetErrorString)(int) = nullptr;
     bool load(std::string& err) {
@@ -40,6 +46,7 @@ struct NcclApi {
         GetUniqueId = (decltype(GetUniqueId)) dlsym(lib, "ncclGetUniqueId");
         CommInitRank = (decltype(CommInitRank)) dlsym(lib, "ncclCommInitRank");
         AllReduce = (decltype(AllReduce)) dlsym(lib, "ncclAllReduce");
+        AllGather = (decltype(AllGather)) dlsym(lib, "ncclAllGather");
         CommDestroy = (decltype(CommDestroy)) dlsym(lib, "ncclCommDestroy");
         GetErrorString = (decltype(GetErrorString)) dlsym(lib, "ncclGetErrorString");
         if (!GetUniqueId || !CommInitRank || !AllReduce) { err = "libnccl lacks required symbols"; return false; }
@@ -47,7 +54,7 @@ struct NcclApi {
     }
 };
 static NcclApi g_nccl;
-enum { NCCL_INT64 = 4, NCCL_FLOAT32 = 7, NCCL_FLOAT64 = 8, NCCL_SUM = 0 };
+enum { NCCL_INT8 = 0, NCCL_INT64 = 4, NCCL_FLOAT32 = 7, NCCL_FLOAT64 = 8, NCCL_SUM = 0 };
 
 struct b200md_ctx {
     int device = 0;
@@ -78,6 +85,7 @@ struct b200md_ctx {
     std::vector<unsigned char> bondGroup, angGroup, torGroup;       // force group of every bonded element (default 0)
     std::vector<int> conI, conJ; std::vector<double> conD;
     int cmFreq = 0;
+    std::vector<int4> hUnitAtoms;        // host copy of the integration units (ownership cuts of the multi-GPU data plane)
     double boxA[3] = {0, 0, 0}, boxB[3] = {0, 0, 0}, boxC[3] = {0, 0, 0};
     bool haveBox = false;
     bool haveOrigin = false;
@@ -85,6 +93,7 @@ struct b200md_ctx {
     // ---- device state ----
     DevBuf<float4> posq, velm, sposq[2], swrap[2], refPos, atomShift, blockCenter[2], blockHalf[2], superCenter[2], superHalf[2];
     DevBuf<float2> sigeps, ssigeps[2];
+    DevBuf<double> chargeD; DevBuf<double2> sigepsD;
     DevBuf<long long> force;
     DevBuf<double> energy, cmScratch;
     DevBuf<int> molStart, molAtoms, cellOffset, sorig[2], sortedOf, cellRank, cellCount, cellFill, atomCell, tmpSorted, tileI[2], tileJ[2], tileMask[2], listCounters, counters, exclStart, exclList;
@@ -123,6 +132,14 @@ struct b200md_ctx {
     // ---- multi-GPU ----
     void* comm = nullptr;
     int rank = 0, world = 1;
+    // peer-memory data plane (comm.cu): one window per rank, mapped by every other rank with CUDA IPC
+    bool p2p = false;                    // world > 1 and B200MD_MGPU != nccl
+    CommDev cd{};                        // world == 1 unless p2p
+    char* window = nullptr; size_t windowBytes = 0;
+    void* peerMapped[B200MD_MAX_RANKS] = {nullptr};
+    DevBuf<unsigned long long> commCounters;   // [0] epoch, [1] posNeed
+    DevBuf<unsigned int> commDone;             // [CH_COUNT]
+    bool velStale = false;               // p2p: the velocities of foreign atoms are behind (only owners integrate)
     std::vector<float4> hbuf4;
     std::vector<int> hoffset;
     std::vector<long long> hforce;
@@ -133,6 +150,8 @@ struct b200md_ctx {
 
 static void require(bool cond, const char* msg) { if (!cond) throw std::runtime_error(msg); }
 static void check_flags(b200md_ctx* c);
+static void sync_velocities(b200md_ctx* c);
+static void sync_positions(b200md_ctx* c);
 
 extern "C" const char* b200md_version(void) { return "b200md 0.1 (sm_100a)"; }
 extern "C" const char* b200md_last_error(const b200md_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
@@ -185,6 +204,7 @@ extern "C" void b200md_destroy(b200md_ctx* ctx) {
     cudaDeviceSynchronize();
     if (ctx->stepGraph) cudaGraphExecDestroy(ctx->stepGraph);
     if (ctx->multiGraph) cudaGraphExecDestroy(ctx->multiGraph);
+    for (int q = 0; q < B200MD_MAX_RANKS; q++) if (ctx->peerMapped[q]) cudaIpcCloseMemHandle(ctx->peerMapped[q]);
     if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
@@ -194,7 +214,9 @@ extern "C" void b200md_destroy(b200md_ctx* ctx) {
     if (ctx->streamList) cudaStreamDestroy(ctx->streamList);
     if (ctx->evListFork) cudaEventDestroy(ctx->evListFork);
     if (ctx->evListJoin) cudaEventDestroy(ctx->evListJoin);
+    char* window = ctx->window;
     delete ctx;
+    if (window) cudaFree(window);
 }
 
 extern "C" int b200md_set_masses(b200md_ctx* ctx, const double* mass) {
@@ -268,6 +290,7 @@ extern "C" int b200md_remove_cm_motion(b200md_ctx* ctx) {
     API_BEGIN(ctx)
     ctx->stepStateValid = false;
     require(ctx->finalized, "remove_cm_motion before finalize");
+    sync_velocities(ctx);
     launch_remove_cm(ctx->nb, ctx->cmScratch.p, ctx->stream);
     ctx->kernelLaunches += 2;
     API_END(ctx)
@@ -379,6 +402,12 @@ static void upload_params(b200md_ctx* c) {
     std::vector<float2> se(c->npad, make_float2(0.f, 0.f));
     for (int i = 0; i < N; i++) se[i] = make_float2((float) (0.5*c->sigma[i]), (float) (2.0*std::sqrt(c->epsilon[i])));
     c->sigeps.upload(se);
+    {
+        std::vector<double> qd(c->npad, 0.0); std::vector<double2> sd(c->npad, make_double2(0.0, 0.0));
+        for (int i = 0; i < N; i++) { qd[i] = c->charge[i]*sk; sd[i] = make_double2(0.5*c->sigma[i], 2.0*std::sqrt(c->epsilon[i])); }
+        c->chargeD.upload(qd); c->sigepsD.upload(sd);
+        c->nb.chargeD = c->chargeD.p; c->nb.sigepsD = c->sigepsD.p;
+    }
     // charges live in posq.w; keep positions
     std::vector<float4> p(c->npad);
     CUDA_CHECK(cudaMemcpy(p.data(), c->posq.p, sizeof(float4)*c->npad, cudaMemcpyDeviceToHost));
@@ -469,6 +498,7 @@ static void build_units(b200md_ctx* c) {
     std::string err;
     if (!classify_units(c->natoms, c->mass.data(), c->conI, c->conJ, c->conD, ua2, ut2, up2, err)) throw std::runtime_error("B200 platform: " + err);
     c->unitAtoms.upload(ua2); c->unitType.upload(ut2); c->unitParams.upload(up2);
+    c->hUnitAtoms = ua2;
     c->units.nunits = (int) ua2.size();
     c->units.unitAtoms = c->unitAtoms.p; c->units.unitType = c->unitType.p; c->units.unitParams = c->unitParams.p;
 }
@@ -547,6 +577,100 @@ static void setup_pme(b200md_ctx* c, int nx, int ny, int nz, double alpha) {
 }
 
 
+// ---------------------------------------------------------------- multi-GPU window (peer-memory data plane, comm.cu)
+static size_t align_up(size_t x, size_t a) { return (x + a - 1)/a*a; }
+
+// Lay the window out, allocate it, exchange the IPC handles (through the NCCL communicator that b200md_comm_init made: the
+// only use of NCCL besides the rare energy reduction) and map every peer.  Called at the top of b200md_finalize; the state
+// arrays that peers store into (posq, velm, force, the potential grid) are then carved out of the window.
+static void setup_window(b200md_ctx* c) {
+    const int P = c->world, NP = c->npad;
+    require(P <= B200MD_MAX_RANKS, "at most 8 ranks");
+    CommDev& cd = c->cd;
+    cd = CommDev{};
+    cd.rank = c->rank; cd.world = P;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { const size_t o = off; off = align_up(off + bytes, 256); return o; };
+    cd.offFlags = take((size_t) CH_COUNT*B200MD_MAX_RANKS*sizeof(unsigned long long));
+    cd.offCm = take((size_t) B200MD_MAX_RANKS*12*sizeof(double));
+    cd.offPosq = take((size_t) NP*sizeof(float4));
+    cd.offVelm = take((size_t) NP*sizeof(float4));
+    cd.offForce = take((size_t) 3*NP*sizeof(long long));
+    cd.offFinbox = take((size_t) P*3*NP*sizeof(long long));
+    const bool pme = c->haveNb && c->nbdesc.method == B200MD_NB_PME;
+    if (pme) {
+        const int nx = c->nbdesc.grid[0], ny = c->nbdesc.grid[1], nz = c->nbdesc.grid[2], nzc = nz/2 + 1;
+        require(nx >= P, "PME grid has fewer x planes than ranks");
+        const int plane = ny*nzc;
+        cd.maxPlanes = 0;
+        for (int q = 0; q <= P; q++) cd.xLo[q] = (int) ((long long) q*nx/P);
+        for (int q = 0; q < P; q++) cd.maxPlanes = std::max(cd.maxPlanes, cd.xLo[q+1] - cd.xLo[q]);
+        cd.lineChunk = (int) align_up((size_t) (plane + P - 1)/P, 16);
+        cd.offGridInbox = take((size_t) P*cd.maxPlanes*ny*nz*sizeof(long long));
+        cd.offLineBuf = take((size_t) nx*cd.lineChunk*sizeof(real2));
+        cd.offPlaneBuf = take((size_t) cd.maxPlanes*plane*sizeof(real2));
+        cd.offGrid = take((size_t) nx*ny*nz*sizeof(real));
+    }
+    c->windowBytes = off;
+    CUDA_CHECK(cudaMalloc(&c->window, off));
+    CUDA_CHECK(cudaMemset(c->window, 0, off));
+    CUDA_CHECK(cudaDeviceSynchronize());            // nobody can map this window before the handle exchange below: it is zero when they do
+    c->posq.attach(c->window + cd.offPosq, NP);
+    c->velm.attach(c->window + cd.offVelm, NP);
+    c->force.attach(c->window + cd.offForce, (size_t) 3*NP);
+    if (pme) c->grid.attach(c->window + cd.offGrid, (size_t) c->nbdesc.grid[0]*c->nbdesc.grid[1]*c->nbdesc.grid[2]);
+    // ---- handle exchange ----
+    require(g_nccl.AllGather != nullptr, "libnccl lacks ncclAllGather");
+    cudaIpcMemHandle_t mine;
+    CUDA_CHECK(cudaIpcGetMemHandle(&mine, c->window));
+    DevBuf<char> send, recv;
+    send.alloc(sizeof(mine)); recv.alloc(sizeof(mine)*P);
+    CUDA_CHECK(cudaMemcpy(send.p, &mine, sizeof(mine), cudaMemcpyHostToDevice));
+    if (g_nccl.AllGather(send.p, recv.p, sizeof(mine), NCCL_INT8, c->comm, c->stream) != 0) throw std::runtime_error("ncclAllGather(ipc handles) failed");
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    std::vector<cudaIpcMemHandle_t> all(P);
+    CUDA_CHECK(cudaMemcpy(all.data(), recv.p, sizeof(mine)*P, cudaMemcpyDeviceToHost));
+    for (int q = 0; q < P; q++) {
+        if (q == c->rank) { cd.peer[q] = c->window; continue; }
+        cudaError_t e = cudaIpcOpenMemHandle(&c->peerMapped[q], all[q], cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess)
+            throw std::runtime_error(std::string("cudaIpcOpenMemHandle(rank ") + std::to_string(q) + "): " + cudaGetErrorString(e) +
+                                     " -- the peer-memory data plane needs CUDA IPC + P2P between the GPUs (B200MD_MGPU=nccl selects the NCCL all-reduce scheme)");
+        cd.peer[q] = (char*) c->peerMapped[q];
+    }
+    c->commCounters.alloc(2); c->commCounters.zero();
+    c->commDone.alloc(CH_COUNT); c->commDone.zero();
+    cd.epoch = c->commCounters.p; cd.posNeed = c->commCounters.p + 1; cd.done = c->commDone.p;
+}
+
+// Ownership: rank q owns the integration units [unitLo[q], unitLo[q+1]) and with them the atoms [atomLo[q], atomLo[q+1]) --
+// cuts are only made where the units before the cut hold exactly the atoms below some index (always the case for the usual
+// molecule-by-molecule atom order).
+static void setup_ownership(b200md_ctx* c) {
+    CommDev& cd = c->cd;
+    const int P = cd.world, N = c->natoms, U = (int) c->hUnitAtoms.size();
+    std::vector<int> prefMax(U + 1, -1), sufMin(U + 1, N);
+    auto lohi = [&](int u, int& lo, int& hi) {
+        const int4 a = c->hUnitAtoms[u]; const int v[4] = {a.x, a.y, a.z, a.w};
+        lo = N; hi = -1;
+        for (int k = 0; k < 4; k++) if (v[k] >= 0) { lo = std::min(lo, v[k]); hi = std::max(hi, v[k]); }
+    };
+    for (int u = 0; u < U; u++) { int lo, hi; lohi(u, lo, hi); prefMax[u+1] = std::max(prefMax[u], hi); }
+    for (int u = U - 1; u >= 0; u--) { int lo, hi; lohi(u, lo, hi); sufMin[u] = std::min(sufMin[u+1], lo); }
+    cd.unitLo[0] = 0; cd.atomLo[0] = 0; cd.unitLo[P] = U; cd.atomLo[P] = N;
+    int u = 1;
+    for (int q = 1; q < P; q++) {
+        const long long target = (long long) q*N/P;
+        // first valid cut at or after the target atom
+        while (u < U && !(prefMax[u] < sufMin[u] && sufMin[u] >= target)) u++;
+        require(u < U, "multi-GPU: cannot cut the atom range at integration-unit boundaries (molecules are not contiguous in atom order)");
+        cd.unitLo[q] = u; cd.atomLo[q] = sufMin[u];
+        u++;
+    }
+    for (int q = 0; q < P; q++) require(cd.atomLo[q+1] > cd.atomLo[q] && cd.unitLo[q+1] > cd.unitLo[q], "multi-GPU: a rank would own no atoms");
+    cd.errFlag = c->counters.p + CT_OVERFLOW;
+}
+
 // ---------------------------------------------------------------- tile pools
 // Capacity of ONE of the TILE_REGIONS slot pools.  The first guess assumes a homogeneous density; prepare_list() measures
 // the pools after every list build that follows a change of the state from outside and grows them (slabs, droplets,
@@ -594,6 +718,9 @@ extern "C" int b200md_finalize(b200md_ctx* ctx) {
     nb.natoms = N; nb.npad = NP; nb.nblocks = c->nblocks;
     nb.method = c->nbdesc.method;
     nb.rank = c->rank; nb.world = c->world;
+    c->cd = CommDev{}; c->cd.world = 1;
+    c->p2p = c->world > 1 && c->comm && !(getenv("B200MD_MGPU") && std::string(getenv("B200MD_MGPU")) == "nccl");
+    if (c->p2p) setup_window(c);
     nb.useRational = getenv("B200MD_PAIR_RATIONAL") ? atoi(getenv("B200MD_PAIR_RATIONAL")) : 0;
     nb.pairDynamic = getenv("B200MD_PAIR_DYNAMIC") ? atoi(getenv("B200MD_PAIR_DYNAMIC")) : 0;
     { const double cc = getenv("B200MD_CLOSE_NM") ? atof(getenv("B200MD_CLOSE_NM")) : 0.32; nb.closeCut2 = (float) (cc*cc); }
@@ -684,6 +811,13 @@ extern "C" int b200md_finalize(b200md_ctx* ctx) {
     }
     upload_params(c);
     build_units(c);
+    if (c->p2p) {
+        setup_ownership(c);
+        if (nb.method == B200MD_NB_PME) {
+            PmeDev probe{}; probe.nx = c->nbdesc.grid[0]; probe.ny = c->nbdesc.grid[1]; probe.nz = c->nbdesc.grid[2]; probe.nzc = probe.nz/2 + 1;
+            require(fft_slab_path(probe), "multi-GPU: the PME grid plane does not fit the slab FFT kernels (B200MD_MGPU=nccl selects the NCCL scheme)");
+        }
+    }
     // ---- molecules (connected components of bonds, angles, torsions, constraints and exceptions) for the wrap at list
     // builds; off for non-periodic systems and with more than one rank (every rank would have to wrap in the same step,
     // and the reciprocal-space rank builds no list) ----
@@ -764,6 +898,21 @@ extern "C" int b200md_update_bonded_params(b200md_ctx* ctx, int kind, int n, con
 }
 
 // ---------------------------------------------------------------- state
+// Multi-GPU (peer-memory data plane): only the owner integrates an atom.  Positions reach every rank with the step itself;
+// velocities stay with the owner until somebody reads them from the host side.
+static void sync_positions(b200md_ctx* c) { if (c->p2p && c->finalized) launch_pos_wait(c->nb, c->cd, c->stream); }
+static void sync_velocities(b200md_ctx* c) {
+    if (!c->p2p || !c->velStale) return;
+    launch_vel_push(c->nb, c->cd, c->stream);
+    c->kernelLaunches += 2;
+    c->velStale = false;
+}
+static void host_set_state(b200md_ctx* c) {       // the host wrote the full state on every rank: nothing to wait for
+    if (!c->p2p) return;
+    const unsigned long long zero = 0ull;
+    CUDA_CHECK(cudaMemcpyAsync(c->cd.posNeed, &zero, sizeof(zero), cudaMemcpyHostToDevice, c->stream));
+}
+
 extern "C" int b200md_set_positions(b200md_ctx* ctx, const double* x) {
     API_BEGIN(ctx)
     ctx->stepStateValid = false;
@@ -782,7 +931,9 @@ extern "C" int b200md_set_positions(b200md_ctx* ctx, const double* x) {
         ctx->haveOrigin = true;
         invalidate_graph(ctx);
     }
+    sync_positions(ctx);          // the peers' stores of the last step must not land after this upload
     CUDA_CHECK(cudaMemcpyAsync(ctx->posq.p, ctx->hbuf4.data(), sizeof(float4)*ctx->npad, cudaMemcpyHostToDevice, ctx->stream));
+    host_set_state(ctx);
     CUDA_CHECK(cudaMemsetAsync(ctx->cellOffset.p, 0, sizeof(int)*3*ctx->npad, ctx->stream));
     const int one = 1;
     CUDA_CHECK(cudaMemcpyAsync(&ctx->counters.p[CT_REBUILD], &one, sizeof(int), cudaMemcpyHostToDevice, ctx->stream)); ctx->listDirty = true;
@@ -792,6 +943,7 @@ extern "C" int b200md_set_positions(b200md_ctx* ctx, const double* x) {
 extern "C" int b200md_get_positions(b200md_ctx* ctx, double* x) {
     API_BEGIN(ctx)
     ctx->hbuf4.resize(ctx->npad);
+    sync_positions(ctx);
     CUDA_CHECK(cudaMemcpyAsync(ctx->hbuf4.data(), ctx->posq.p, sizeof(float4)*ctx->npad, cudaMemcpyDeviceToHost, ctx->stream));
     check_flags(ctx);
     for (int i = 0; i < ctx->natoms; i++) { x[3*i] = ctx->hbuf4[i].x; x[3*i+1] = ctx->hbuf4[i].y; x[3*i+2] = ctx->hbuf4[i].z; }
@@ -820,12 +972,14 @@ extern "C" int b200md_set_velocities(b200md_ctx* ctx, const double* v) {
     for (int i = 0; i < ctx->natoms; i++)
         ctx->hbuf4[i] = make_float4((float) v[3*i], (float) v[3*i+1], (float) v[3*i+2], ctx->mass[i] > 0 ? (float) (1.0/ctx->mass[i]) : 0.f);
     CUDA_CHECK(cudaMemcpyAsync(ctx->velm.p, ctx->hbuf4.data(), sizeof(float4)*ctx->npad, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->velStale = false;
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     API_END(ctx)
 }
 extern "C" int b200md_get_velocities(b200md_ctx* ctx, double* v) {
     API_BEGIN(ctx)
     ctx->hbuf4.resize(ctx->npad);
+    sync_velocities(ctx);
     CUDA_CHECK(cudaMemcpyAsync(ctx->hbuf4.data(), ctx->velm.p, sizeof(float4)*ctx->npad, cudaMemcpyDeviceToHost, ctx->stream));
     check_flags(ctx);
     for (int i = 0; i < ctx->natoms; i++) { v[3*i] = ctx->hbuf4[i].x; v[3*i+1] = ctx->hbuf4[i].y; v[3*i+2] = ctx->hbuf4[i].z; }
@@ -861,6 +1015,7 @@ extern "C" int64_t b200md_checkpoint_save(b200md_ctx* ctx, void* buf, int64_t ca
     try {
         CUDA_CHECK(cudaSetDevice(ctx->device));
         require(cap >= need, "checkpoint buffer too small");
+        sync_positions(ctx); sync_velocities(ctx);
         CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
         CkptHeader h; memset(&h, 0, sizeof(h));
         memcpy(h.magic, "B200MDCK", 8); h.version = 2; h.natoms = ctx->natoms; h.time = ctx->time; h.stepCount = ctx->stepCount;
@@ -882,6 +1037,7 @@ extern "C" int b200md_checkpoint_load(b200md_ctx* ctx, const void* buf, int64_t 
     require(size >= need, "checkpoint blob too small");
     CkptHeader h; memcpy(&h, buf, sizeof(h));
     require(memcmp(h.magic, "B200MDCK", 8) == 0 && h.version == 2 && h.natoms == ctx->natoms, "checkpoint blob does not match this context");
+    sync_positions(ctx);
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     ctx->time = h.time; ctx->stepCount = h.stepCount;
     for (int i = 0; i < 3; i++) { ctx->boxA[i] = h.box[i]; ctx->boxB[i] = h.box[3+i]; ctx->boxC[i] = h.box[6+i]; }
@@ -890,6 +1046,7 @@ extern "C" int b200md_checkpoint_load(b200md_ctx* ctx, const void* buf, int64_t 
     CUDA_CHECK(cudaMemcpy(ctx->velm.p, p, sizeof(float4)*ctx->npad, cudaMemcpyHostToDevice)); p += sizeof(float4)*ctx->npad;
     CUDA_CHECK(cudaMemcpy(ctx->cellOffset.p, p, sizeof(int)*3*ctx->npad, cudaMemcpyHostToDevice));
     CUDA_CHECK(cudaMemcpy(ctx->stepCounter.p, &h.rngStep, sizeof(unsigned long long), cudaMemcpyHostToDevice));
+    host_set_state(ctx); ctx->velStale = false;
     if (ctx->haveBox) apply_box(ctx);
     const int one = 1;
     CUDA_CHECK(cudaMemcpy(&ctx->counters.p[CT_REBUILD], &one, sizeof(int), cudaMemcpyHostToDevice)); ctx->listDirty = true;
@@ -899,7 +1056,7 @@ extern "C" int b200md_checkpoint_load(b200md_ctx* ctx, const void* buf, int64_t 
 // Multi-GPU role split (replicated atoms): with PME and world > 1 the LAST rank computes reciprocal space for all atoms and
 // nothing else; the other world-1 ranks share the direct-space tiles (by i-block: list construction AND tile kernel) and the
 // bonded terms.  Returns the rank's view of the sharding.
-static bool role_split(const b200md_ctx* c) { return c->world > 1 && c->comm && c->nb.method == B200MD_NB_PME && c->haveNb; }
+static bool role_split(const b200md_ctx* c) { return c->world > 1 && c->comm && !c->p2p && c->nb.method == B200MD_NB_PME && c->haveNb; }
 static NbDev role_nb(const b200md_ctx* c) {
     NbDev nb = c->nb;
     if (role_split(c)) {
@@ -934,20 +1091,23 @@ static int enqueue_forces(b200md_ctx* c, int terms, bool energy, bool forcesAlre
     // direct space (list check / rebuild, tile kernel, bonded terms) are independent until the integrator: fork them onto
     // two streams (also inside the captured step graph).  Both accumulate into the same fixed-point force buffer, so the
     // overlap cannot change the result.  Single-GPU only: with NCCL the collectives of one communicator stay on one stream.
-    const bool fork = direct && recip && c->overlapPme && !(c->world > 1 && c->comm);
+    const bool p2p = c->p2p;
+    const bool fork = direct && recip && c->overlapPme && !(c->world > 1 && c->comm && !p2p);
     cudaStream_t sp = fork ? c->streamPme : s;
+    if (p2p && !direct) { launch_pos_wait(c->nb, c->cd, s); launches++; }       // nobody else on this stream waits for the owners' position stores
     if (fork) {
         CUDA_CHECK(cudaEventRecord(c->evFork, s));
         CUDA_CHECK(cudaStreamWaitEvent(sp, c->evFork, 0));
     }
     if (recip) {
-        launch_pme_spread(c->nb, c->pme, sp); launches++;
-        if (c->world > 1 && c->comm && !split) {
+        launch_pme_spread(c->nb, c->pme, c->cd, sp); launches++;
+        if (p2p) { launch_grid_push(c->pme, c->cd, sp); launches++; }
+        else if (c->world > 1 && c->comm && !split) {
             int rc = g_nccl.AllReduce(c->gridFixed.p, c->gridFixed.p, (size_t) c->pme.nx*c->pme.ny*c->pme.nz, NCCL_INT64, NCCL_SUM, c->comm, sp);
             if (rc != 0) throw std::runtime_error("ncclAllReduce(grid) failed");
         }
-        launch_pme_fft_conv(c->nb, c->pme, energy && (split || c->rank == 0), sp); launches += pme_fft_launch_count(c->pme);
-        launch_pme_gather(c->nb, c->pme, sp); launches++;
+        launch_pme_fft_conv(c->nb, c->pme, c->cd, energy && (split || p2p || c->rank == 0), sp); launches += pme_fft_launch_count(c->pme);
+        launch_pme_gather(c->nb, c->pme, c->cd, sp); launches++;
     }
     if (fork) CUDA_CHECK(cudaEventRecord(c->evJoin, sp));
     bool joinList = false;
@@ -978,7 +1138,7 @@ static int enqueue_forces(b200md_ctx* c, int terms, bool energy, bool forcesAlre
             c->nb.condHandle = (unsigned long long) h;
             c->nb.condAsync = async ? (unsigned long long) ha : 0ull;
             c->nb.softPad2 = async ? c->softPad2 : 3e38f;
-            launch_check_displacement(c->nb, s); launches++;
+            launch_check_displacement(c->nb, c->cd, s); launches++;
             NbDev nbBody = c->nb;
             cudaGraph_t tmp;
             if (!spec) {
@@ -1019,7 +1179,7 @@ static int enqueue_forces(b200md_ctx* c, int terms, bool energy, bool forcesAlre
         }
         else {
             c->nb.condHandle = 0ull;
-            launch_check_displacement(c->nb, s); launches++;
+            launch_check_displacement(c->nb, c->cd, s); launches++;
             launch_list_build(c->nb, s); launches += list_build_launch_count();
         }
     }
@@ -1030,8 +1190,15 @@ static int enqueue_forces(b200md_ctx* c, int terms, bool energy, bool forcesAlre
     if (bterms && nbonded > 0 && !(split && c->rank == pmeRank)) { BondedDev bd = c->bd; bd.groupMask = groupMask; launch_bonded(c->nb, bd, bterms, energy, s); launches++; }
     if (fork) CUDA_CHECK(cudaStreamWaitEvent(s, c->evJoin, 0));
     if (joinList) CUDA_CHECK(cudaStreamWaitEvent(s, c->evListJoin, 0));
+    if (p2p) {
+        // partial forces of the atoms this rank does not own -> the owners' inboxes; in the step path k_integrate totals them,
+        // here (energies, getState) the owners total and broadcast so that every rank ends up with every force
+        launch_force_push(c->nb, c->cd, s); launches++;
+        if (!inStep) { launch_force_total(c->nb, c->cd, s); launches += 2; }
+    }
     if (c->world > 1 && c->comm) {
-        int rc = g_nccl.AllReduce(c->force.p, c->force.p, (size_t) 3*c->npad, NCCL_INT64, NCCL_SUM, c->comm, s);
+        int rc = 0;
+        if (!p2p) rc = g_nccl.AllReduce(c->force.p, c->force.p, (size_t) 3*c->npad, NCCL_INT64, NCCL_SUM, c->comm, s);
         if (rc != 0) throw std::runtime_error("ncclAllReduce(force) failed");
         if (energy) {
             rc = g_nccl.AllReduce(c->energy.p, c->energy.p, B200MD_NUM_ENERGY, NCCL_FLOAT64, NCCL_SUM, c->comm, s);
@@ -1051,6 +1218,7 @@ static void check_flags(b200md_ctx* c) {
     CUDA_CHECK(cudaMemcpyAsync(h, c->counters.p, sizeof(int)*8, cudaMemcpyDeviceToHost, c->stream));
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
     if (h[CT_OVERFLOW] == 2) throw std::runtime_error("B200 platform: neighbour-list construction timed out at a grid barrier (k_list_prep)");
+    if (h[CT_OVERFLOW] == 3) throw std::runtime_error("B200 platform: multi-GPU exchange timed out waiting for a peer rank (every rank must issue the same sequence of calls)");
     if (h[CT_OVERFLOW]) throw std::runtime_error("B200 platform: neighbour-list tile capacity exceeded (" + std::to_string(c->nb.maxTiles) + " tiles) during the preceding steps; the trajectory since the last state read is invalid");
 }
 
@@ -1065,7 +1233,7 @@ static void prepare_list(b200md_ctx* c) {
     if (c->pmeOnly || (role_split(c) && c->rank == c->world - 1)) { c->listDirty = false; return; }    // keeps no list
     for (int attempt = 0; attempt < 8; attempt++) {
         const NbDev nb = role_nb(c);
-        launch_check_displacement(nb, c->stream);
+        launch_check_displacement(nb, c->cd, c->stream);
         launch_list_build(nb, c->stream, 0);
         c->kernelLaunches += 1 + list_build_launch_count();
         int h[16], lc[2*LC_STRIDE];
@@ -1158,7 +1326,7 @@ static int enqueue_step(b200md_ctx* c) {
     in.cmEveryStep = (c->cmFreq == 1) ? 1 : 0;
     in.cmScratch = c->cmScratch.p;
     in.blocksDone = c->blocksDone.p;
-    launch_integrate(c->nb, c->units, in, c->stream); launches += 1;
+    launch_integrate(c->nb, c->units, in, c->cd, c->stream); launches += 1;
     return launches;
 }
 
@@ -1166,8 +1334,9 @@ extern "C" int b200md_integrate_only(b200md_ctx* ctx) {
     API_BEGIN(ctx)
     ctx->stepStateValid = false;
     require(ctx->finalized && ctx->haveIntegrator, "integrate before finalize / set_integrator");
-    launch_integrate(ctx->nb, ctx->units, ctx->integ, ctx->stream);
+    launch_integrate(ctx->nb, ctx->units, ctx->integ, ctx->cd, ctx->stream);
     ctx->kernelLaunches += 2;
+    ctx->velStale = ctx->p2p;
     ctx->time += ctx->dt; ctx->stepCount++;
     CUDA_CHECK(cudaGetLastError());
     API_END(ctx)
@@ -1212,12 +1381,13 @@ extern "C" int b200md_step(b200md_ctx* ctx, int nsteps) {
         if (c->cmFreq == 1) {
             IntegDev in = c->integ;
             in.cmScratch = c->cmScratch.p;
-            launch_cm_prime(c->nb, in, c->stream);
+            sync_velocities(c);
+            launch_cm_prime(c->nb, in, c->cd, c->stream);
         }
         c->stepStateValid = true;
     }
     while (remaining > 0) {
-        if (c->cmFreq > 1 && c->stepCount % c->cmFreq == 0) { launch_remove_cm(c->nb, c->cmScratch.p, c->stream); c->kernelLaunches += 2; }
+        if (c->cmFreq > 1 && c->stepCount % c->cmFreq == 0) { sync_velocities(c); launch_remove_cm(c->nb, c->cmScratch.p, c->stream); c->kernelLaunches += 2; }
         int done = 1;
         if (c->useGraph) {
             if (!c->graphValid) {
@@ -1239,6 +1409,7 @@ extern "C" int b200md_step(b200md_ctx* ctx, int nsteps) {
         }
         else
             c->kernelLaunches += enqueue_step(c);
+        c->velStale = c->p2p;
         c->forceEvals += done;
         c->stepCount += done;
         c->time += c->dt*done;
@@ -1252,6 +1423,7 @@ extern "C" int b200md_kinetic_energy(b200md_ctx* ctx, double* ke) {
     API_BEGIN(ctx)
     require(ctx->finalized, "kinetic_energy before finalize");
     const float shift = (ctx->haveIntegrator && ctx->integ.kind != B200MD_INT_LANGEVIN_MIDDLE) ? 0.5f*ctx->integ.dt : 0.f;
+    sync_positions(ctx); sync_velocities(ctx);
     CUDA_CHECK(cudaMemsetAsync(ctx->energy.p + EN_KE, 0, sizeof(double), ctx->stream));
     launch_kinetic_energy(ctx->nb, ctx->units, ctx->integ, shift, ctx->stream);
     ctx->kernelLaunches++;
@@ -1261,6 +1433,7 @@ extern "C" int b200md_kinetic_energy(b200md_ctx* ctx, double* ke) {
 }
 extern "C" int b200md_apply_constraints(b200md_ctx* ctx, double tol) {
     API_BEGIN(ctx)
+    sync_positions(ctx);
     launch_constrain_positions(ctx->nb, ctx->units, (float) tol, ctx->stream);
     ctx->kernelLaunches++;
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
@@ -1269,6 +1442,7 @@ extern "C" int b200md_apply_constraints(b200md_ctx* ctx, double tol) {
 extern "C" int b200md_apply_velocity_constraints(b200md_ctx* ctx, double tol) {
     API_BEGIN(ctx)
     ctx->stepStateValid = false;
+    sync_positions(ctx); sync_velocities(ctx);
     launch_constrain_velocities(ctx->nb, ctx->units, (float) tol, ctx->stream);
     ctx->kernelLaunches++;
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
@@ -1370,6 +1544,7 @@ extern "C" int b200md_time_phase(b200md_ctx* ctx, int phase, int reps, double* m
     c->stepStateValid = false;            // phases 0, 3, 6 accumulate into the force buffer, phase 5 flips the list
     cudaStream_t s = c->stream;
     const NbDev nbv = role_nb(c);        // the sharding the step graphs use
+    CommDev local{}; local.world = 1;   // phases are timed rank-locally (no peer traffic, no waits)
     cudaEvent_t e0, e1;
     CUDA_CHECK(cudaEventCreate(&e0)); CUDA_CHECK(cudaEventCreate(&e1));
     const int one = 1;
@@ -1393,10 +1568,10 @@ extern "C" int b200md_time_phase(b200md_ctx* ctx, int phase, int reps, double* m
         CUDA_CHECK(cudaEventRecord(e0, s));
         switch (phase) {
             case 0: launch_pair(nbv, false, s); break;
-            case 1: launch_pme_spread(nbv, c->pme, s); break;
-            case 2: launch_pme_fft_conv(nbv, c->pme, false, s); break;
-            case 3: launch_pme_gather(nbv, c->pme, s); break;
-            case 4: launch_integrate(nbv, c->units, c->integ, s); break;
+            case 1: launch_pme_spread(nbv, c->pme, local, s); break;
+            case 2: launch_pme_fft_conv(nbv, c->pme, local, false, s); break;
+            case 3: launch_pme_gather(nbv, c->pme, local, s); break;
+            case 4: launch_integrate(nbv, c->units, c->integ, local, s); break;
             case 5: launch_list_build(nbv, s); break;
             case 6: launch_bonded(nbv, c->bd, B200MD_TERM_ALL, false, s); break;
             default: throw std::runtime_error("unknown phase");

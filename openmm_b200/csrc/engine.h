@@ -83,6 +83,8 @@ struct NbDev {
     float4* posq;                // xyz + charge*sqrt(ONE_4PI_EPS0)
     float4* velm;                // v + 1/mass
     float2* sigeps;              // (sigma/2, 2 sqrt(eps))  (ReferenceKernels.cpp:1093-1097)
+    const double* chargeD;       // the same parameters in double (user order): the double-precision close-pair path
+    const double2* sigepsD;
     long long* force;            // [3][npad] fixed point, user order
     double* energy;              // [B200MD_NUM_ENERGY] accumulators
     // sorted (nonbonded) copies, blocks and tiles: two complete lists.  counters[CT_CUR] names the one the tile kernel reads;
@@ -176,6 +178,98 @@ struct IntegDev {
     unsigned int* blocksDone;
 };
 
+// ---------------------------------------------------------------------------------------------------------------
+// Multi-GPU data plane (one process per GPU): every rank maps every other rank's WINDOW (one cudaMalloc, exported with
+// cudaIpcGetMemHandle) and the kernels themselves move the data with plain stores over NVLink, tile by tile, and
+// publish a flag per (channel, source rank) when a stage is complete; consumers spin on their LOCAL flag copy.  No
+// NCCL call on the step path.  Ownership: rank q owns the user atoms [atomLo[q], atomLo[q+1]) (cut at integration-unit
+// boundaries): it reduces their forces, integrates them and pushes their new positions to everybody.  Reciprocal space
+// is slab-decomposed: rank q owns the x planes [xLo[q], xLo[q+1]) for the (y,z) transforms and the (ky,kz) lines
+// [q*lineChunk, ...) for the x transform; the two transposes are the stores of the FFT kernels themselves.
+#define B200MD_MAX_RANKS 8
+enum { CH_POS = 0,      // new positions of the owner's atoms are in everybody's posq        (k_integrate)
+       CH_FORCE = 1,    // partial forces are in the owners' inboxes                         (k_force_push)
+       CH_FINAL = 2,    // total forces of the owner's atoms are in everybody's force buffer (k_force_total; compute path only)
+       CH_GRID = 3,     // charge-grid contributions are in the slab owners' inboxes         (k_grid_push)
+       CH_FWD = 4,      // (y,z)-transformed planes are in the line owners' buffers          (k_fft_slab_fwd)
+       CH_INV = 5,      // x-transformed, convolved lines are back in the slab owners' buffers (k_fft_x_conv)
+       CH_POT = 6,      // potential planes are in everybody's grid                          (k_fft_slab_inv)
+       CH_VEL = 7,      // velocities of the owner's atoms are in everybody's velm           (k_vel_push; state reads only)
+       CH_COUNT = 8 };
+struct CommDev {
+    int rank, world;                     // world == 1: no peer traffic, every wait/signal is skipped
+    int atomLo[B200MD_MAX_RANKS + 1];
+    int unitLo[B200MD_MAX_RANKS + 1];
+    int xLo[B200MD_MAX_RANKS + 1];       // x planes of the PME grid
+    int lineChunk;                       // (ky,kz) lines per rank (multiple of the x-pass batch; the last rank may get fewer)
+    int maxPlanes;                       // max x planes per rank
+    char* peer[B200MD_MAX_RANKS];        // window base of every rank as mapped HERE (peer[rank] = own window)
+    // offsets inside a window (identical on every rank)
+    size_t offFlags, offPosq, offVelm, offForce, offFinbox, offCm, offGridInbox, offLineBuf, offPlaneBuf, offGrid;
+    unsigned long long* epoch;           // local: number of completed exchanges; every evaluation uses E = *epoch + 1
+    unsigned long long* posNeed;         // local: CH_POS value the next evaluation must wait for (0: positions were set by the host)
+    unsigned int* done;                  // local: [CH_COUNT] block-completion counters of the signalling kernels
+    int* errFlag;                        // local: sticky error (NbDev::counters + CT_OVERFLOW): a wait that times out raises 3
+};
+
+#ifdef __CUDACC__
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long* comm_flag(const CommDev& cd, int onRank, int ch, int src) {
+    return (unsigned long long*) (cd.peer[onRank] + cd.offFlags) + ch*B200MD_MAX_RANKS + src;
+}
+// Block-wide: wait until every peer has published `need` on channel ch.  Bounded (~1 s): a lost peer raises the sticky
+// error flag instead of hanging the device.
+__device__ __forceinline__ void comm_wait(const CommDev& cd, int ch, unsigned long long need) {
+    if (cd.world > 1 && need != 0ull) {
+        if (threadIdx.x < cd.world && (int) threadIdx.x != cd.rank && threadIdx.y == 0 && threadIdx.z == 0) {
+            const unsigned long long* f = comm_flag(cd, cd.rank, ch, threadIdx.x);
+            long spins = 0;
+            while (ld_acquire_sys(f) < need) {
+                if (*((volatile int*) cd.errFlag) == 3) break;        // a peer was lost earlier: fail fast, the host raises at its next sync
+                __nanosleep(64);
+                if (++spins > (1L << 22)) { *cd.errFlag = 3; break; }
+            }
+        }
+    }
+    __syncthreads();
+}
+// Block-wide: this block's stores to peer memory are complete.  Returns true (to all threads) in the LAST block of the grid,
+// which then publishes the stage with comm_publish (possibly after a little more work of its own).
+__device__ __forceinline__ bool comm_arrive(const CommDev& cd, int ch, unsigned int nblocks) {
+    __shared__ int lastBlock;
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0 && threadIdx.y == 0 && threadIdx.z == 0) {
+        lastBlock = (atomicAdd(&cd.done[ch], 1u) == nblocks - 1u);
+        if (lastBlock) { cd.done[ch] = 0u; __threadfence_system(); }
+    }
+    __syncthreads();
+    return lastBlock != 0;
+}
+__device__ __forceinline__ void comm_publish(const CommDev& cd, int ch, unsigned long long value) {       // one thread
+    __threadfence_system();
+    for (int q = 0; q < cd.world; q++) if (q != cd.rank) st_release_sys(comm_flag(cd, q, ch, cd.rank), value);
+}
+__device__ __forceinline__ bool comm_signal(const CommDev& cd, int ch, unsigned long long value, unsigned int nblocks) {
+    const bool last = comm_arrive(cd, ch, nblocks);
+    if (last && threadIdx.x == 0 && threadIdx.y == 0 && threadIdx.z == 0) comm_publish(cd, ch, value);
+    return last;
+}
+__device__ __forceinline__ int comm_owner_of_atom(const CommDev& cd, int a) {
+    int q = 0;
+#pragma unroll
+    for (int k = 1; k < B200MD_MAX_RANKS; k++) q += (k < cd.world && a >= cd.atomLo[k]) ? 1 : 0;
+    return q;
+}
+#endif
+
 // 2^32 fixed point <-> fp32 without the 64-bit conversion instructions (I2F.S64 / F2I.S64 are multi-pass on the XU pipe and
 // showed up as the hottest instructions of the FFT load loop and of the integrator in the round-1 profiles)
 #ifdef __CUDACC__
@@ -193,7 +287,7 @@ __device__ __forceinline__ long long float_to_fixed(float f) {           // |f| 
 #endif
 
 // ---- launchers (defined in the .cu files) ----
-void launch_check_displacement(const NbDev& nb, cudaStream_t s);
+void launch_check_displacement(const NbDev& nb, const CommDev& cd, cudaStream_t s);
 bool list_build_merged();        // list build = 2 gated launches (k_list_prep with grid barriers + k_build_tiles); B200MD_LIST_MERGED=0: 7
 void launch_list_build(const NbDev& nb, cudaStream_t s, int mode = 0);   // all list kernels, gated on counters[CT_REBUILD] (mode 0) or counters[CT_SOFT] (mode 1)
 void launch_pair(const NbDev& nb, bool energy, cudaStream_t s);
@@ -201,21 +295,27 @@ void launch_count_pairs(const NbDev& nb, cudaStream_t s);
 int  list_build_launch_count();
 
 void launch_pme_eterm(const NbDev& nb, const PmeDev& pme, cudaStream_t s);
-void launch_pme_spread(const NbDev& nb, const PmeDev& pme, cudaStream_t s);
-void launch_pme_fft_conv(const NbDev& nb, const PmeDev& pme, bool energy, cudaStream_t s);
-void launch_pme_gather(const NbDev& nb, const PmeDev& pme, cudaStream_t s);
+void launch_pme_spread(const NbDev& nb, const PmeDev& pme, const CommDev& cd, cudaStream_t s);
+void launch_pme_fft_conv(const NbDev& nb, const PmeDev& pme, const CommDev& cd, bool energy, cudaStream_t s);
+void launch_pme_gather(const NbDev& nb, const PmeDev& pme, const CommDev& cd, cudaStream_t s);
+void launch_grid_push(const PmeDev& pme, const CommDev& cd, cudaStream_t s);
 void launch_fft3d_r2c(const PmeDev& pme, cudaStream_t s);         // grid -> cgrid
 void launch_fft3d_c2r(const PmeDev& pme, cudaStream_t s);         // cgrid -> grid
 size_t fft_plane_smem_bytes(int ny, int nz);
 size_t fft_line_smem_bytes(int nx);
 bool fft_make_radices(int n, int* radix, int* nstages);
 int pme_fft_launch_count(const PmeDev& pme);
+bool fft_slab_path(const PmeDev& pme);          // the 3-launch slab pipeline is usable for this grid (precondition of the multi-GPU FFT)
 
 void launch_bonded(const NbDev& nb, const BondedDev& bd, int terms, bool energy, cudaStream_t s);
 
-void launch_integrate(const NbDev& nb, const UnitDev& units, const IntegDev& integ, cudaStream_t s);
+void launch_integrate(const NbDev& nb, const UnitDev& units, const IntegDev& integ, const CommDev& cd, cudaStream_t s);
+void launch_force_push(const NbDev& nb, const CommDev& cd, cudaStream_t s);          // partial forces of foreign atoms -> owners' inboxes
+void launch_force_total(const NbDev& nb, const CommDev& cd, cudaStream_t s);         // compute path: owners total and broadcast, everybody waits
+void launch_vel_push(const NbDev& nb, const CommDev& cd, cudaStream_t s);            // owners' velocities -> everybody (state reads)
+void launch_pos_wait(const NbDev& nb, const CommDev& cd, cudaStream_t s);            // wait for the peers' position stores (state reads)
 void launch_constrain_positions(const NbDev& nb, const UnitDev& units, float tol, cudaStream_t s);
 void launch_constrain_velocities(const NbDev& nb, const UnitDev& units, float tol, cudaStream_t s);
 void launch_kinetic_energy(const NbDev& nb, const UnitDev& units, const IntegDev& integ, float shiftDt, cudaStream_t s);
 void launch_remove_cm(const NbDev& nb, double* scratch, cudaStream_t s);
-void launch_cm_prime(const NbDev& nb, const IntegDev& integ, cudaStream_t s);
+void launch_cm_prime(const NbDev& nb, const IntegDev& integ, const CommDev& cd, cudaStream_t s);

@@ -5,22 +5,26 @@
 // pme_reciprocal_convolution (ReferencePME.cpp:409-514, 793-799): unnormalised transforms in both directions,
 // forward = exp(-2 pi i jk/n).
 //
-// Five launches for forward + convolution + inverse; every launch is a batch of independent 1-D lines that live in
-// shared memory for the whole transform, so the grid is read and written exactly once per pass and stays in L2:
-//   1  k_fft_z_fwd   real-to-complex along z; two real rows are packed into one complex line (half the work)
-//   2  k_fft_y       complex along y, 16 adjacent kz columns per CTA (128-byte coalesced segments)
-//   3  k_fft_x_conv  forward along x, multiply by the influence function, accumulate the reciprocal energy,
-//                    inverse along x -- the k-space grid never leaves shared memory between the three
-//   4  k_fft_y       inverse along y
-//   5  k_fft_z_inv   complex-to-real along z (Hermitian unpacking, two rows per complex line)
-// Round 1 v1 used one CTA per x-slab (3 launches); profiles/r01_launches_bench_nograph.csv showed 56 under-filled
-// CTAs taking 27 us each -- the line-batched layout below gives 100-200 CTAs per pass.
+// Single precision spectral pipeline (typedef real, engine.h); the INPUT is the int64 fixed-point charge grid, which makes
+// spreading -- and therefore every force -- independent of the order of the atomics.
 //
-// 1-D transforms are Stockham autosort, mixed radix with generic radices 2..16 (any n whose prime factors are
-// <= 13: 56 = 8*7, 88 = 8*11, 90 = 6*5*3, 128 = 8*4*4 ...), out of place between two shared-memory buffers, twiddles
-// staged in shared memory.  The whole reciprocal pipeline is DOUBLE precision (the forces are small differences of a
-// smooth potential of magnitude ~1e2: an fp32 grid alone costs ~1e-3 kJ/mol/nm); the B200 FP64
-// rate is ample for 1e5..1e6 grid points and these kernels are latency bound.
+// Three launches when two copies of a (y,z) plane fit in shared memory (grids up to ~160^2 per plane; the usual case):
+//   1  k_fft_slab_fwd   one x plane per CTA: R2C along z (two real rows packed into one complex line), then along y
+//   2  k_fft_x_conv     16 (ky,kz) lines per CTA: forward along x, multiply by the influence function, accumulate the
+//                       reciprocal energy, inverse along x -- the k-space grid never leaves shared memory between the three
+//   3  k_fft_slab_inv   one x plane per CTA: inverse along y, C2R along z
+// otherwise five line-batched passes (k_fft_z_fwd, k_fft_y, k_fft_x_conv, k_fft_y, k_fft_z_inv).
+//
+// Multi-GPU (CommDev::world > 1): x planes are dealt to the ranks in contiguous slabs, (ky,kz) lines in contiguous chunks.
+// The two transposes of a slab-decomposed 3-D FFT are the STORES of kernels 1 and 2: k_fft_slab_fwd writes every
+// transformed plane straight into the line owners' buffers over NVLink, k_fft_x_conv writes its lines back into the slab
+// owners' buffers, k_fft_slab_inv writes the potential plane into everybody's grid; each publishes one flag per stage
+// (CH_FWD, CH_INV, CH_POT) and the consumer kernel spins on it.  k_fft_slab_fwd also sums the charge-grid contributions
+// that the other ranks pushed (k_grid_push, CH_GRID) while it loads its plane.
+//
+// 1-D transforms are Stockham autosort, mixed radix 2..16 (any n whose prime factors are <= 13), out of place between two
+// shared-memory buffers, twiddles staged in shared memory; radix 2/4 butterflies are multiplication free, odd radices use
+// the conjugate-pair form.
 #include "engine.h"
 #include <algorithm>
 #include <math.h>
@@ -174,8 +178,6 @@ __device__ real2* fft_lines(real2* a, real2* b, const FftPlanDev& plan, int nlin
     return in;
 }
 
-__device__ __forceinline__ void fft_build_tables(unsigned int* tab, const FftPlanDev& plan) { (void) tab; (void) plan; }
-
 // factorisation into radices <= 16 minimising sum(R + 4): R complex MACs per point per generic stage plus a
 // synchronisation cost per stage (exhaustive search, n is small)
 static int best_cost(int n, int* radix, int depth) {
@@ -224,7 +226,6 @@ size_t fft_line_smem_bytes(int nx) { return (2*(size_t) LINE_BATCH*nx + 3*nx)*si
 __device__ __forceinline__ unsigned int* stage_twiddles(real2* tws, const FftPlanDev& plan) {
     for (int i = TID; i < plan.n; i += NTHR) tws[i] = plan.tw[i];
     unsigned int* tab = (unsigned int*) (tws + plan.n);
-    fft_build_tables(tab, plan);
     return tab;
 }
 
@@ -338,7 +339,7 @@ __global__ void __launch_bounds__(FFT_THREADS) k_fft_y(PmeDev pme, int inverse) 
 // ---- 3: forward x, convolution + energy, inverse x; one batch of (ky,kz) lines per CTA ----
 // mode 0: forward + convolution + inverse (PME); mode 1: forward only; mode 2: inverse only (stand-alone FFT)
 template <bool ENERGY>
-__global__ void __launch_bounds__(FFT_THREADS) k_fft_x_conv(PmeDev pme, double* energyOut, int mode) {
+__global__ void __launch_bounds__(FFT_THREADS) k_fft_x_conv(PmeDev pme, double* energyOut, int mode, CommDev cd) {
     extern __shared__ real2 smem[];
     const int nx = pme.nx;
     const int plane = pme.ny*pme.nzc;
@@ -346,17 +347,24 @@ __global__ void __launch_bounds__(FFT_THREADS) k_fft_x_conv(PmeDev pme, double* 
     real2* B = A + LINE_BATCH*nx;
     real2* tws = B + LINE_BATCH*nx;
     const unsigned int* tab = stage_twiddles(tws, pme.plan[0]);
+    const bool multi = cd.world > 1;
+    const unsigned long long E = multi ? *cd.epoch + 1ull : 0ull;
+    // multi-GPU: this rank's chunk of lines [mlo, mlo + mcount) arrives in its line buffer, layout [x][mcount]
+    const int mlo = multi ? cd.rank*cd.lineChunk : 0;
+    const int mcount = multi ? max(0, min(cd.lineChunk, plane - mlo)) : plane;
+    const real2* src = multi ? (const real2*) (cd.peer[cd.rank] + cd.offLineBuf) : pme.cgrid;
+    if (multi) comm_wait(cd, CH_FWD, E);
     const int m0 = blockIdx.x*LINE_BATCH;
-    const int nl = min(LINE_BATCH, plane - m0);
+    const int nl = min(LINE_BATCH, mcount - m0);
     for (int i = TID; i < nx*LINE_BATCH; i += NTHR) {
         const int x = i/LINE_BATCH, l = i - x*LINE_BATCH;
-        if (l < nl) A[l*nx + x] = pme.cgrid[(size_t) x*plane + m0 + l];
+        if (l < nl) A[l*nx + x] = src[(size_t) x*mcount + m0 + l];
     }
     __syncthreads();
     real2* R = A;
     real2* other = B;
     if (mode != 2) {
-        R = fft_lines(A, B, pme.plan[0], nl, tab, tws, false);
+        R = fft_lines(A, B, pme.plan[0], max(nl, 0), tab, tws, false);
         other = (R == A) ? B : A;
     }
     if (mode == 0) {
@@ -364,7 +372,7 @@ __global__ void __launch_bounds__(FFT_THREADS) k_fft_x_conv(PmeDev pme, double* 
         for (int i = TID; i < nx*LINE_BATCH; i += NTHR) {
             const int x = i/LINE_BATCH, l = i - x*LINE_BATCH;
             if (l < nl) {
-                const int m = m0 + l;
+                const int m = mlo + m0 + l;
                 const real et = pme.eterm[(size_t) x*plane + m];
                 const real2 v = R[l*nx + x];
                 if (ENERGY) {
@@ -389,7 +397,21 @@ __global__ void __launch_bounds__(FFT_THREADS) k_fft_x_conv(PmeDev pme, double* 
         __syncthreads();
     }
     if (mode != 1)
-        R = fft_lines(R, other, pme.plan[0], nl, tab, tws, true);
+        R = fft_lines(R, other, pme.plan[0], max(nl, 0), tab, tws, true);
+    if (multi) {
+        // second transpose: every x plane goes back to the rank that owns its slab, layout [x - xLo][plane]
+        for (int i = TID; i < nx*LINE_BATCH; i += NTHR) {
+            const int x = i/LINE_BATCH, l = i - x*LINE_BATCH;
+            if (l < nl) {
+                int q = 0;
+#pragma unroll
+                for (int k = 1; k < B200MD_MAX_RANKS; k++) q += (k < cd.world && x >= cd.xLo[k]) ? 1 : 0;
+                ((real2*) (cd.peer[q] + cd.offPlaneBuf))[(size_t) (x - cd.xLo[q])*plane + mlo + m0 + l] = R[l*nx + x];
+            }
+        }
+        comm_signal(cd, CH_INV, E, gridDim.x);
+        return;
+    }
     for (int i = TID; i < nx*LINE_BATCH; i += NTHR) {
         const int x = i/LINE_BATCH, l = i - x*LINE_BATCH;
         if (l < nl) pme.cgrid[(size_t) x*plane + m0 + l] = R[l*nx + x];
@@ -414,8 +436,6 @@ __device__ __forceinline__ SlabSmem slab_setup(real2* smem, const PmeDev& pme, s
     S.taby = S.tabz + 8*pme.nz;
     for (int i = TID; i < pme.nz; i += NTHR) S.twz[i] = pme.plan[2].tw[i];
     for (int i = TID; i < pme.ny; i += NTHR) S.twy[i] = pme.plan[1].tw[i];
-    fft_build_tables(S.tabz, pme.plan[2]);
-    fft_build_tables(S.taby, pme.plan[1]);
     return S;
 }
 
@@ -429,14 +449,34 @@ static size_t slab_smem_bytes(const PmeDev& p) {
     return 2*slab_elems(p)*sizeof(real2) + (size_t) (p.nz + p.ny)*sizeof(real2) + (size_t) 8*(p.nz + p.ny)*sizeof(unsigned int);
 }
 
-__global__ void __launch_bounds__(FFT_THREADS) k_fft_slab_fwd(PmeDev pme, size_t elems) {
+__global__ void __launch_bounds__(FFT_THREADS) k_fft_slab_fwd(PmeDev pme, size_t elems, CommDev cd) {
     extern __shared__ real2 smem[];
     const int ny = pme.ny, nz = pme.nz, nzc = pme.nzc;
     const FastDiv divNz(nz), divNzc(nzc);
     const int np = (ny + 1)/2;
     SlabSmem S = slab_setup(smem, pme, elems);
-    const int x = blockIdx.x;
-    if (pme.gridFixed != nullptr) {
+    const bool multi = cd.world > 1;
+    const unsigned long long E = multi ? *cd.epoch + 1ull : 0ull;
+    const int x = (multi ? cd.xLo[cd.rank] : 0) + blockIdx.x;
+    if (multi) {
+        // the plane = this rank's own spread + what the other ranks pushed into the inboxes (exact int64 sums)
+        comm_wait(cd, CH_GRID, E);
+        const size_t planeCells = (size_t) ny*nz;
+        const long long* own = pme.gridFixed + (size_t) x*planeCells;
+        const long long* inbox = (const long long*) (cd.peer[cd.rank] + cd.offGridInbox) + (size_t) (x - cd.xLo[cd.rank])*planeCells;
+        const size_t inboxStride = (size_t) cd.maxPlanes*planeCells;
+        for (int i = TID; i < np*nz; i += NTHR) {
+            const int p = divNz.div(i), z = i - p*nz;
+            long long a = own[(size_t) (2*p)*nz + z], b = (2*p+1 < ny) ? own[(size_t) (2*p+1)*nz + z] : 0ll;
+            for (int q = 0; q < cd.world; q++) if (q != cd.rank) {
+                const long long* iq = inbox + (size_t) q*inboxStride;
+                a += iq[(size_t) (2*p)*nz + z];
+                if (2*p+1 < ny) b += iq[(size_t) (2*p+1)*nz + z];
+            }
+            S.A[i] = make_real2(fixed_to_float(a), fixed_to_float(b));
+        }
+    }
+    else if (pme.gridFixed != nullptr) {
         long long* base = pme.gridFixed + (size_t) x*ny*nz;
         for (int i = TID; i < np*nz; i += NTHR) {
             const int p = divNz.div(i), z = i - p*nz;
@@ -470,6 +510,20 @@ __global__ void __launch_bounds__(FFT_THREADS) k_fft_slab_fwd(PmeDev pme, size_t
     __syncthreads();
     real2* other = (O == S.A) ? S.B : S.A;
     const real2* Y = fft_lines(O, other, pme.plan[1], nzc, S.taby, S.twy, false);
+    if (multi) {
+        // first transpose: line m = y*nzc + k of this plane goes to the rank that owns the line, layout [x][its line count]
+        const int plane = ny*nzc;
+        const FastDiv divChunk(cd.lineChunk);
+        for (int i = TID; i < plane; i += NTHR) {
+            const int y = divNzc.div(i), k = i - y*nzc;
+            const int q = divChunk.div(i);
+            const int mq = i - q*cd.lineChunk;
+            const int cnt = min(cd.lineChunk, plane - q*cd.lineChunk);
+            ((real2*) (cd.peer[q] + cd.offLineBuf))[(size_t) x*cnt + mq] = Y[k*ny + y];
+        }
+        comm_signal(cd, CH_FWD, E, gridDim.x);
+        return;
+    }
     real2* dst = pme.cgrid + (size_t) x*ny*nzc;
     for (int i = TID; i < ny*nzc; i += NTHR) {
         const int y = divNzc.div(i), k = i - y*nzc;
@@ -477,14 +531,18 @@ __global__ void __launch_bounds__(FFT_THREADS) k_fft_slab_fwd(PmeDev pme, size_t
     }
 }
 
-__global__ void __launch_bounds__(FFT_THREADS) k_fft_slab_inv(PmeDev pme, size_t elems) {
+__global__ void __launch_bounds__(FFT_THREADS) k_fft_slab_inv(PmeDev pme, size_t elems, CommDev cd) {
     extern __shared__ real2 smem[];
     const int ny = pme.ny, nz = pme.nz, nzc = pme.nzc;
     const FastDiv divNz(nz), divNzc(nzc);
     const int np = (ny + 1)/2;
     SlabSmem S = slab_setup(smem, pme, elems);
-    const int x = blockIdx.x;
-    const real2* src = pme.cgrid + (size_t) x*ny*nzc;
+    const bool multi = cd.world > 1;
+    const unsigned long long E = multi ? *cd.epoch + 1ull : 0ull;
+    const int x = (multi ? cd.xLo[cd.rank] : 0) + blockIdx.x;
+    if (multi) comm_wait(cd, CH_INV, E);
+    const real2* src = multi ? (const real2*) (cd.peer[cd.rank] + cd.offPlaneBuf) + (size_t) (x - cd.xLo[cd.rank])*ny*nzc
+                             : pme.cgrid + (size_t) x*ny*nzc;
     for (int i = TID; i < ny*nzc; i += NTHR) {
         const int y = divNzc.div(i), k = i - y*nzc;
         S.A[k*ny + y] = src[i];
@@ -504,6 +562,20 @@ __global__ void __launch_bounds__(FFT_THREADS) k_fft_slab_inv(PmeDev pme, size_t
     __syncthreads();
     real2* other = (O == S.A) ? S.B : S.A;
     const real2* Z = fft_lines(O, other, pme.plan[2], np, S.tabz, S.twz, true);
+    if (multi) {
+        // the potential plane goes into EVERY rank's grid (each rank interpolates the forces of its own atoms, wherever they are)
+        for (int q = 0; q < cd.world; q++) {
+            real* dq = (real*) (cd.peer[q] + cd.offGrid) + (size_t) x*ny*nz;
+            for (int i = TID; i < np*nz; i += NTHR) {
+                const int p = divNz.div(i), z = i - p*nz;
+                const real2 v = Z[i];
+                dq[(size_t) (2*p)*nz + z] = v.x;
+                if (2*p+1 < ny) dq[(size_t) (2*p+1)*nz + z] = v.y;
+            }
+        }
+        comm_signal(cd, CH_POT, E, gridDim.x);
+        return;
+    }
     real* dst = pme.grid + (size_t) x*ny*nz;
     for (int i = TID; i < np*nz; i += NTHR) {
         const int p = divNz.div(i), z = i - p*nz;
@@ -557,15 +629,16 @@ struct FftLaunch {
     }
 };
 
+static const CommDev g_single = [] { CommDev c{}; c.world = 1; return c; }();
 static void fwd_zy(const FftLaunch& L, const PmeDev& pme, cudaStream_t s) {
-    if (L.slab) k_fft_slab_fwd<<<pme.nx, L.st, L.ss, s>>>(pme, L.selems);
+    if (L.slab) k_fft_slab_fwd<<<pme.nx, L.st, L.ss, s>>>(pme, L.selems, g_single);
     else {
         k_fft_z_fwd<<<L.zb, L.zt, L.zs, s>>>(pme);
         k_fft_y<<<L.yb, L.yt, L.ys, s>>>(pme, 0);
     }
 }
 static void inv_yz(const FftLaunch& L, const PmeDev& pme, cudaStream_t s) {
-    if (L.slab) k_fft_slab_inv<<<pme.nx, L.st, L.ss, s>>>(pme, L.selems);
+    if (L.slab) k_fft_slab_inv<<<pme.nx, L.st, L.ss, s>>>(pme, L.selems, g_single);
     else {
         k_fft_y<<<L.yb, L.yt, L.ys, s>>>(pme, 1);
         k_fft_z_inv<<<L.zb, L.zt, L.zs, s>>>(pme);
@@ -574,22 +647,36 @@ static void inv_yz(const FftLaunch& L, const PmeDev& pme, cudaStream_t s) {
 
 int pme_fft_launch_count(const PmeDev& pme) { FftLaunch L(pme); return L.slab ? 3 : 5; }
 
-void launch_pme_fft_conv(const NbDev& nb, const PmeDev& pme, bool energy, cudaStream_t s) {
+bool fft_slab_path(const PmeDev& pme) { FftLaunch L(pme); return L.slab; }
+
+void launch_pme_fft_conv(const NbDev& nb, const PmeDev& pme, const CommDev& cd, bool energy, cudaStream_t s) {
     FftLaunch L(pme);
+    if (cd.world > 1) {
+        // slab-decomposed over the ranks (the slab path is a precondition, checked when the communicator is set up)
+        const int planes = cd.xLo[cd.rank + 1] - cd.xLo[cd.rank];
+        const int plane = pme.ny*pme.nzc;
+        const int mcount = std::max(0, std::min(cd.lineChunk, plane - cd.rank*cd.lineChunk));
+        const int xb = std::max(1, (mcount + LINE_BATCH - 1)/LINE_BATCH);
+        k_fft_slab_fwd<<<std::max(1, planes), L.st, L.ss, s>>>(pme, L.selems, cd);
+        if (energy) k_fft_x_conv<true><<<xb, L.xt, L.xs, s>>>(pme, nb.energy + EN_RECIP, 0, cd);
+        else k_fft_x_conv<false><<<xb, L.xt, L.xs, s>>>(pme, nb.energy + EN_RECIP, 0, cd);
+        k_fft_slab_inv<<<std::max(1, planes), L.st, L.ss, s>>>(pme, L.selems, cd);
+        return;
+    }
     fwd_zy(L, pme, s);
-    if (energy) k_fft_x_conv<true><<<L.xb, L.xt, L.xs, s>>>(pme, nb.energy + EN_RECIP, 0);
-    else k_fft_x_conv<false><<<L.xb, L.xt, L.xs, s>>>(pme, nb.energy + EN_RECIP, 0);
+    if (energy) k_fft_x_conv<true><<<L.xb, L.xt, L.xs, s>>>(pme, nb.energy + EN_RECIP, 0, g_single);
+    else k_fft_x_conv<false><<<L.xb, L.xt, L.xs, s>>>(pme, nb.energy + EN_RECIP, 0, g_single);
     inv_yz(L, pme, s);
 }
 
 void launch_fft3d_r2c(const PmeDev& pme, cudaStream_t s) {
     FftLaunch L(pme);
     fwd_zy(L, pme, s);
-    k_fft_x_conv<false><<<L.xb, L.xt, L.xs, s>>>(pme, nullptr, 1);
+    k_fft_x_conv<false><<<L.xb, L.xt, L.xs, s>>>(pme, nullptr, 1, g_single);
 }
 
 void launch_fft3d_c2r(const PmeDev& pme, cudaStream_t s) {
     FftLaunch L(pme);
-    k_fft_x_conv<false><<<L.xb, L.xt, L.xs, s>>>(pme, nullptr, 2);
+    k_fft_x_conv<false><<<L.xb, L.xt, L.xs, s>>>(pme, nullptr, 2, g_single);
     inv_yz(L, pme, s);
 }

@@ -8,6 +8,7 @@
 // applyShake* -> integrateLangevinPart2 -> generateRandomNumbers (4-6 launches + an RNG refill) with one kernel;
 // the noise is Philox4x32-10 keyed on (seed; atom, step) so results do not depend on launch geometry.
 #include "engine.h"
+#include <algorithm>
 #include "../../include/b200md.h"
 
 // ---------------------------------------------------------------- Philox4x32-10 (Salmon et al., SC'11)
@@ -177,7 +178,7 @@ struct Unit {
     float4 prm;
 };
 
-__device__ __forceinline__ bool load_unit(const NbDev& nb, const UnitDev& un, int u, Unit& U, bool wantForce) {
+__device__ __forceinline__ bool load_unit(const NbDev& nb, const UnitDev& un, int u, Unit& U, bool wantForce, const CommDev* cd = nullptr) {
     const int4 at = un.unitAtoms[u];
     U.atom[0] = at.x; U.atom[1] = at.y; U.atom[2] = at.z; U.atom[3] = at.w;
     U.type = un.unitType[u];
@@ -195,7 +196,16 @@ __device__ __forceinline__ bool load_unit(const NbDev& nb, const UnitDev& un, in
         U.invM[k] = v.w;
         U.m[k] = (v.w > 0.f) ? 1.0f/v.w : 0.f;
         if (wantForce) {
-            U.f[k] = {fixed_to_float(nb.force[a]), fixed_to_float(nb.force[a + nb.npad]), fixed_to_float(nb.force[a + 2*nb.npad])};
+            long long fx = nb.force[a], fy = nb.force[a + nb.npad], fz = nb.force[a + 2*nb.npad];
+            if (cd != nullptr && cd->world > 1) {
+                // owner: total = own partial + what the other ranks pushed into the inboxes (exact int64 sums, any order)
+                const long long* in = (const long long*) (cd->peer[cd->rank] + cd->offFinbox);
+                for (int q = 0; q < cd->world; q++) if (q != cd->rank) {
+                    const long long* iq = in + (size_t) q*3*nb.npad;
+                    fx += iq[a]; fy += iq[a + nb.npad]; fz += iq[a + 2*nb.npad];
+                }
+            }
+            U.f[k] = {fixed_to_float(fx), fixed_to_float(fy), fixed_to_float(fz)};
         }
     }
     return true;
@@ -216,10 +226,18 @@ __device__ __forceinline__ void constrain_vel(const Unit& U, V3* v, float tol) {
 //    result as removing it at the start of that step, ReferenceKernels RemoveCMMotion); cm[(step+2)%3] is zeroed for reuse.
 //  * the force buffer is zeroed after it has been read (saves the memset node at the head of the next step's graph).
 //  * the last block to finish advances the step counter (saves a 1-thread kernel).
+//
+// Multi-GPU (cd.world > 1): this rank integrates the units it OWNS.  The kernel first waits for the other ranks' partial
+// forces (CH_FORCE), totals them with its own, and stores the new positions into EVERY rank's posq over NVLink -- the
+// integrate step IS the position all-gather.  The last block hands its momentum sums to everybody and publishes CH_POS.
 template <int KIND>
-__global__ void __launch_bounds__(128) k_integrate(NbDev nb, UnitDev un, IntegDev in) {
-    const int u = blockIdx.x*blockDim.x + threadIdx.x;
-    const bool active = u < un.nunits;
+__global__ void __launch_bounds__(128) k_integrate(NbDev nb, UnitDev un, IntegDev in, CommDev cd) {
+    const bool multi = cd.world > 1;
+    const bool useInbox = multi && in.fused;       // step path; after b200md_compute the force buffer already holds the totals
+    const unsigned long long E = multi ? *cd.epoch + 1ull : 0ull;
+    if (useInbox) comm_wait(cd, CH_FORCE, E);
+    const int u = (multi ? cd.unitLo[cd.rank] : 0) + blockIdx.x*blockDim.x + threadIdx.x;
+    const bool active = u < (multi ? cd.unitLo[cd.rank + 1] : un.nunits);
     const unsigned long long step = *in.stepCounter;
     Unit U;
     U.n = 0;
@@ -228,12 +246,19 @@ __global__ void __launch_bounds__(128) k_integrate(NbDev nb, UnitDev un, IntegDe
     const bool cmFused = in.fused && in.cmEveryStep;
     V3 vcm = {0.f, 0.f, 0.f};
     if (cmFused) {
-        const double* c = in.cmScratch + 4*(step % 3ull);
+        double c[4];
+        if (multi) {
+            // every rank left the momentum of ITS atoms in slot [rank][step % 3] of everybody's table
+            const double* t = (const double*) (cd.peer[cd.rank] + cd.offCm) + 4*(step % 3ull);
+            c[0] = c[1] = c[2] = c[3] = 0.0;
+            for (int q = 0; q < cd.world; q++) for (int k = 0; k < 4; k++) c[k] += t[q*12 + k];
+        }
+        else { const double* t = in.cmScratch + 4*(step % 3ull); c[0] = t[0]; c[1] = t[1]; c[2] = t[2]; c[3] = t[3]; }
         const double im = (c[3] > 0.0) ? 1.0/c[3] : 0.0;
         vcm = {(float) (c[0]*im), (float) (c[1]*im), (float) (c[2]*im)};
     }
     if (active) {
-    load_unit(nb, un, u, U, true);
+    load_unit(nb, un, u, U, true, useInbox ? &cd : nullptr);
     if (in.fused) {
         _Pragma("unroll") for (int k = 0; k < 4; k++) if (k < U.n) {
             const int a = U.atom[k];
@@ -280,11 +305,14 @@ __global__ void __launch_bounds__(128) k_integrate(NbDev nb, UnitDev un, IntegDe
     _Pragma("unroll") for (int k = 0; k < 4; k++) if (k < U.n) {
         const int a = U.atom[k];
         const float4 p = nb.posq[a];
-        nb.posq[a] = make_float4(U.x[k].x + d[k].x, U.x[k].y + d[k].y, U.x[k].z + d[k].z, p.w);
+        const float4 pn = make_float4(U.x[k].x + d[k].x, U.x[k].y + d[k].y, U.x[k].z + d[k].z, p.w);
+        nb.posq[a] = pn;
         nb.velm[a] = make_float4(U.v[k].x, U.v[k].y, U.v[k].z, U.invM[k]);
+        if (multi)
+            for (int q = 0; q < cd.world; q++) if (q != cd.rank) ((float4*) (cd.peer[q] + cd.offPosq))[a] = pn;
     }
     }   // active
-    if (!in.fused) return;
+    if (!in.fused && !multi) return;
     if (cmFused) {
         double px = 0, py = 0, pz = 0, m = 0;
         _Pragma("unroll") for (int k = 0; k < 4; k++) if (k < U.n && U.invM[k] > 0.f) {
@@ -305,6 +333,25 @@ __global__ void __launch_bounds__(128) k_integrate(NbDev nb, UnitDev un, IntegDe
             if (blockIdx.x == 0) in.cmScratch[4*((step + 2ull) % 3ull) + threadIdx.x] = 0.0;
         }
     }
+    if (multi) {
+        // last block: momentum sums of this rank's atoms -> slot [rank][(step+1) % 3] of every rank's table, then CH_POS
+        const bool lastBlock = comm_arrive(cd, CH_POS, gridDim.x);
+        if (lastBlock && threadIdx.x == 0) {
+            if (cmFused) {
+                const double* mine = in.cmScratch + 4*((step + 1ull) % 3ull);
+                for (int q = 0; q < cd.world; q++) {
+                    double* t = (double*) (cd.peer[q] + cd.offCm) + cd.rank*12 + 4*((step + 1ull) % 3ull);
+                    for (int k = 0; k < 4; k++) t[k] = ((volatile const double*) mine)[k];
+                }
+            }
+            comm_publish(cd, CH_POS, E);
+            *cd.posNeed = E;
+            *cd.epoch = E;
+            *in.stepCounter = step + 1ull;
+            if (nb.counters[CT_PENDING]) { nb.counters[CT_PENDING] = 0; nb.counters[CT_CUR] ^= 1; }
+        }
+        return;
+    }
     // last block to finish: advance the step counter
     __shared__ int last;
     __syncthreads();
@@ -324,9 +371,9 @@ __global__ void __launch_bounds__(128) k_integrate(NbDev nb, UnitDev un, IntegDe
 __global__ void k_step_advance(IntegDev in) { *in.stepCounter += 1ull; }
 
 // momentum of the current velocities into cm[step % 3] (validates the fused scheme after the state was set from outside)
-__global__ void __launch_bounds__(256) k_cm_prime(NbDev nb, IntegDev in) {
+__global__ void __launch_bounds__(256) k_cm_prime(NbDev nb, IntegDev in, double* table) {
     const unsigned long long step = *in.stepCounter;
-    double* c = in.cmScratch + 4*(step % 3ull);
+    double* c = table + 4*(step % 3ull);
     const int a = blockIdx.x*blockDim.x + threadIdx.x;
     double px = 0, py = 0, pz = 0, m = 0;
     if (a < nb.natoms) {
@@ -347,18 +394,26 @@ __global__ void __launch_bounds__(256) k_cm_prime(NbDev nb, IntegDev in) {
     }
 }
 
-void launch_cm_prime(const NbDev& nb, const IntegDev& integ, cudaStream_t s) {
+// Multi-GPU: the velocities are in sync at this point (the caller ran launch_vel_push), every rank computes the same total
+// over ALL atoms and leaves it in row 0 of its own table (the other rows zero): k_integrate sums the rows.
+void launch_cm_prime(const NbDev& nb, const IntegDev& integ, const CommDev& cd, cudaStream_t s) {
     cudaMemsetAsync(integ.cmScratch, 0, 12*sizeof(double), s);
-    k_cm_prime<<<(nb.natoms + 255)/256, 256, 0, s>>>(nb, integ);
+    double* table = integ.cmScratch;
+    if (cd.world > 1) {
+        table = (double*) (cd.peer[cd.rank] + cd.offCm);
+        cudaMemsetAsync(table, 0, (size_t) B200MD_MAX_RANKS*12*sizeof(double), s);
+    }
+    k_cm_prime<<<(nb.natoms + 255)/256, 256, 0, s>>>(nb, integ, table);
 }
 
-void launch_integrate(const NbDev& nb, const UnitDev& units, const IntegDev& integ, cudaStream_t s) {
+void launch_integrate(const NbDev& nb, const UnitDev& units, const IntegDev& integ, const CommDev& cd, cudaStream_t s) {
     // 64-thread blocks: at DHFR size (8k units) 128-thread blocks fill only 65 of the 148 SMs
-    const int grid = (units.nunits + 63)/64;
-    if (integ.kind == B200MD_INT_VERLET) k_integrate<B200MD_INT_VERLET><<<grid, 64, 0, s>>>(nb, units, integ);
-    else if (integ.kind == B200MD_INT_LANGEVIN) k_integrate<B200MD_INT_LANGEVIN><<<grid, 64, 0, s>>>(nb, units, integ);
-    else k_integrate<B200MD_INT_LANGEVIN_MIDDLE><<<grid, 64, 0, s>>>(nb, units, integ);
-    if (!integ.fused) k_step_advance<<<1, 1, 0, s>>>(integ);
+    const int n = cd.world > 1 ? cd.unitLo[cd.rank + 1] - cd.unitLo[cd.rank] : units.nunits;
+    const int grid = std::max(1, (n + 63)/64);
+    if (integ.kind == B200MD_INT_VERLET) k_integrate<B200MD_INT_VERLET><<<grid, 64, 0, s>>>(nb, units, integ, cd);
+    else if (integ.kind == B200MD_INT_LANGEVIN) k_integrate<B200MD_INT_LANGEVIN><<<grid, 64, 0, s>>>(nb, units, integ, cd);
+    else k_integrate<B200MD_INT_LANGEVIN_MIDDLE><<<grid, 64, 0, s>>>(nb, units, integ, cd);
+    if (!integ.fused && cd.world <= 1) k_step_advance<<<1, 1, 0, s>>>(integ);
 }
 
 // ApplyConstraintsKernel::apply: project the current positions onto the constraints (reference & target identical)

@@ -62,7 +62,8 @@ __device__ __forceinline__ float box_dist2(float3 d, float hx, float hy, float h
 // 1. rebuild decision: any atom moved more than padding/2 since the last build (findInteractingBlocks.cu:67-76), fused
 // with the per-step refresh of the sorted position copy (with the CURRENT order; a rebuild in the same step rewrites it).
 // The last block to finish publishes the decision to the CUDA-graph conditional node that holds the rebuild kernels.
-__global__ void __launch_bounds__(256) k_check_gather(NbDev nb) {
+__global__ void __launch_bounds__(256) k_check_gather(NbDev nb, CommDev cd) {
+    comm_wait(cd, CH_POS, cd.world > 1 ? *cd.posNeed : 0ull);      // multi-GPU: the owners' position stores of the last step have landed
     const int s = blockIdx.x*blockDim.x + threadIdx.x;
     const ListDev& L = nb.list[nb.counters[CT_CUR] & 1];
     if (s == 0) nb.counters[CT_CURSOR] = 0;           // tile cursor of the tile kernel's dynamic schedule
@@ -738,8 +739,8 @@ __global__ void k_list_done(NbDev nb, int mode) {
     if (threadIdx.x == 0 && blockIdx.x == 0) list_done(nb, mode);
 }
 
-void launch_check_displacement(const NbDev& nb, cudaStream_t s) {
-    k_check_gather<<<(nb.npad+255)/256, 256, 0, s>>>(nb);
+void launch_check_displacement(const NbDev& nb, const CommDev& cd, cudaStream_t s) {
+    k_check_gather<<<(nb.npad+255)/256, 256, 0, s>>>(nb, cd);
 }
 
 // B200MD_LIST_MERGED=0: the six separate kernels instead of k_list_prep + k_build_tiles
@@ -849,10 +850,15 @@ __device__ __forceinline__ float wrap_rel(float p, float c, double L, double inv
 // rotations the warp evaluates the queued pairs in double from the EXACT user coordinates and adds the forces to the
 // fixed-point buffer directly.  ReferenceLJCoulombIxn.cpp:388-447 (PME) / :559-575 (cutoff) / calculateOneIxn restated.
 #define CLOSE_QCAP 96
+__device__ __forceinline__ float ewald_g(float w);
 template <bool ENERGY, int METHOD, bool SWITCH>
 __device__ __forceinline__ void close_pair_double(const NbDev& nb, const ListDev& L, int si, int sj, double& energyD) {
     const float4 a = L.sposq[si], b = L.sposq[sj];
-    const float2 sa = L.ssigeps[si], sb = L.ssigeps[sj];
+    const int ai = L.sorig[si], aj = L.sorig[sj];
+    // parameters in double from the user-order tables: the fp32 copies (q sqrt(k), sigma/2, 2 sqrt(eps)) carry a relative
+    // rounding of 6e-8 each, i.e. up to 7e-7 on the r^-12 term of a pair whose force is in the hundreds
+    const double qq = nb.chargeD[ai]*nb.chargeD[aj];
+    const double2 sa = nb.sigepsD[ai], sb = nb.sigepsD[aj];
     double dx = (double) b.x - (double) a.x, dy = (double) b.y - (double) a.y, dz = (double) b.z - (double) a.z;
     const BoxDev& bx = nb.box;
     if (bx.periodic) {
@@ -869,31 +875,39 @@ __device__ __forceinline__ void close_pair_double(const NbDev& nb, const ListDev
         }
     }
     const double r2 = dx*dx + dy*dy + dz*dz;
-    const double invR = rsqrt(r2), invR2 = invR*invR, r = r2*invR;
-    const double qq = (double) a.w*(double) b.w;
-    double dEdR, e;
+    const double invR = rsqrt(r2), invR2 = invR*invR;
+    double dEdR, e = 0.0;
     if (METHOD == B200MD_NB_PME) {
-        const double ar = (double) nb.alpha*r;
-        const double ec = erfc(ar), ex = exp(-ar*ar);
-        dEdR = qq*invR*invR2*(ec + 1.12837916709551257390*ar*ex);
-        e = qq*invR*ec;
+        // qq/r^3 in double; the Ewald screening term  -qq alpha^3 g(alpha^2 r^2),  g(w) = (erf z - 2 z exp(-z^2)/sqrt(pi))/z^3,
+        // is a fifth of it at most for r < 0.32 nm and smooth: the fp32 rational fit of g (|err| 1.2e-7) leaves < 4e-5 kJ/mol/nm
+        const float w = nb.alpha*nb.alpha*(float) r2;
+        const double a3 = (double) nb.alpha*(double) nb.alpha*(double) nb.alpha;
+        if (w < PME_G_WMAX && !ENERGY) dEdR = qq*(invR*invR2 - a3*(double) ewald_g(w));
+        else {
+            const double ar = (double) nb.alpha*r2*invR;
+            const double ec = erfc(ar), ex = exp(-ar*ar);
+            dEdR = qq*invR*invR2*(ec + 1.12837916709551257390*ar*ex);
+            e = qq*invR*ec;
+        }
     }
     else if (METHOD == B200MD_NB_NOCUTOFF) { dEdR = qq*invR*invR2; e = qq*invR; }
     else { dEdR = qq*(invR*invR2 - 2.0*(double) nb.krf); e = qq*(invR + (double) nb.krf*r2 - (double) nb.crf); }
-    const double sig = (double) sa.x + (double) sb.x, eps = (double) sa.y*(double) sb.y;
+    const double sig = sa.x + sb.x, eps = sa.y*sb.y;
     const double s2 = sig*sig*invR2, s6 = s2*s2*s2;
     double ljF = eps*s6*invR2*(12.0*s6 - 6.0), ljE = eps*s6*(s6 - 1.0);
-    if (SWITCH && r > (double) nb.switchDist) {
-        const double swInv = 1.0/((double) nb.cutoff - (double) nb.switchDist);
-        const double x = (r - (double) nb.switchDist)*swInv;
-        const double sw = 1.0 + x*x*x*(-10.0 + x*(15.0 - x*6.0));
-        const double dsw = x*x*(-30.0 + x*(60.0 - x*30.0))*swInv;
-        ljF = sw*ljF - ljE*dsw*invR;
-        ljE *= sw;
+    if (SWITCH) {
+        const double r = r2*invR;
+        if (r > (double) nb.switchDist) {
+            const double swInv = 1.0/((double) nb.cutoff - (double) nb.switchDist);
+            const double x = (r - (double) nb.switchDist)*swInv;
+            const double sw = 1.0 + x*x*x*(-10.0 + x*(15.0 - x*6.0));
+            const double dsw = x*x*(-30.0 + x*(60.0 - x*30.0))*swInv;
+            ljF = sw*ljF - ljE*dsw*invR;
+            ljE *= sw;
+        }
     }
     dEdR += ljF;
     if (ENERGY) energyD += e + ljE;
-    const int ai = L.sorig[si], aj = L.sorig[sj];
     const long long fx = __double2ll_rn(dx*dEdR*B200MD_FORCE_SCALE), fy = __double2ll_rn(dy*dEdR*B200MD_FORCE_SCALE), fz = __double2ll_rn(dz*dEdR*B200MD_FORCE_SCALE);
     atomicAdd((unsigned long long*) &nb.force[ai], (unsigned long long) (-fx));
     atomicAdd((unsigned long long*) &nb.force[ai + nb.npad], (unsigned long long) (-fy));
@@ -1072,7 +1086,7 @@ __device__ __forceinline__ void pair_tiles_sw(const NbDev& nb, const ListDev& L,
 }
 
 template <bool ENERGY, int METHOD>
-__global__ void __launch_bounds__(256) k_pair(NbDev nb) {
+__global__ void __launch_bounds__(256, ENERGY ? 2 : 4) k_pair(NbDev nb) {
     float energy = 0.f;
     __shared__ unsigned short closeQ[8][CLOSE_QCAP];       // per-warp queue of close pairs: i lane | j slot << 5
     unsigned short* cq = closeQ[threadIdx.x >> 5];

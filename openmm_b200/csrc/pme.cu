@@ -6,6 +6,7 @@
 // reference GPU platforms (platforms/common/src/kernels/pme.cc:1-161, 506-606).  Order-5 cardinal B-splines,
 // forward-only stencil with periodic wrap, charges carry sqrt(ONE_4PI_EPS0).
 #include "engine.h"
+#include <algorithm>
 
 #define ORDER B200MD_PME_ORDER
 
@@ -56,12 +57,17 @@ __device__ __forceinline__ bool grid_index(const float4& p, const NbDev& nb, con
 
 // 8 lanes per atom, lane ix < 5 owns one x-plane of the 5x5x5 stencil (25 grid points): five times more independent
 // atomics / loads in flight per atom than the one-thread-per-atom form (both kernels are L2-latency bound at 24k atoms).
-__global__ void __launch_bounds__(128) k_pme_spread(NbDev nb, PmeDev pme) {
-    const int per = (nb.natoms + nb.world - 1)/nb.world;
+// Multi-GPU: every rank spreads the atoms it owns into its OWN full-size grid; k_grid_push then hands each x slab to its
+// owner.  The kernel waits for the position stores of the last step first (it runs on the reciprocal-space stream,
+// beside k_check_gather).
+__global__ void __launch_bounds__(128) k_pme_spread(NbDev nb, PmeDev pme, CommDev cd) {
+    comm_wait(cd, CH_POS, cd.world > 1 ? *cd.posNeed : 0ull);
     const int t = blockIdx.x*blockDim.x + threadIdx.x;
-    const int s = nb.rank*per + (t >> 3);
+    int s, end;
+    if (cd.world > 1) { s = cd.atomLo[cd.rank] + (t >> 3); end = cd.atomLo[cd.rank + 1]; }
+    else { const int per = (nb.natoms + nb.world - 1)/nb.world; s = nb.rank*per + (t >> 3); end = min(nb.natoms, (nb.rank+1)*per); }
     const int ix = t & 7;
-    if (s >= min(nb.natoms, (nb.rank+1)*per) || ix >= ORDER) return;
+    if (s >= end || ix >= ORDER) return;
     // USER order and the user-order (never lattice-shifted) coordinate: reciprocal space then does not depend on the
     // neighbour list at all and runs concurrently with the list rebuild; the fractional position is formed in double, so
     // the grid index/fraction is exact for fp32 inputs wherever the atom sits relative to the primary cell
@@ -94,10 +100,14 @@ __global__ void __launch_bounds__(128) k_pme_spread(NbDev nb, PmeDev pme) {
     }
 }
 
-__global__ void __launch_bounds__(128) k_pme_gather(NbDev nb, PmeDev pme) {
-    const int per = (nb.natoms + nb.world - 1)/nb.world;
-    const int s = nb.rank*per + blockIdx.x*blockDim.x + threadIdx.x;
-    if (s >= min(nb.natoms, (nb.rank+1)*per)) return;
+// Multi-GPU: the owner interpolates the forces of its atoms from the potential grid that the slab owners have written
+// into everybody's window (CH_POT).
+__global__ void __launch_bounds__(128) k_pme_gather(NbDev nb, PmeDev pme, CommDev cd) {
+    if (cd.world > 1) comm_wait(cd, CH_POT, *cd.epoch + 1ull);
+    int s, end;
+    if (cd.world > 1) { s = cd.atomLo[cd.rank] + blockIdx.x*blockDim.x + threadIdx.x; end = cd.atomLo[cd.rank + 1]; }
+    else { const int per = (nb.natoms + nb.world - 1)/nb.world; s = nb.rank*per + blockIdx.x*blockDim.x + threadIdx.x; end = min(nb.natoms, (nb.rank+1)*per); }
+    if (s >= end) return;
     const float4 p = nb.posq[s];
     if (p.w == 0.f) return;
     int idx[3];
@@ -108,6 +118,16 @@ __global__ void __launch_bounds__(128) k_pme_gather(NbDev nb, PmeDev pme) {
     bspline(fr[1], ty, dy);
     bspline(fr[2], tz, dz);
     float fx = 0.f, fy = 0.f, fz = 0.f;
+    // The derivative weights sum to zero along their axis, so a constant added to the potential changes no force: take the
+    // potential relative to the stencil's centre point.  |phi| is hundreds of kJ/mol/e, its variation over a stencil a few
+    // tens: the fp32 sums below lose ~10x less (ApoA1: reciprocal-space force error 3.8e-4 -> see profiles/r02_parity_probe).
+    float phi0;
+    {
+        int xc = idx[0] + 2; if (xc >= pme.nx) xc -= pme.nx;
+        int yc = idx[1] + 2; if (yc >= pme.ny) yc -= pme.ny;
+        int zc = idx[2] + 2; if (zc >= pme.nz) zc -= pme.nz;
+        phi0 = __ldg(pme.grid + ((size_t) xc*pme.ny + yc)*pme.nz + zc);
+    }
 #pragma unroll
     for (int ix = 0; ix < ORDER; ix++) {
         int xi = idx[0] + ix; if (xi >= pme.nx) xi -= pme.nx;
@@ -119,7 +139,7 @@ __global__ void __launch_bounds__(128) k_pme_gather(NbDev nb, PmeDev pme) {
 #pragma unroll
             for (int iz = 0; iz < ORDER; iz++) {
                 int zi = idx[2] + iz; if (zi >= pme.nz) zi -= pme.nz;
-                const float g = __ldg(row + zi);
+                const float g = __ldg(row + zi) - phi0;
                 sz += tz[iz]*g;
                 sdz += dz[iz]*g;
             }
@@ -171,13 +191,13 @@ void launch_pme_eterm(const NbDev& nb, const PmeDev& pme, cudaStream_t s) {
     k_pme_eterm<<<(unsigned) ((total + 255)/256), 256, 0, s>>>(nb, pme);
 }
 
-void launch_pme_spread(const NbDev& nb, const PmeDev& pme, cudaStream_t s) {
+void launch_pme_spread(const NbDev& nb, const PmeDev& pme, const CommDev& cd, cudaStream_t s) {
     cudaMemsetAsync(pme.gridFixed, 0, sizeof(long long)*(size_t) pme.nx*pme.ny*pme.nz, s);
-    const int per = (nb.natoms + nb.world - 1)/nb.world;
-    k_pme_spread<<<(per*8 + 127)/128, 128, 0, s>>>(nb, pme);
+    const int per = cd.world > 1 ? cd.atomLo[cd.rank + 1] - cd.atomLo[cd.rank] : (nb.natoms + nb.world - 1)/nb.world;
+    k_pme_spread<<<std::max(1, (per*8 + 127)/128), 128, 0, s>>>(nb, pme, cd);
 }
 
-void launch_pme_gather(const NbDev& nb, const PmeDev& pme, cudaStream_t s) {
-    const int per = (nb.natoms + nb.world - 1)/nb.world;
-    k_pme_gather<<<(per + 127)/128, 128, 0, s>>>(nb, pme);
+void launch_pme_gather(const NbDev& nb, const PmeDev& pme, const CommDev& cd, cudaStream_t s) {
+    const int per = cd.world > 1 ? cd.atomLo[cd.rank + 1] - cd.atomLo[cd.rank] : (nb.natoms + nb.world - 1)/nb.world;
+    k_pme_gather<<<std::max(1, (per + 127)/128), 128, 0, s>>>(nb, pme, cd);
 }
