@@ -10,6 +10,7 @@
 #include <map>
 #include <set>
 #include <dlfcn.h>
+#include <thread>
 
 static std::string g_create_error;
 
@@ -110,6 +111,12 @@ struct b200md_ctx {
     DevBuf<int4> angleAtoms, torsionAtoms, unitAtoms; DevBuf<double4> torsionParams, excParams;
     DevBuf<int> unitType; DevBuf<float4> unitParams;
     DevBuf<unsigned char> bondGroupDev, angGroupDev, torGroupDev;
+    // general constraint networks (CCMA, constraints.cu)
+    std::vector<int> ccmaCons;           // indices into conI/conJ/conD
+    DevBuf<int> ccCompCon, ccCompAtom, ccRowStart, ccCol, ccAtoms, ccAStart, ccACon;
+    DevBuf<int2> ccConAtoms; DevBuf<float> ccDist, ccRedMass, ccVal, ccDelta1, ccDelta2;
+    DevBuf<float4> ccRij, ccXold, ccXunc;
+    CcmaDev ccma{};
     NbDev nb{};
     PmeDev pme{};
     BondedDev bd{};
@@ -406,7 +413,7 @@ static void upload_params(b200md_ctx* c) {
         std::vector<double> qd(c->npad, 0.0); std::vector<double2> sd(c->npad, make_double2(0.0, 0.0));
         for (int i = 0; i < N; i++) { qd[i] = c->charge[i]*sk; sd[i] = make_double2(0.5*c->sigma[i], 2.0*std::sqrt(c->epsilon[i])); }
         c->chargeD.upload(qd); c->sigepsD.upload(sd);
-        c->nb.chargeD = c->chargeD.p; c->nb.sigepsD = c->sigepsD.p;
+        c->nb.chargeD = c->pmeOnly ? nullptr : c->chargeD.p; c->nb.sigepsD = c->sigepsD.p;     // stand-alone PME: the charges arrive with every call (posq.w)
     }
     // charges live in posq.w; keep positions
     std::vector<float4> p(c->npad);
@@ -431,11 +438,13 @@ static void upload_params(b200md_ctx* c) {
 // Integration units: SETTLE waters, X-H_n SHAKE clusters, free atoms.  Pure host function so that the plugin can run it
 // as a dry run from Platform::contextCreated (b200md_check_constraints) before anything is allocated.
 static bool classify_units(int N, const double* mass, const std::vector<int>& conI, const std::vector<int>& conJ, const std::vector<double>& conD,
-                           std::vector<int4>& ua2, std::vector<int>& ut2, std::vector<float4>& up2, std::string& err) {
+                           std::vector<int4>& ua2, std::vector<int>& ut2, std::vector<float4>& up2, std::string& err, std::vector<int>* ccmaCons = nullptr) {
     const int nc = (int) conI.size();
     std::vector<std::vector<std::pair<int, double> > > adj(N);
     for (int k = 0; k < nc; k++) {
         if (conI[k] < 0 || conI[k] >= N || conJ[k] < 0 || conJ[k] >= N || conI[k] == conJ[k]) { err = "constraint with an illegal particle index"; return false; }
+        if (mass[conI[k]] == 0 && mass[conJ[k]] == 0) continue;           // constraints between immovable particles are ignored (ReferenceConstraints.cpp:60)
+        if (mass[conI[k]] == 0 || mass[conJ[k]] == 0) { err = "A constraint cannot involve a massless particle"; return false; }      // ContextImpl.cpp:86-87
         adj[conI[k]].push_back(std::make_pair(conJ[k], conD[k]));
         adj[conJ[k]].push_back(std::make_pair(conI[k], conD[k]));
     }
@@ -477,11 +486,18 @@ static bool classify_units(int N, const double* mass, const std::vector<int>& co
         order.push_back(std::make_pair(a, (int) ua.size()));
         ua.push_back(make_int4(at[0], at[1], at[2], at[3])); ut.push_back(2); up.push_back(make_float4(dd[0], dd[1], dd[2], 0.f));
     }
+    // everything else is a general constraint network: CCMA (ReferenceConstraints.cpp:148-184).  Its atoms get no
+    // integration unit: k_ccma_step (constraints.cu) takes them through the step, one CTA per connected component.
+    std::vector<char> isCcma(N, 0);
+    for (int a = 0; a < N; a++) if (!assigned[a] && !adj[a].empty()) {
+        isCcma[a] = 1;
+    }
+    if (ccmaCons) {
+        ccmaCons->clear();
+        for (int k = 0; k < nc; k++) if ((isCcma[conI[k]] || isCcma[conJ[k]]) && mass[conI[k]] != 0) ccmaCons->push_back(k);
+    }
     for (int a = 0; a < N; a++) {
-        if (!assigned[a] && !adj[a].empty()) {
-            err = "unsupported constraint topology (only rigid 3-atom molecules and X-H_n clusters; general CCMA constraints are not implemented)";
-            return false;
-        }
+        if (isCcma[a]) continue;
         if (!assigned[a]) {
             order.push_back(std::make_pair(a, (int) ua.size()));
             ua.push_back(make_int4(a, -1, -1, -1)); ut.push_back(0); up.push_back(make_float4(0, 0, 0, 0));
@@ -496,11 +512,155 @@ static bool classify_units(int N, const double* mass, const std::vector<int>& co
 static void build_units(b200md_ctx* c) {
     std::vector<int4> ua2; std::vector<int> ut2; std::vector<float4> up2;
     std::string err;
-    if (!classify_units(c->natoms, c->mass.data(), c->conI, c->conJ, c->conD, ua2, ut2, up2, err)) throw std::runtime_error("B200 platform: " + err);
+    if (!classify_units(c->natoms, c->mass.data(), c->conI, c->conJ, c->conD, ua2, ut2, up2, err, &c->ccmaCons)) throw std::runtime_error("B200 platform: " + err);
     c->unitAtoms.upload(ua2); c->unitType.upload(ut2); c->unitParams.upload(up2);
     c->hUnitAtoms = ua2;
     c->units.nunits = (int) ua2.size();
     c->units.unitAtoms = c->unitAtoms.p; c->units.unitType = c->unitType.p; c->units.unitParams = c->unitParams.p;
+}
+
+// ---------------------------------------------------------------- CCMA setup (host)
+// Coupling matrix exactly as ReferenceCCMAAlgorithm's constructor builds it (ReferenceCCMAAlgorithm.cpp:73-135: constraints
+// j, k that share an atom couple with scale * cos(angle), the angle from a third constraint that closes the triangle or
+// else from a HarmonicAngleForce term); its inverse is then APPROXIMATED column by column from the constraints within three
+// bonds of the column's constraint (a dense solve of ~50-100 unknowns) instead of the reference's global sparse QR
+// (:137-190, QUERN): the inverse decays by ~3x per bond, entries below the reference's cut-off 0.02 (ReferenceConstraints.cpp:183)
+// are dropped either way, and CCMA only needs an approximate inverse -- it iterates to the tolerance.
+static void build_ccma(b200md_ctx* c) {
+    const int nc = (int) c->ccmaCons.size();
+    c->ccma = CcmaDev{};
+    if (nc == 0) return;
+    require(!c->p2p && c->world == 1, "general (CCMA) constraint networks are not supported in multi-GPU runs");
+    const int N = c->natoms;
+    // ---- components ----
+    std::vector<int> parent(N);
+    for (int i = 0; i < N; i++) parent[i] = i;
+    auto find = [&](int x) { while (parent[x] != x) { parent[x] = parent[parent[x]]; x = parent[x]; } return x; };
+    for (int k : c->ccmaCons) { int a = find(c->conI[k]), b = find(c->conJ[k]); if (a != b) parent[std::max(a, b)] = std::min(a, b); }
+    std::vector<int> order(nc);
+    for (int k = 0; k < nc; k++) order[k] = k;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return find(c->conI[c->ccmaCons[a]]) < find(c->conI[c->ccmaCons[b]]); });
+    std::vector<int2> conAtoms(nc); std::vector<float> dist(nc), redMass(nc); std::vector<double> distD(nc);
+    std::vector<int> compCon(1, 0), compOfCon(nc);
+    for (int k = 0; k < nc; k++) {
+        const int src = c->ccmaCons[order[k]];
+        conAtoms[k] = make_int2(c->conI[src], c->conJ[src]);
+        distD[k] = c->conD[src]; dist[k] = (float) distD[k];
+        redMass[k] = (float) (0.5/(1.0/c->mass[conAtoms[k].x] + 1.0/c->mass[conAtoms[k].y]));
+        if (k > 0 && find(conAtoms[k].x) != find(conAtoms[k-1].x)) compCon.push_back(k);
+        compOfCon[k] = (int) compCon.size() - 1;
+    }
+    compCon.push_back(nc);
+    const int ncomp = (int) compCon.size() - 1;
+    // ---- atoms per component, atom -> constraints ----
+    std::vector<std::vector<int> > atomCons(N);
+    for (int k = 0; k < nc; k++) { atomCons[conAtoms[k].x].push_back(k + 1); atomCons[conAtoms[k].y].push_back(-(k + 1)); }
+    std::vector<int> atoms, compAtom(1, 0), aStart(1, 0), aCon;
+    for (int cidx = 0; cidx < ncomp; cidx++) {
+        std::set<int> as;
+        for (int k = compCon[cidx]; k < compCon[cidx+1]; k++) { as.insert(conAtoms[k].x); as.insert(conAtoms[k].y); }
+        for (int a : as) { atoms.push_back(a); aCon.insert(aCon.end(), atomCons[a].begin(), atomCons[a].end()); aStart.push_back((int) aCon.size()); }
+        compAtom.push_back((int) atoms.size());
+    }
+    // ---- coupling matrix ----
+    std::vector<std::vector<int> > atomAngles(N);
+    for (size_t i = 0; i < c->angJ.size(); i++) atomAngles[c->angJ[i]].push_back((int) i);
+    std::vector<std::vector<std::pair<int, double> > > M(nc);
+    auto consOf = [&](int a) { std::vector<int> v; for (int code : atomCons[a]) v.push_back(std::abs(code) - 1); return v; };
+    for (int j = 0; j < nc; j++) {
+        const int j0 = conAtoms[j].x, j1 = conAtoms[j].y;
+        const double w0 = 1.0/c->mass[j0], w1 = 1.0/c->mass[j1];
+        std::set<int> nbrs;
+        for (int k : consOf(j0)) nbrs.insert(k);
+        for (int k : consOf(j1)) nbrs.insert(k);
+        for (int k : nbrs) {
+            if (k == j) { M[j].push_back(std::make_pair(j, 1.0)); continue; }
+            const int k0 = conAtoms[k].x, k1 = conAtoms[k].y;
+            int aa, ab, ac; double scale;
+            if (j0 == k0) { aa = j1; ab = j0; ac = k1; scale = w0/(w0+w1); }
+            else if (j1 == k1) { aa = j0; ab = j1; ac = k0; scale = w1/(w0+w1); }
+            else if (j0 == k1) { aa = j1; ab = j0; ac = k0; scale = w0/(w0+w1); }
+            else if (j1 == k0) { aa = j0; ab = j1; ac = k1; scale = w1/(w0+w1); }
+            else continue;
+            bool found = false;
+            for (int other : consOf(aa))
+                if (conAtoms[other].x == ac || conAtoms[other].y == ac) {
+                    const double d1 = distD[j], d2 = distD[k], d3 = distD[other];
+                    M[j].push_back(std::make_pair(k, scale*(d1*d1 + d2*d2 - d3*d3)/(2.0*d1*d2)));
+                    found = true;
+                    break;
+                }
+            if (!found)
+                for (int cand : atomAngles[ab])
+                    if ((c->angI[cand] == aa && c->angK[cand] == ac) || (c->angK[cand] == aa && c->angI[cand] == ac)) {
+                        M[j].push_back(std::make_pair(k, scale*std::cos(c->angT0[cand])));
+                        break;
+                    }
+        }
+    }
+    // ---- approximate inverse, column by column ----
+    std::vector<std::vector<std::pair<int, float> > > inv(nc);      // inv[row] = (col, value)
+    std::vector<std::vector<std::pair<int, float> > > colOut(nc);   // per column: (row, value), filled in parallel
+    auto solve_columns = [&](int begin, int end) {
+        std::vector<int> S, localOf(nc, -1);
+        std::vector<double> A, x;
+        for (int i = begin; i < end; i++) {
+            // constraints within 3 bonds of constraint i (breadth first over "shares an atom"), at most 160
+            S.assign(1, i); localOf[i] = 0;
+            size_t head = 0; int depthEnd = 1, depth = 0;
+            while (head < S.size() && depth < 3 && S.size() < 160) {
+                const int k = S[head++];
+                for (auto& el : M[k]) if (localOf[el.first] < 0 && S.size() < 160) { localOf[el.first] = (int) S.size(); S.push_back(el.first); }
+                if ((int) head == depthEnd) { depth++; depthEnd = (int) S.size(); }
+            }
+            const int n = (int) S.size();
+            A.assign((size_t) n*n, 0.0); x.assign(n, 0.0); x[0] = 1.0;
+            for (int r = 0; r < n; r++) for (auto& el : M[S[r]]) if (localOf[el.first] >= 0) A[(size_t) r*n + localOf[el.first]] = el.second;
+            for (int p = 0; p < n; p++) {              // Gaussian elimination with partial pivoting
+                int piv = p;
+                for (int r = p+1; r < n; r++) if (std::fabs(A[(size_t) r*n + p]) > std::fabs(A[(size_t) piv*n + p])) piv = r;
+                if (piv != p) { for (int q = 0; q < n; q++) std::swap(A[(size_t) p*n + q], A[(size_t) piv*n + q]); std::swap(x[p], x[piv]); }
+                const double d = A[(size_t) p*n + p];
+                if (d == 0.0) continue;
+                for (int r = p+1; r < n; r++) {
+                    const double f = A[(size_t) r*n + p]/d;
+                    if (f == 0.0) continue;
+                    for (int q = p; q < n; q++) A[(size_t) r*n + q] -= f*A[(size_t) p*n + q];
+                    x[r] -= f*x[p];
+                }
+            }
+            for (int p = n-1; p >= 0; p--) {
+                double sacc = x[p];
+                for (int q = p+1; q < n; q++) sacc -= A[(size_t) p*n + q]*x[q];
+                x[p] = (A[(size_t) p*n + p] != 0.0) ? sacc/A[(size_t) p*n + p] : 0.0;
+            }
+            for (int r = 0; r < n; r++) {
+                const int j = S[r];
+                const double value = x[r]*distD[i]/distD[j];            // ReferenceCCMAAlgorithm.cpp:177
+                if (std::fabs(value) > 0.02) colOut[i].push_back(std::make_pair(j, (float) value));
+                localOf[j] = -1;
+            }
+        }
+    };
+    {
+        const int nthreads = std::max(1, std::min(16, (int) std::thread::hardware_concurrency()));
+        std::vector<std::thread> pool;
+        for (int t = 0; t < nthreads; t++) pool.emplace_back(solve_columns, (int) ((long long) nc*t/nthreads), (int) ((long long) nc*(t+1)/nthreads));
+        for (auto& th : pool) th.join();
+    }
+    for (int i = 0; i < nc; i++) for (auto& el : colOut[i]) inv[el.first].push_back(std::make_pair(i, el.second));
+    std::vector<int> rowStart(1, 0), col; std::vector<float> val;
+    for (int j = 0; j < nc; j++) { for (auto& el : inv[j]) { col.push_back(el.first); val.push_back(el.second); } rowStart.push_back((int) col.size()); }
+    // ---- device ----
+    c->ccCompCon.upload(compCon); c->ccCompAtom.upload(compAtom); c->ccConAtoms.upload(conAtoms); c->ccDist.upload(dist); c->ccRedMass.upload(redMass);
+    c->ccRowStart.upload(rowStart); c->ccCol.upload(col); c->ccVal.upload(val); c->ccAtoms.upload(atoms); c->ccAStart.upload(aStart); c->ccACon.upload(aCon);
+    c->ccRij.alloc(nc); c->ccDelta1.alloc(nc); c->ccDelta2.alloc(nc); c->ccXold.alloc(c->npad); c->ccXunc.alloc(c->npad);
+    CcmaDev& cc = c->ccma;
+    cc.ncomp = ncomp; cc.ncon = nc; cc.natomsC = (int) atoms.size();
+    cc.compConStart = c->ccCompCon.p; cc.compAtomStart = c->ccCompAtom.p; cc.conAtoms = c->ccConAtoms.p; cc.conDist = c->ccDist.p; cc.conRedMass = c->ccRedMass.p;
+    cc.rowStart = c->ccRowStart.p; cc.col = c->ccCol.p; cc.val = c->ccVal.p; cc.atoms = c->ccAtoms.p; cc.aStart = c->ccAStart.p; cc.aCon = c->ccACon.p;
+    cc.rij = c->ccRij.p; cc.delta1 = c->ccDelta1.p; cc.delta2 = c->ccDelta2.p; cc.xold = c->ccXold.p; cc.xunc = c->ccXunc.p;
+    cc.maxIter = 150;                   // ReferenceCCMAAlgorithm.cpp:55
 }
 
 // dry run of the constraint classification (no context, no device): 0 = every constraint is supported
@@ -723,7 +883,7 @@ extern "C" int b200md_finalize(b200md_ctx* ctx) {
     if (c->p2p) setup_window(c);
     nb.useRational = getenv("B200MD_PAIR_RATIONAL") ? atoi(getenv("B200MD_PAIR_RATIONAL")) : 0;
     nb.pairDynamic = getenv("B200MD_PAIR_DYNAMIC") ? atoi(getenv("B200MD_PAIR_DYNAMIC")) : 0;
-    { const double cc = getenv("B200MD_CLOSE_NM") ? atof(getenv("B200MD_CLOSE_NM")) : 0.32; nb.closeCut2 = (float) (cc*cc); }
+    { const double cc = getenv("B200MD_CLOSE_NM") ? atof(getenv("B200MD_CLOSE_NM")) : 0.36; nb.closeCut2 = (float) (cc*cc); }
     nb.packCull = getenv("B200MD_BT_PACK") ? atoi(getenv("B200MD_BT_PACK")) : 1;
     // ---- state arrays ----
     c->posq.alloc(NP); c->posq.zero(); c->velm.alloc(NP); c->velm.zero();
@@ -811,6 +971,7 @@ extern "C" int b200md_finalize(b200md_ctx* ctx) {
     }
     upload_params(c);
     build_units(c);
+    build_ccma(c);
     if (c->p2p) {
         setup_ownership(c);
         if (nb.method == B200MD_NB_PME) {
@@ -1326,6 +1487,7 @@ static int enqueue_step(b200md_ctx* c) {
     in.cmEveryStep = (c->cmFreq == 1) ? 1 : 0;
     in.cmScratch = c->cmScratch.p;
     in.blocksDone = c->blocksDone.p;
+    if (c->ccma.ncomp > 0) { launch_ccma_step(c->nb, c->ccma, in, c->stream); launches += 1; }      // before k_integrate: its last block advances the step counter
     launch_integrate(c->nb, c->units, in, c->cd, c->stream); launches += 1;
     return launches;
 }
@@ -1334,6 +1496,7 @@ extern "C" int b200md_integrate_only(b200md_ctx* ctx) {
     API_BEGIN(ctx)
     ctx->stepStateValid = false;
     require(ctx->finalized && ctx->haveIntegrator, "integrate before finalize / set_integrator");
+    if (ctx->ccma.ncomp > 0) launch_ccma_step(ctx->nb, ctx->ccma, ctx->integ, ctx->stream);
     launch_integrate(ctx->nb, ctx->units, ctx->integ, ctx->cd, ctx->stream);
     ctx->kernelLaunches += 2;
     ctx->velStale = ctx->p2p;
@@ -1426,6 +1589,7 @@ extern "C" int b200md_kinetic_energy(b200md_ctx* ctx, double* ke) {
     sync_positions(ctx); sync_velocities(ctx);
     CUDA_CHECK(cudaMemsetAsync(ctx->energy.p + EN_KE, 0, sizeof(double), ctx->stream));
     launch_kinetic_energy(ctx->nb, ctx->units, ctx->integ, shift, ctx->stream);
+    launch_ccma_kinetic(ctx->nb, ctx->ccma, shift, 1e-4f, ctx->stream);
     ctx->kernelLaunches++;
     CUDA_CHECK(cudaMemcpyAsync(ke, ctx->energy.p + EN_KE, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     check_flags(ctx);
@@ -1435,6 +1599,7 @@ extern "C" int b200md_apply_constraints(b200md_ctx* ctx, double tol) {
     API_BEGIN(ctx)
     sync_positions(ctx);
     launch_constrain_positions(ctx->nb, ctx->units, (float) tol, ctx->stream);
+    launch_ccma_apply(ctx->nb, ctx->ccma, false, (float) tol, ctx->stream);
     ctx->kernelLaunches++;
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     API_END(ctx)
@@ -1444,6 +1609,7 @@ extern "C" int b200md_apply_velocity_constraints(b200md_ctx* ctx, double tol) {
     ctx->stepStateValid = false;
     sync_positions(ctx); sync_velocities(ctx);
     launch_constrain_velocities(ctx->nb, ctx->units, (float) tol, ctx->stream);
+    launch_ccma_apply(ctx->nb, ctx->ccma, true, (float) tol, ctx->stream);
     ctx->kernelLaunches++;
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     API_END(ctx)

@@ -286,6 +286,53 @@ __device__ __forceinline__ long long float_to_fixed(float f) {           // |f| 
 }
 #endif
 
+// General constraint networks (CCMA, constraints.cu): one CTA per connected component of the constraint graph.
+struct CcmaDev {
+    int ncomp, ncon, natomsC;
+    const int* compConStart;     // [ncomp+1] constraints of a component are contiguous
+    const int* compAtomStart;    // [ncomp+1] so are its atoms (positions in `atoms`)
+    const int2* conAtoms;        // [ncon] user atom indices
+    const float* conDist;        // [ncon]
+    const float* conRedMass;     // [ncon] 0.5/(1/mi + 1/mj)
+    const int* rowStart; const int* col; const float* val;      // approximate inverse of the coupling matrix, CSR over constraints
+    const int* atoms;            // [natomsC] user atom index
+    const int* aStart;           // [natomsC+1] constraints of an atom: +(k+1) if it is the first atom of constraint k, -(k+1) if the second
+    const int* aCon;
+    float4* rij; float* delta1; float* delta2;                   // [ncon] scratch
+    float4* xold; float4* xunc;                                  // [npad] scratch (user atom order)
+    int maxIter;
+};
+
+#ifdef __CUDACC__
+// ---------------------------------------------------------------- Philox4x32-10 (Salmon et al., SC'11)
+__device__ __forceinline__ uint4 philox(uint4 c, uint2 k) {
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        const unsigned int hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u*c.x;
+        const unsigned int hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u*c.z;
+        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+        k.x += 0x9E3779B9u; k.y += 0xBB67AE85u;
+    }
+    return c;
+}
+
+// three independent N(0,1) for (atom, step)
+__device__ __forceinline__ float3 gauss3(unsigned int seed, int atom, unsigned long long step) {
+    uint4 r = philox(make_uint4((unsigned int) atom, (unsigned int) step, (unsigned int) (step >> 32), 0x5eed5eedu), make_uint2(seed, 0xb200b200u));
+    const float u1 = ((r.x >> 8) + 1u)*(1.0f/16777216.0f);      // (0,1]
+    const float u2 = (r.y >> 8)*(1.0f/16777216.0f);
+    const float u3 = ((r.z >> 8) + 1u)*(1.0f/16777216.0f);
+    const float u4 = (r.w >> 8)*(1.0f/16777216.0f);
+    const float m1 = sqrtf(-2.0f*logf(u1)), m2 = sqrtf(-2.0f*logf(u3));
+    float s1, c1, s2, c2;
+    sincospif(2.0f*u2, &s1, &c1);
+    sincospif(2.0f*u4, &s2, &c2);
+    (void) s2;
+    return make_float3(m1*c1, m1*s1, m2*c2);
+}
+
+#endif
+
 // ---- launchers (defined in the .cu files) ----
 void launch_check_displacement(const NbDev& nb, const CommDev& cd, cudaStream_t s);
 bool list_build_merged();        // list build = 2 gated launches (k_list_prep with grid barriers + k_build_tiles); B200MD_LIST_MERGED=0: 7
@@ -318,4 +365,7 @@ void launch_constrain_positions(const NbDev& nb, const UnitDev& units, float tol
 void launch_constrain_velocities(const NbDev& nb, const UnitDev& units, float tol, cudaStream_t s);
 void launch_kinetic_energy(const NbDev& nb, const UnitDev& units, const IntegDev& integ, float shiftDt, cudaStream_t s);
 void launch_remove_cm(const NbDev& nb, double* scratch, cudaStream_t s);
+void launch_ccma_step(const NbDev& nb, const CcmaDev& cc, const IntegDev& in, cudaStream_t s);      // before launch_integrate in a step
+void launch_ccma_apply(const NbDev& nb, const CcmaDev& cc, bool velocities, float tol, cudaStream_t s);
+void launch_ccma_kinetic(const NbDev& nb, const CcmaDev& cc, float shiftDt, float tol, cudaStream_t s);
 void launch_cm_prime(const NbDev& nb, const IntegDev& integ, const CommDev& cd, cudaStream_t s);

@@ -11,33 +11,6 @@
 #include <algorithm>
 #include "../../include/b200md.h"
 
-// ---------------------------------------------------------------- Philox4x32-10 (Salmon et al., SC'11)
-__device__ __forceinline__ uint4 philox(uint4 c, uint2 k) {
-#pragma unroll
-    for (int r = 0; r < 10; r++) {
-        const unsigned int hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u*c.x;
-        const unsigned int hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u*c.z;
-        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
-        k.x += 0x9E3779B9u; k.y += 0xBB67AE85u;
-    }
-    return c;
-}
-
-// three independent N(0,1) for (atom, step)
-__device__ __forceinline__ float3 gauss3(unsigned int seed, int atom, unsigned long long step) {
-    uint4 r = philox(make_uint4((unsigned int) atom, (unsigned int) step, (unsigned int) (step >> 32), 0x5eed5eedu), make_uint2(seed, 0xb200b200u));
-    const float u1 = ((r.x >> 8) + 1u)*(1.0f/16777216.0f);      // (0,1]
-    const float u2 = (r.y >> 8)*(1.0f/16777216.0f);
-    const float u3 = ((r.z >> 8) + 1u)*(1.0f/16777216.0f);
-    const float u4 = (r.w >> 8)*(1.0f/16777216.0f);
-    const float m1 = sqrtf(-2.0f*logf(u1)), m2 = sqrtf(-2.0f*logf(u3));
-    float s1, c1, s2, c2;
-    sincospif(2.0f*u2, &s1, &c1);
-    sincospif(2.0f*u4, &s2, &c2);
-    (void) s2;
-    return make_float3(m1*c1, m1*s1, m2*c2);
-}
-
 struct V3 { float x, y, z; };
 __device__ __forceinline__ V3 operator+(V3 a, V3 b) { return {a.x+b.x, a.y+b.y, a.z+b.z}; }
 __device__ __forceinline__ V3 operator-(V3 a, V3 b) { return {a.x-b.x, a.y-b.y, a.z-b.z}; }

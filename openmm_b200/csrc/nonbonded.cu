@@ -845,7 +845,7 @@ __device__ __forceinline__ float wrap_rel(float p, float c, double L, double inv
 // fp32 pair arithmetic has a relative error of ~1.5e-7 and the coordinates relative to the block centre are rounded to
 // ~3e-8 nm.  On a hydrogen-bonded pair (|F| ~ 1,500 kJ/mol/nm, dF/dr ~ 16,000) that is 2-5e-4 kJ/mol/nm of absolute error
 // on BOTH atoms, which is what an atom with a small net force (a lipid tail atom next to a water, say) is measured
-// against in the reference's 1e-4 criterion.  Pairs closer than nb.closeCut (default 0.32 nm, ~4 % of the pairs inside the
+// against in the reference's 1e-4 criterion.  Pairs closer than nb.closeCut (default 0.36 nm, ~6 % of the pairs inside the
 // cutoff) are therefore taken out of the fp32 loop: the lane notes (i lane, j slot) in a per-warp queue, and after the 32
 // rotations the warp evaluates the queued pairs in double from the EXACT user coordinates and adds the forces to the
 // fixed-point buffer directly.  ReferenceLJCoulombIxn.cpp:388-447 (PME) / :559-575 (cutoff) / calculateOneIxn restated.

@@ -11,13 +11,18 @@
 #define ORDER B200MD_PME_ORDER
 
 // theta / dtheta for one axis, the recursion of pme_update_bsplines (ReferencePME.cpp:274-327)
-__device__ __forceinline__ void bspline(float dr, float* data, float* ddata) {
+// The weights are formed in DOUBLE: every charge interacts with its own spread image through them (a term of
+// q^2 x ~25 x 138 kJ/mol/nm that only cancels if spreading and interpolation use the same, accurate weights); fp32 weights
+// left a reciprocal-space force error of ~4e-4 kJ/mol/nm on every system, whatever the precision of the FFT
+// (profiles/r02_parity_probe.md).  ~75 DFMA per atom and axis: nothing against the grid traffic.
+typedef double wreal;
+__device__ __forceinline__ void bspline(wreal dr, wreal* data, wreal* ddata) {
     data[ORDER-1] = 0.f;
     data[1] = dr;
     data[0] = 1.f - dr;
 #pragma unroll
     for (int k = 3; k < ORDER; k++) {
-        const float div = 1.f/(k - 1.f);
+        const wreal div = 1.f/(k - 1.f);
         data[k-1] = div*dr*data[k-2];
 #pragma unroll
         for (int l = 1; l < k-1; l++)
@@ -27,7 +32,7 @@ __device__ __forceinline__ void bspline(float dr, float* data, float* ddata) {
     ddata[0] = -data[0];
 #pragma unroll
     for (int k = 1; k < ORDER; k++) ddata[k] = data[k-1] - data[k];
-    const float div = 1.f/(ORDER - 1);
+    const wreal div = 1.f/(ORDER - 1);
     data[ORDER-1] = div*dr*data[ORDER-2];
 #pragma unroll
     for (int l = 1; l < ORDER-1; l++)
@@ -39,7 +44,7 @@ __device__ __forceinline__ void bspline(float dr, float* data, float* ddata) {
 // B-spline argument keeps full fp32 precision on 128-point grids
 // returns false for a non-finite coordinate (the atom is skipped; the NaN shows up in the integrator instead of
 // as an out-of-bounds grid access)
-__device__ __forceinline__ bool grid_index(const float4& p, const NbDev& nb, const PmeDev& pme, int* idx, float* frac) {
+__device__ __forceinline__ bool grid_index(const float4& p, const NbDev& nb, const PmeDev& pme, int* idx, wreal* frac) {
     const double* R = nb.box.recip;
     const int n[3] = {pme.nx, pme.ny, pme.nz};
     bool ok = true;
@@ -49,7 +54,7 @@ __device__ __forceinline__ bool grid_index(const float4& p, const NbDev& nb, con
         t = (t - floor(t))*n[d];
         ok = ok && (t >= 0.0) && (t <= (double) n[d]);
         int ti = (int) t;
-        frac[d] = (float) (t - ti);
+        frac[d] = (wreal) (t - ti);
         idx[d] = (ti >= n[d]) ? ti - n[d] : ti;
     }
     return ok;
@@ -74,28 +79,27 @@ __global__ void __launch_bounds__(128) k_pme_spread(NbDev nb, PmeDev pme, CommDe
     const float4 p = nb.posq[s];
     if (p.w == 0.f) return;
     int idx[3];
-    float fr[3];
+    wreal fr[3];
     if (!grid_index(p, nb, pme, idx, fr)) return;
-    float tx[ORDER], ty[ORDER], tz[ORDER], dd[ORDER];
+    wreal tx[ORDER], ty[ORDER], tz[ORDER], dd[ORDER];
     bspline(fr[0], tx, dd);
     bspline(fr[1], ty, dd);
     bspline(fr[2], tz, dd);
-    float txi = tx[0];
+    wreal txi = tx[0];
 #pragma unroll
     for (int k = 1; k < ORDER; k++) if (ix == k) txi = tx[k];
     int xi = idx[0] + ix; if (xi >= pme.nx) xi -= pme.nx;
-    const float qx = p.w*txi;
+    const wreal qx = (nb.chargeD != nullptr ? nb.chargeD[s] : (double) p.w)*txi;
 #pragma unroll
     for (int iy = 0; iy < ORDER; iy++) {
         int yi = idx[1] + iy; if (yi >= pme.ny) yi -= pme.ny;
-        const float qxy = qx*ty[iy];
+        const wreal qxy = qx*ty[iy];
         long long* row = pme.gridFixed + ((size_t) xi*pme.ny + yi)*pme.nz;
 #pragma unroll
         for (int iz = 0; iz < ORDER; iz++) {
             int zi = idx[2] + iz; if (zi >= pme.nz) zi -= pme.nz;
-            // integer accumulation: the grid (hence every force) is independent of the order of the atomics.
-            // |q theta theta theta| < 32: one F2I.S32 at scale 2^26, widened and shifted to the grid's 2^32 scale
-            atomicAdd((unsigned long long*) (row + zi), (unsigned long long) ((long long) __float2int_rn(qxy*tz[iz]*67108864.0f) << 6));
+            // integer accumulation: the grid (hence every force) is independent of the order of the atomics
+            atomicAdd((unsigned long long*) (row + zi), (unsigned long long) __double2ll_rn(qxy*tz[iz]*4294967296.0));
         }
     }
 }
@@ -111,13 +115,13 @@ __global__ void __launch_bounds__(128) k_pme_gather(NbDev nb, PmeDev pme, CommDe
     const float4 p = nb.posq[s];
     if (p.w == 0.f) return;
     int idx[3];
-    float fr[3];
+    wreal fr[3];
     if (!grid_index(p, nb, pme, idx, fr)) return;
-    float tx[ORDER], ty[ORDER], tz[ORDER], dx[ORDER], dy[ORDER], dz[ORDER];
+    wreal tx[ORDER], ty[ORDER], tz[ORDER], dx[ORDER], dy[ORDER], dz[ORDER];
     bspline(fr[0], tx, dx);
     bspline(fr[1], ty, dy);
     bspline(fr[2], tz, dz);
-    float fx = 0.f, fy = 0.f, fz = 0.f;
+    wreal fx = 0.f, fy = 0.f, fz = 0.f;
     // The derivative weights sum to zero along their axis, so a constant added to the potential changes no force: take the
     // potential relative to the stencil's centre point.  |phi| is hundreds of kJ/mol/e, its variation over a stencil a few
     // tens: the fp32 sums below lose ~10x less (ApoA1: reciprocal-space force error 3.8e-4 -> see profiles/r02_parity_probe).
@@ -135,7 +139,7 @@ __global__ void __launch_bounds__(128) k_pme_gather(NbDev nb, PmeDev pme, CommDe
         for (int iy = 0; iy < ORDER; iy++) {
             int yi = idx[1] + iy; if (yi >= pme.ny) yi -= pme.ny;
             const real* row = pme.grid + ((size_t) xi*pme.ny + yi)*pme.nz;
-            float sz = 0.f, sdz = 0.f;
+            wreal sz = 0.f, sdz = 0.f;
 #pragma unroll
             for (int iz = 0; iz < ORDER; iz++) {
                 int zi = idx[2] + iz; if (zi >= pme.nz) zi -= pme.nz;
@@ -150,7 +154,7 @@ __global__ void __launch_bounds__(128) k_pme_gather(NbDev nb, PmeDev pme, CommDe
     }
     // ReferencePME.cpp:708-711 (triclinic-aware)
     const double* R = nb.box.recip;
-    const double q = p.w;
+    const double q = nb.chargeD != nullptr ? nb.chargeD[s] : (double) p.w;
     const double gx = (double) fx*pme.nx, gy = (double) fy*pme.ny, gz = (double) fz*pme.nz;
     const double Fx = -q*(gx*R[0]);
     const double Fy = -q*(gx*R[3] + gy*R[4]);
