@@ -885,6 +885,12 @@ extern "C" int b200md_finalize(b200md_ctx* ctx) {
     nb.pairDynamic = getenv("B200MD_PAIR_DYNAMIC") ? atoi(getenv("B200MD_PAIR_DYNAMIC")) : 0;
     { const double cc = getenv("B200MD_CLOSE_NM") ? atof(getenv("B200MD_CLOSE_NM")) : 0.36; nb.closeCut2 = (float) (cc*cc); }
     nb.packCull = getenv("B200MD_BT_PACK") ? atoi(getenv("B200MD_BT_PACK")) : 1;
+    // SM partition between the tile kernel and the reciprocal-space chain (B200MD_PME_SMS=k reserves k SMs; 0 = off)
+    for (int w = 0; w < 4; w++) nb.pmeSmMask[w] = 0ull;
+    if (c->nbdesc.method == B200MD_NB_PME && !c->pmeOnly && c->overlapPme) {
+        const int want = getenv("B200MD_PME_SMS") ? atoi(getenv("B200MD_PME_SMS")) : 0;
+        if (want > 0 && choose_pme_sms(want, nb.pmeSmMask) > 0) nb.pairDynamic = 2;
+    }
     // ---- state arrays ----
     c->posq.alloc(NP); c->posq.zero(); c->velm.alloc(NP); c->velm.zero();
     c->refPos.alloc(NP); c->refPos.zero(); c->atomShift.alloc(NP); c->sigeps.alloc(NP);
@@ -1731,6 +1737,7 @@ extern "C" int b200md_time_phase(b200md_ctx* ctx, int phase, int reps, double* m
             CUDA_CHECK(cudaMemcpyAsync(c->velm.p, saveVel.p, sizeof(float4)*c->npad, cudaMemcpyDeviceToDevice, s));
         }
         if (phase == 5) CUDA_CHECK(cudaMemcpyAsync(&c->counters.p[CT_REBUILD], &one, sizeof(int), cudaMemcpyHostToDevice, s));
+        if (phase == 0) CUDA_CHECK(cudaMemsetAsync(&c->counters.p[CT_CURSOR], 0, sizeof(int), s));      // the dynamic tile schedule starts from tile 0
         CUDA_CHECK(cudaEventRecord(e0, s));
         switch (phase) {
             case 0: launch_pair(nbv, false, s); break;

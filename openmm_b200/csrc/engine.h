@@ -126,6 +126,10 @@ struct NbDev {
     unsigned long long condAsync;   // second IF node: build of the successor list on a side stream
     int packCull;                // k_build_tiles: exact cull on full warps (B200MD_BT_PACK)
     int pairDynamic;             // tile kernel fetches tiles from a cursor instead of a static stride
+    // SM partition: the tile kernel's CTAs that land on an SM whose bit is set here return at once, so those SMs stay free for
+    // the reciprocal-space chain (spread -> FFT -> gather) that runs beside it; the other CTAs (one persistent wave) share ALL
+    // tiles through the cursor.  All zero: no partition.
+    unsigned long long pmeSmMask[4];
     float closeCut2;             // pairs closer than this (squared) are evaluated in double from the exact coordinates (0: off)
     int useRational;             // B200MD_PAIR_RATIONAL=1: rational Ewald kernel in the force-only tile loop (1 MUFU less, lower accuracy)
 };
@@ -339,6 +343,7 @@ bool list_build_merged();        // list build = 2 gated launches (k_list_prep w
 void launch_list_build(const NbDev& nb, cudaStream_t s, int mode = 0);   // all list kernels, gated on counters[CT_REBUILD] (mode 0) or counters[CT_SOFT] (mode 1)
 void launch_pair(const NbDev& nb, bool energy, cudaStream_t s);
 void launch_count_pairs(const NbDev& nb, cudaStream_t s);
+int choose_pme_sms(int reserve, unsigned long long mask[4]);     // SM partition of the tile kernel (NbDev::pmeSmMask)
 int  list_build_launch_count();
 
 void launch_pme_eterm(const NbDev& nb, const PmeDev& pme, cudaStream_t s);

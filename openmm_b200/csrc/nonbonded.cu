@@ -1087,6 +1087,12 @@ __device__ __forceinline__ void pair_tiles_sw(const NbDev& nb, const ListDev& L,
 
 template <bool ENERGY, int METHOD>
 __global__ void __launch_bounds__(256, ENERGY ? 2 : 4) k_pair(NbDev nb) {
+    if (nb.pairDynamic == 2) {
+        // SM partition (launch_pair_m): this SM is reserved for the reciprocal-space kernels
+        unsigned int smid;
+        asm("mov.u32 %0, %%smid;" : "=r"(smid));
+        if ((nb.pmeSmMask[(smid >> 6) & 3] >> (smid & 63)) & 1ull) return;
+    }
     float energy = 0.f;
     __shared__ unsigned short closeQ[8][CLOSE_QCAP];       // per-warp queue of close pairs: i lane | j slot << 5
     unsigned short* cq = closeQ[threadIdx.x >> 5];
@@ -1123,12 +1129,44 @@ static void launch_pair_m(const NbDev& nb, cudaStream_t s) {
     // let a later grid overtake CTAs that are already queued)
     static const int waves = getenv("B200MD_PAIR_WAVES") ? std::max(1, atoi(getenv("B200MD_PAIR_WAVES"))) : 4;
     static const int perSm = getenv("B200MD_PAIR_CTAS_PER_SM") ? std::max(1, atoi(getenv("B200MD_PAIR_CTAS_PER_SM"))) : 4;
-    dim3 grid(sms*perSm*waves), block(256);
+    dim3 grid(sms*perSm*(nb.pairDynamic == 2 ? 1 : waves)), block(256);       // partitioned: ONE persistent wave, tiles from the cursor
     switch (nb.method) {
         case B200MD_NB_PME: k_pair<ENERGY, B200MD_NB_PME><<<grid, block, 0, s>>>(nb); break;
         case B200MD_NB_NOCUTOFF: k_pair<ENERGY, B200MD_NB_NOCUTOFF><<<grid, block, 0, s>>>(nb); break;
         default: k_pair<ENERGY, B200MD_NB_CUTOFF_PERIODIC><<<grid, block, 0, s>>>(nb); break;
     }
+}
+
+// which SM ids exist (they need not be contiguous): one CTA per resident slot writes its %smid into a bitmap
+__global__ void k_smid_probe(unsigned long long* bitmap) {
+    unsigned int smid;
+    asm("mov.u32 %0, %%smid;" : "=r"(smid));
+    if (threadIdx.x == 0) atomicOr(&bitmap[(smid >> 6) & 3], 1ull << (smid & 63));
+    // stay resident a little so that the grid spreads over every SM
+    const long long t0 = clock64();
+    while (clock64() - t0 < 20000) { }
+}
+// choose `reserve` SMs (the highest ids) for the reciprocal-space chain; returns the number actually reserved
+int choose_pme_sms(int reserve, unsigned long long mask[4]) {
+    mask[0] = mask[1] = mask[2] = mask[3] = 0ull;
+    if (reserve <= 0) return 0;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    unsigned long long* d = nullptr;
+    unsigned long long h[4] = {0, 0, 0, 0};
+    if (cudaMalloc(&d, sizeof(h)) != cudaSuccess) return 0;
+    cudaMemset(d, 0, sizeof(h));
+    k_smid_probe<<<sms*16, 128>>>(d);
+    cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    int found = 0, taken = 0;
+    for (int w = 0; w < 4; w++) found += __builtin_popcountll(h[w]);
+    if (found < sms) return 0;                        // the probe did not see every SM: do not partition
+    reserve = std::min(reserve, found/2);
+    for (int id = 255; id >= 0 && taken < reserve; id--)
+        if ((h[id >> 6] >> (id & 63)) & 1ull) { mask[id >> 6] |= 1ull << (id & 63); taken++; }
+    return taken;
 }
 
 void launch_pair(const NbDev& nb, bool energy, cudaStream_t s) {

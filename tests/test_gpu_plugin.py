@@ -163,3 +163,22 @@ def test_standalone_pme_kernel_serves_the_reference_cpu_platform():
     # absolute error of the fp32 spectral pipeline (measured 3.9e-4); against the total force it is 3e-6
     assert float(ferr) < 1e-3 and float(eerr) < 1e-7, msg
     assert float(ferr_all) < 1e-4 and float(eerr_all) < 1e-5, msg
+
+
+def test_cpp_host_application_loads_system_xml_and_pdb(omm, tmp_path):
+    """SURVEY.md 8(f) rank 1: a C++ program that uses only the reference's public API (XmlSerializer::deserialize<System>,
+    a PDB reader, Platform::loadPluginLibrary, Context, LangevinIntegrator::step) runs the real DHFR System on the B200
+    platform (plugin/examples/run_system_xml.cpp)."""
+    import json
+    import sys
+    exe = os.path.join(REFTESTS, "run_system_xml")
+    if not os.path.exists(exe):
+        pytest.fail("run_system_xml not built (make -C plugin reftests where /root/reference exists)")
+    base = str(tmp_path/"dhfr")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "make_system_xml.py"), "dhfr", base], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    r = subprocess.run([exe, base + ".xml", base + ".pdb", "--plugin", PLUGIN, "--steps", "1000"], capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert r.returncode == 0, r.stdout + r.stderr
+    j = json.loads(r.stdout.strip().splitlines()[-1])
+    assert j["platform"] == "B200" and j["atoms"] == 23558
+    assert j["ns_per_day"] > 200 and -4.5e5 < j["potential_after"] < -2.0e5

@@ -4,7 +4,7 @@ import json
 import os
 import numpy as np
 import pytest
-from conftest import relative_force_error, GOLDEN
+from conftest import relative_force_error, GOLDEN, ROOT
 from openmm_b200 import systems
 from oracle import port
 
@@ -135,3 +135,18 @@ def test_port_integrator_matches_live_reference(kind):
     # measured 4e-9 nm after 5 steps (the port integrates from its own forces, which differ from the reference's at 1e-9)
     assert np.abs(x - st["positions"]).max() < 1e-7
     assert np.abs(v - st["velocities"]).max() < 1e-4
+
+
+def test_baseline_config0_hello_sodium_chloride_on_the_reference_platform():
+    """BASELINE.json configs[0]: examples/HelloSodiumChloride.cpp as shipped (6 ions, NoCutoff + GBSA-OBC, LangevinMiddle),
+    compiled by oracle/Makefile from the source where it lies, on the reference's own Reference platform.  The first frame
+    is deterministic: energy -297.971 kcal/mole (SURVEY.md 8c probe)."""
+    import subprocess
+    exe = os.path.join(ROOT, "oracle", "_ref", "tests", "HelloSodiumChloride")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/tests/HelloSodiumChloride not built (needs /root/reference at build time)")
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120).stdout
+    assert "Using OpenMM platform Reference" in out
+    frames = [l for l in out.splitlines() if l.startswith("REMARK 250")]
+    assert len(frames) > 10
+    assert "time=0.000 ps; energy=-297.971 kcal/mole" in frames[0]
