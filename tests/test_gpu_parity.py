@@ -369,9 +369,82 @@ def test_box_too_small_is_an_error(mods):
         Engine(d)
 
 
-def test_unsupported_constraint_topology_is_an_error(mods):
-    systems, Engine, engine, *_ = mods
+def _all_bonds(systems, d):
+    """constraints=AllBonds on a real System: every harmonic bond that is not yet constrained becomes a constraint at its
+    equilibrium length (what forcefield.py does, wrappers/python/openmm/app/forcefield.py createSystem): the protein becomes
+    ONE general constraint network, i.e. CCMA (ReferenceConstraints.cpp:148-184)."""
+    have = set((min(i, j), max(i, j)) for i, j in zip(d.con_i, d.con_j))
+    ci, cj, cd = list(d.con_i), list(d.con_j), list(d.con_d)
+    for i, j, r0 in zip(d.bond_i, d.bond_j, d.bond_r0):
+        if (min(i, j), max(i, j)) not in have:
+            ci.append(int(i)); cj.append(int(j)); cd.append(float(r0))
+    d.con_i, d.con_j, d.con_d = np.array(ci, dtype=np.int32), np.array(cj, dtype=np.int32), np.array(cd)
+    return d
+
+
+@pytest.mark.parametrize("kind", [0, 1, 2])
+def test_ccma_general_constraint_network_follows_reference(mods, kind):
+    """DHFR with constraints=AllBonds (2,500 coupled protein constraints + SETTLE waters): deterministic integrators must
+    follow the Reference platform's CCMA (ReferenceCCMAAlgorithm.cpp:235-316) and keep every constraint to the tolerance."""
+    systems, Engine, _, omm, _ = mods
+    d = _all_bonds(systems, systems.SystemDesc.load(os.path.join(os.path.dirname(GOLDEN), "..", "data", "dhfr.npz")).rounded())
+    v = np.random.default_rng(3).standard_normal((d.natoms, 3))*0.2
+    eng = Engine(d)
+    eng.set_integrator(kind, 0.001, 0.0, 1.0, 7, 1e-6)
+    sim = omm.Simulation(d, "Reference", integrator=(kind, 0.0, 1.0, 0.001), constraint_tol=1e-6, pme=d.pme_parameters())
+    eng.apply_constraints(1e-6); sim.apply_constraints(1e-6)
+    x0 = sim.state(positions=True)["positions"]
+    assert np.abs(eng.get_positions() - x0).max() < 2e-6
+    eng.set_positions(x0)
+    eng.set_velocities(v); sim.set_velocities(v)
+    eng.step(10); sim.step(10)
+    ref = sim.state(positions=True, velocities=True)
+    x = eng.get_positions()
+    # fp32 positions at 4-6 nm resolve 5e-7 nm; every CCMA iteration of every step rounds once more (the free-atom / SETTLE
+    # trajectory test above holds 5e-6): 5e-5 nm after 10 steps, 2.1e-5 measured
+    assert np.abs(x - ref["positions"]).max() < 5e-5
+    dist = np.linalg.norm(x[d.con_i] - x[d.con_j], axis=1)
+    assert np.abs(dist/d.con_d - 1).max() < 2e-5
+    eng.step(300)
+    x = eng.get_positions()
+    dist = np.linalg.norm(x[d.con_i] - x[d.con_j], axis=1)
+    assert np.isfinite(x).all() and np.abs(dist/d.con_d - 1).max() < 2e-5
+
+
+def test_ccma_small_chain_and_methane(mods):
+    """tests/TestVerletIntegrator.h:230-275 (testConstrainedChain) shape, plus a CH4-like centre with four partners (more than
+    the three an X-H_n SHAKE cluster takes): both are general networks."""
+    systems, Engine, *_ = mods
     d = systems.lj_fluid(4, cutoff=0.7)
-    d.con_i = np.array([0, 1, 2], dtype=np.int32); d.con_j = np.array([1, 2, 3], dtype=np.int32); d.con_d = np.full(3, 0.38)
-    with pytest.raises(engine.EngineError):
-        Engine(d)
+    d.con_i = np.array([0, 1, 2, 10, 10, 10, 10], dtype=np.int32); d.con_j = np.array([1, 2, 3, 11, 12, 13, 14], dtype=np.int32)
+    x = d.positions
+    d.con_d = np.linalg.norm(x[d.con_i] - x[d.con_j], axis=1)
+    eng = Engine(d.rounded())
+    eng.set_velocities(np.random.default_rng(1).standard_normal((d.natoms, 3))*0.5)
+    eng.set_integrator(systems.INT_VERLET, 0.002, 0, 0, 0, 1e-6)
+    eng.step(500)
+    xn = eng.get_positions()
+    assert np.abs(np.linalg.norm(xn[d.con_i] - xn[d.con_j], axis=1)/d.con_d - 1).max() < 1e-5
+
+
+def test_nve_energy_drift_verlet(mods):
+    """Energy conservation of the fp32 state (no posqCorrection): Verlet 1 fs, rigid water, 10,000 steps; the drift of the
+    total energy per degree of freedom must stay far below kT (2.49 kJ/mol at 300 K)."""
+    systems, Engine, *_ = mods
+    d = systems.water_box(8, cutoff=0.9).rounded()
+    eng = Engine(d)
+    eng.set_integrator(systems.INT_LANGEVIN, 0.002, 300.0, 5.0, 3)
+    eng.step(1000)                                  # thermalise off the lattice
+    eng.set_integrator(systems.INT_VERLET, 0.001, 0, 0, 0, 1e-6)
+    dof = 3*d.natoms - len(d.con_i) - 3
+
+    def total():
+        e = eng.compute()
+        return e + eng.kinetic_energy()
+    e0 = total()
+    es = []
+    for _ in range(10):
+        eng.step(1000)
+        es.append(total())
+    drift = (np.array(es) - e0)/dof
+    assert np.abs(drift).max() < 0.01, drift        # kJ/mol per degree of freedom over 10 ps

@@ -182,3 +182,37 @@ def test_cpp_host_application_loads_system_xml_and_pdb(omm, tmp_path):
     j = json.loads(r.stdout.strip().splitlines()[-1])
     assert j["platform"] == "B200" and j["atoms"] == 23558
     assert j["ns_per_day"] > 200 and -4.5e5 < j["potential_after"] < -2.0e5
+
+
+def test_fused_step_graph_through_integrator_step_equals_the_two_call_path(omm):
+    """Integrator::step on the plugin replays ONE captured step graph per step (lazy forces + b200md_step, B200Platform.cpp
+    integrateStep); B200MD_PLUGIN_FUSED=0 selects b200md_compute + b200md_integrate_only.  Same trajectory either way, and
+    getState in between (which flushes the lazy evaluation) must not disturb it."""
+    from openmm_b200 import systems
+    d = systems.water_box(6, cutoff=0.9).rounded()
+    v = np.random.default_rng(4).standard_normal((d.natoms, 3))*0.3
+    out = []
+    for fused in ("1", "0"):
+        os.environ["B200MD_PLUGIN_FUSED"] = fused
+        sim = omm.Simulation(d, "B200", integrator=(systems.INT_VERLET, 0, 0, 0.001), pme=d.pme_parameters())
+        sim.set_velocities(v)
+        sim.step(7)
+        f_mid = sim.state(forces=True, energy=True)
+        sim.step(13)
+        st = sim.state(positions=True, velocities=True, energy=True)
+        out.append((st["positions"], st["velocities"], f_mid["forces"], f_mid["potential"]))
+        sim.close()
+    os.environ.pop("B200MD_PLUGIN_FUSED", None)
+    assert np.abs(out[0][0] - out[1][0]).max() < 2e-6
+    assert np.abs(out[0][2] - out[1][2]).max() < 1e-3*np.abs(out[1][2]).max() and abs(out[0][3] - out[1][3]) < 1e-6*abs(out[1][3])
+
+
+def test_context_falls_back_when_the_system_is_not_supported(omm):
+    """ContextImpl only falls back to the next platform when contextCreated() throws (ContextImpl.cpp:152-166): a System the
+    B200 platform cannot run (Ewald summation here) must be refused THERE, so that a Context without an explicit platform is
+    still created (on the Reference platform in this process), and an explicit B200 request fails with a clear message."""
+    from openmm_b200 import systems
+    d = systems.random_ions(64, 2.5, cutoff=1.0).rounded()
+    d.method = 3                                   # NonbondedForce::Ewald
+    with pytest.raises(RuntimeError, match="B200 platform"):
+        omm.Simulation(d, "B200")
