@@ -13,6 +13,7 @@
 //   k_grid_push     this rank's charge-grid contribution, slab by slab -> the slab owners' inboxes
 //   k_vel_push      velocities of the owner's atoms -> every rank (before any read of the velocities from the host)
 #include "engine.h"
+#include <algorithm>
 #include "../../include/b200md.h"
 
 __device__ __forceinline__ long long* win_force(const CommDev& cd, int q) { return (long long*) (cd.peer[q] + cd.offForce); }
@@ -76,24 +77,26 @@ __global__ void k_pos_wait(CommDev cd) {
 }
 
 // this rank's contribution to the charge grid (int64 fixed point, from the atoms it owns), slab by slab into the inbox
-// that the slab's owner keeps for this rank
+// that the slab's owner keeps for this rank.  blockIdx.y = peer (skipping this rank), 16-byte loads and stores.
 __global__ void __launch_bounds__(256) k_grid_push(PmeDev pme, CommDev cd) {
     const unsigned long long E = *cd.epoch + 1ull;
     const size_t planeCells = (size_t) pme.ny*pme.nz;
     const size_t inboxStride = (size_t) cd.maxPlanes*planeCells;
-    const size_t total = (size_t) pme.nx*planeCells;
-    // 16-byte stores: planeCells*8 bytes per plane; ny*nz is even for every grid the FFT accepts except odd*odd, handled by the scalar tail
+    const int q = (int) blockIdx.y + ((int) blockIdx.y >= cd.rank ? 1 : 0);
+    const size_t begin = (size_t) cd.xLo[q]*planeCells, cells = (size_t) (cd.xLo[q+1] - cd.xLo[q])*planeCells;
+    const long long* src = pme.gridFixed + begin;
+    long long* dst = (long long*) (cd.peer[q] + cd.offGridInbox) + (size_t) cd.rank*inboxStride;
     const size_t stride = (size_t) gridDim.x*blockDim.x;
-    for (size_t i = (size_t) blockIdx.x*blockDim.x + threadIdx.x; i < total; i += stride) {
-        const int x = (int) (i/planeCells);
-        int q = 0;
-#pragma unroll
-        for (int k = 1; k < B200MD_MAX_RANKS; k++) q += (k < cd.world && x >= cd.xLo[k]) ? 1 : 0;
-        if (q == cd.rank) continue;
-        long long* in = (long long*) (cd.peer[q] + cd.offGridInbox) + (size_t) cd.rank*inboxStride;
-        in[i - (size_t) cd.xLo[q]*planeCells] = pme.gridFixed[i];
+    if ((begin & 1) == 0 && ((((size_t) cd.rank*inboxStride) & 1) == 0)) {      // 16-byte aligned on both sides
+        const size_t pairs = cells >> 1;
+        const ulonglong2* s2 = (const ulonglong2*) src;
+        ulonglong2* d2 = (ulonglong2*) dst;
+        for (size_t i = (size_t) blockIdx.x*blockDim.x + threadIdx.x; i < pairs; i += stride) d2[i] = s2[i];
+        if ((cells & 1) && blockIdx.x == 0 && threadIdx.x == 0) dst[cells-1] = src[cells-1];
     }
-    comm_signal(cd, CH_GRID, E, gridDim.x);
+    else
+        for (size_t i = (size_t) blockIdx.x*blockDim.x + threadIdx.x; i < cells; i += stride) dst[i] = src[i];
+    comm_signal(cd, CH_GRID, E, gridDim.x*gridDim.y);
 }
 
 static int sm_count() {
@@ -125,5 +128,7 @@ void launch_pos_wait(const NbDev& nb, const CommDev& cd, cudaStream_t s) {
 }
 void launch_grid_push(const PmeDev& pme, const CommDev& cd, cudaStream_t s) {
     if (cd.world <= 1) return;
-    k_grid_push<<<2*sm_count(), 256, 0, s>>>(pme, cd);
+    const size_t slab = (size_t) cd.maxPlanes*pme.ny*pme.nz/2;          // 16-byte elements per peer
+    const int bx = (int) std::max<size_t>(1, std::min<size_t>((slab + 255)/256/4, (size_t) (4*sm_count()/(cd.world - 1) + 1)));
+    k_grid_push<<<dim3(bx, cd.world - 1), 256, 0, s>>>(pme, cd);
 }

@@ -1355,12 +1355,17 @@ static int enqueue_forces(b200md_ctx* c, int terms, bool energy, bool forcesAlre
     if (c->haveNb) bterms |= terms & B200MD_TERM_NB_DIRECT;
     const int nbonded = c->bd.nbonds + c->bd.nangles + c->bd.ntorsions + c->bd.nexc;
     if (bterms && nbonded > 0 && !(split && c->rank == pmeRank)) { BondedDev bd = c->bd; bd.groupMask = groupMask; launch_bonded(c->nb, bd, bterms, energy, s); launches++; }
+    // p2p: partial forces of the atoms this rank does not own -> the owners' inboxes.  Reciprocal space only ever touches the
+    // atoms this rank OWNS (k_pme_gather), so when it runs on its own stream the push does not have to wait for it: it goes
+    // out right behind the tile kernel and the bonded terms, beside the FFT chain.
+    const bool pushEarly = p2p && fork;
+    if (pushEarly) { launch_force_push(c->nb, c->cd, s); launches++; }
     if (fork) CUDA_CHECK(cudaStreamWaitEvent(s, c->evJoin, 0));
     if (joinList) CUDA_CHECK(cudaStreamWaitEvent(s, c->evListJoin, 0));
     if (p2p) {
-        // partial forces of the atoms this rank does not own -> the owners' inboxes; in the step path k_integrate totals them,
-        // here (energies, getState) the owners total and broadcast so that every rank ends up with every force
-        launch_force_push(c->nb, c->cd, s); launches++;
+        if (!pushEarly) { launch_force_push(c->nb, c->cd, s); launches++; }
+        // in the step path k_integrate totals own partial + inboxes; here (energies, getState) the owners total and broadcast
+        // so that every rank ends up with every force
         if (!inStep) { launch_force_total(c->nb, c->cd, s); launches += 2; }
     }
     if (c->world > 1 && c->comm) {
@@ -1737,7 +1742,7 @@ extern "C" int b200md_time_phase(b200md_ctx* ctx, int phase, int reps, double* m
             CUDA_CHECK(cudaMemcpyAsync(c->velm.p, saveVel.p, sizeof(float4)*c->npad, cudaMemcpyDeviceToDevice, s));
         }
         if (phase == 5) CUDA_CHECK(cudaMemcpyAsync(&c->counters.p[CT_REBUILD], &one, sizeof(int), cudaMemcpyHostToDevice, s));
-        if (phase == 0) CUDA_CHECK(cudaMemsetAsync(&c->counters.p[CT_CURSOR], 0, sizeof(int), s));      // the dynamic tile schedule starts from tile 0
+        if (phase == 0) { CUDA_CHECK(cudaMemsetAsync(&c->counters.p[CT_CURSOR], 0, sizeof(int), s)); CUDA_CHECK(cudaMemsetAsync(&c->counters.p[CT_PAIRSTART], 0, sizeof(int), s)); }      // the dynamic tile schedule starts from tile 0
         CUDA_CHECK(cudaEventRecord(e0, s));
         switch (phase) {
             case 0: launch_pair(nbv, false, s); break;

@@ -67,7 +67,8 @@ struct ListDev {
 enum { LC_TILES = 0, LC_MASKS = TILE_REGIONS, LC_MAXHALF = 2*TILE_REGIONS, LC_USED = 2*TILE_REGIONS + 1, LC_STRIDE = 128 };
 
 // indices into NbDev::counters
-enum { CT_REBUILD = 2, CT_OVERFLOW = 3, CT_BUILDS = 4, CT_PAIRS = 5, CT_LASTBLOCK = 8, CT_CUR = 10, CT_SOFT = 11, CT_PENDING = 12, CT_STALE = 13, CT_CURSOR = 14,
+enum { CT_PAIRSTART = 0,      // SM partition: CTAs of the tile kernel that have started (see k_pair)
+       CT_REBUILD = 2, CT_OVERFLOW = 3, CT_BUILDS = 4, CT_PAIRS = 5, CT_LASTBLOCK = 8, CT_CUR = 10, CT_SOFT = 11, CT_PENDING = 12, CT_STALE = 13, CT_CURSOR = 14,
        CT_BTDONE = 7, CT_BAR = 9, CT_BAREXIT = 15 };      // k_build_tiles completion count; grid barrier of k_list_prep
 
 struct NbDev {

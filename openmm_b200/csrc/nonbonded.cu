@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(256) k_check_gather(NbDev nb, CommDev cd) {
     comm_wait(cd, CH_POS, cd.world > 1 ? *cd.posNeed : 0ull);      // multi-GPU: the owners' position stores of the last step have landed
     const int s = blockIdx.x*blockDim.x + threadIdx.x;
     const ListDev& L = nb.list[nb.counters[CT_CUR] & 1];
-    if (s == 0) nb.counters[CT_CURSOR] = 0;           // tile cursor of the tile kernel's dynamic schedule
+    if (s == 0) { nb.counters[CT_CURSOR] = 0; nb.counters[CT_PAIRSTART] = 0; }       // tile cursor / start count of the tile kernel's dynamic schedule
     if (s < nb.natoms) {
         const float4 p = nb.posq[s];
         const float4 r = nb.refPos[s];
@@ -929,7 +929,14 @@ __device__ __forceinline__ void pair_tiles(const NbDev& nb, const ListDev& L, fl
     const float alpha2 = nb.alpha*nb.alpha, nalpha3 = -alpha2*nb.alpha;
     const float cutoff2 = nb.cutoff2;
     const float swInv = SWITCH ? 1.0f/(nb.cutoff - nb.switchDist) : 0.f;
-    const int src = (lane + 1) & 31;
+    // Rotation schedule: the 32 j atoms of a tile visit the lanes in four groups of eight.  Inside a group the j atoms rotate
+    // through the 8 lanes of their octet; after 8 steps every j is back in its lane, the group's partial forces are folded
+    // into running totals, and the octets move on by 8 lanes.  The fp32 accumulators therefore never hold more than 8
+    // contributions before they are folded: the rounding of a sum of 32 terms whose partial sums reach hundreds of
+    // kJ/mol/nm was the largest remaining error of the fp32 path (profiles/r02_parity_probe.md).
+    const int srcIn = (lane & ~7) | ((lane + 1) & 7);
+    const int srcOut = (lane + 8) & 31;
+    const int sub = lane & 7;
     const float close2 = CLOSE ? nb.closeCut2 : 0.f;
     const unsigned int ltMask = (1u << lane) - 1u;
     double energyD = 0.0;
@@ -961,9 +968,7 @@ __device__ __forceinline__ void pair_tiles(const NbDev& nb, const ListDev& L, fl
         float4 pj = L.sposq[jj];
         float2 sej = L.ssigeps[jj];
         const int mi = L.tileMask[t];
-        unsigned int mask = (mi < 0) ? FULL : L.maskPool[mi*32 + lane];
-        // rotate the mask so that bit 0 is always the current slot: slot = (lane + k) & 31
-        mask = __funnelshift_r(mask, mask, lane);
+        const unsigned int mask32 = (mi < 0) ? FULL : L.maskPool[mi*32 + lane];
         if (SHIFT) {
             // single-image mode: coordinates relative to the i-block centre, image chosen ONCE per atom and tile, in
             // double from the exact user coordinates (a lattice shift applied in fp32 costs half an ulp of the box
@@ -974,10 +979,17 @@ __device__ __forceinline__ void pair_tiles(const NbDev& nb, const ListDev& L, fl
             pi.x = wrap_rel(pi.x, c.x, bx.dax, bx.recip[0]); pi.y = wrap_rel(pi.y, c.y, bx.dby, bx.recip[4]); pi.z = wrap_rel(pi.z, c.z, bx.dcz, bx.recip[8]);
             pj.x = wrap_rel(pj.x, c.x, bx.dax, bx.recip[0]); pj.y = wrap_rel(pj.y, c.y, bx.dby, bx.recip[4]); pj.z = wrap_rel(pj.z, c.z, bx.dcz, bx.recip[8]);
         }
-        float fix = 0.f, fiy = 0.f, fiz = 0.f, fjx = 0.f, fjy = 0.f, fjz = 0.f;
+        float fiTx = 0.f, fiTy = 0.f, fiTz = 0.f, fjTx = 0.f, fjTy = 0.f, fjTz = 0.f;
         int qn = 0;
+#pragma unroll 1
+        for (int g = 0; g < 4; g++) {
+        // j slots of this group: octet ((lane >> 3) + g) & 3, starting at this lane's position in the octet
+        const int slotBase = (((lane >> 3) + g) & 3) << 3;
+        unsigned int mask = (mask32 >> slotBase) & 0xffu;
+        mask = ((mask | (mask << 8)) >> sub) & 0xffu;          // bit 0 = the slot held now, bit k = after k rotations
+        float fix = 0.f, fiy = 0.f, fiz = 0.f, fjx = 0.f, fjy = 0.f, fjz = 0.f;
 #pragma unroll 4
-        for (int k = 0; k < 32; k++) {
+        for (int k = 0; k < 8; k++) {
             float3 d = make_float3(pj.x-pi.x, pj.y-pi.y, pj.z-pi.z);
             if (!SHIFT && periodic) d = min_image(d, nb.box);
             const float r2raw = fmaf(d.z, d.z, fmaf(d.y, d.y, d.x*d.x));
@@ -988,7 +1000,7 @@ __device__ __forceinline__ void pair_tiles(const NbDev& nb, const ListDev& L, fl
                 const unsigned int cm = __ballot_sync(FULL, isClose);
                 if (cm) {           // warp-uniform; ~1 rotation in 8 at water density
                     const int pos = qn + __popc(cm & ltMask);
-                    if (isClose && pos < CLOSE_QCAP) { cq[pos] = (unsigned short) (lane | (((lane + k) & 31) << 5)); valid = false; }
+                    if (isClose && pos < CLOSE_QCAP) { cq[pos] = (unsigned short) (lane | ((slotBase | ((sub + k) & 7)) << 5)); valid = false; }
                     qn = min(CLOSE_QCAP, qn + __popc(cm));
                 }
             }
@@ -1043,11 +1055,20 @@ __device__ __forceinline__ void pair_tiles(const NbDev& nb, const ListDev& L, fl
             if (ENERGY) energy += valid ? e + ljE : 0.f;
             fix = fmaf(-d.x, dEdR, fix); fiy = fmaf(-d.y, dEdR, fiy); fiz = fmaf(-d.z, dEdR, fiz);
             fjx = fmaf(d.x, dEdR, fjx); fjy = fmaf(d.y, dEdR, fjy); fjz = fmaf(d.z, dEdR, fjz);
-            pj.x = __shfl_sync(FULL, pj.x, src); pj.y = __shfl_sync(FULL, pj.y, src);
-            pj.z = __shfl_sync(FULL, pj.z, src); pj.w = __shfl_sync(FULL, pj.w, src);
-            sej.x = __shfl_sync(FULL, sej.x, src); sej.y = __shfl_sync(FULL, sej.y, src);
-            fjx = __shfl_sync(FULL, fjx, src); fjy = __shfl_sync(FULL, fjy, src); fjz = __shfl_sync(FULL, fjz, src);
+            pj.x = __shfl_sync(FULL, pj.x, srcIn); pj.y = __shfl_sync(FULL, pj.y, srcIn);
+            pj.z = __shfl_sync(FULL, pj.z, srcIn); pj.w = __shfl_sync(FULL, pj.w, srcIn);
+            sej.x = __shfl_sync(FULL, sej.x, srcIn); sej.y = __shfl_sync(FULL, sej.y, srcIn);
+            fjx = __shfl_sync(FULL, fjx, srcIn); fjy = __shfl_sync(FULL, fjy, srcIn); fjz = __shfl_sync(FULL, fjz, srcIn);
         }
+        // the octet is home again: fold the group's sums, then the j atoms (with their totals) move on by one octet
+        fiTx += fix; fiTy += fiy; fiTz += fiz;
+        fjTx += fjx; fjTy += fjy; fjTz += fjz;
+        pj.x = __shfl_sync(FULL, pj.x, srcOut); pj.y = __shfl_sync(FULL, pj.y, srcOut);
+        pj.z = __shfl_sync(FULL, pj.z, srcOut); pj.w = __shfl_sync(FULL, pj.w, srcOut);
+        sej.x = __shfl_sync(FULL, sej.x, srcOut); sej.y = __shfl_sync(FULL, sej.y, srcOut);
+        fjTx = __shfl_sync(FULL, fjTx, srcOut); fjTy = __shfl_sync(FULL, fjTy, srcOut); fjTz = __shfl_sync(FULL, fjTz, srcOut);
+        }   // groups
+
         if (CLOSE && qn > 0) {
             __syncwarp();
             for (int e = lane; e < qn; e += 32) {
@@ -1056,18 +1077,18 @@ __device__ __forceinline__ void pair_tiles(const NbDev& nb, const ListDev& L, fl
             }
             __syncwarp();
         }
-        // after 32 rotations every lane holds its own j again
+        // after 4 x 8 rotations every lane holds its own j again
         const int ai = L.sorig[si];
         if (ai >= 0) {
-            atomicAdd((unsigned long long*) &nb.force[ai], (unsigned long long) float_to_fixed(fix));
-            atomicAdd((unsigned long long*) &nb.force[ai + nb.npad], (unsigned long long) float_to_fixed(fiy));
-            atomicAdd((unsigned long long*) &nb.force[ai + 2*nb.npad], (unsigned long long) float_to_fixed(fiz));
+            atomicAdd((unsigned long long*) &nb.force[ai], (unsigned long long) float_to_fixed(fiTx));
+            atomicAdd((unsigned long long*) &nb.force[ai + nb.npad], (unsigned long long) float_to_fixed(fiTy));
+            atomicAdd((unsigned long long*) &nb.force[ai + 2*nb.npad], (unsigned long long) float_to_fixed(fiTz));
         }
         if (jidx >= 0) {
             const int aj = L.sorig[jidx];
-            atomicAdd((unsigned long long*) &nb.force[aj], (unsigned long long) float_to_fixed(fjx));
-            atomicAdd((unsigned long long*) &nb.force[aj + nb.npad], (unsigned long long) float_to_fixed(fjy));
-            atomicAdd((unsigned long long*) &nb.force[aj + 2*nb.npad], (unsigned long long) float_to_fixed(fjz));
+            atomicAdd((unsigned long long*) &nb.force[aj], (unsigned long long) float_to_fixed(fjTx));
+            atomicAdd((unsigned long long*) &nb.force[aj + nb.npad], (unsigned long long) float_to_fixed(fjTy));
+            atomicAdd((unsigned long long*) &nb.force[aj + 2*nb.npad], (unsigned long long) float_to_fixed(fjTz));
         }
     }
     if (ENERGY && CLOSE && energyD != 0.0) atomicAdd(&nb.energy[EN_NB], energyD);
@@ -1088,10 +1109,22 @@ __device__ __forceinline__ void pair_tiles_sw(const NbDev& nb, const ListDev& L,
 template <bool ENERGY, int METHOD>
 __global__ void __launch_bounds__(256, ENERGY ? 2 : 4) k_pair(NbDev nb) {
     if (nb.pairDynamic == 2) {
-        // SM partition (launch_pair_m): this SM is reserved for the reciprocal-space kernels
+        // SM partition (launch_pair_m): CTAs that land on an SM reserved for the reciprocal-space kernels do no tile work.
+        // They must not leave at once, though: a reserved SM would then swallow the grid's still-pending CTAs one after the
+        // other (each finds room there and exits) while the other SMs are still busy with the charge spreading, and the
+        // tile kernel would be left with a fraction of its workers.  So they hold their slots until EVERY CTA of the grid
+        // has started (the pending ones can then only have gone to the other SMs), and only then hand the SM over.
         unsigned int smid;
         asm("mov.u32 %0, %%smid;" : "=r"(smid));
-        if ((nb.pmeSmMask[(smid >> 6) & 3] >> (smid & 63)) & 1ull) return;
+        const bool reserved = (nb.pmeSmMask[(smid >> 6) & 3] >> (smid & 63)) & 1ull;
+        if (threadIdx.x == 0) {
+            atomicAdd(&nb.counters[CT_PAIRSTART], 1);
+            if (reserved) {
+                long spins = 0;
+                while (*((volatile int*) &nb.counters[CT_PAIRSTART]) < (int) gridDim.x && ++spins < (1L << 20)) __nanosleep(200);
+            }
+        }
+        if (reserved) { __syncthreads(); return; }
     }
     float energy = 0.f;
     __shared__ unsigned short closeQ[8][CLOSE_QCAP];       // per-warp queue of close pairs: i lane | j slot << 5
