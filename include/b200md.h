@@ -121,7 +121,11 @@ int b200md_get_positions(b200md_ctx* ctx, double* xyz);   /* continuous (unwrapp
                                                              * internal molecule wrapping is undone ("Long runs") */
 int b200md_set_velocities(b200md_ctx* ctx, const double* xyz);
 int b200md_get_velocities(b200md_ctx* ctx, double* xyz);
-int b200md_get_forces(b200md_ctx* ctx, double* xyz);        /* forces of the last b200md_compute */
+int b200md_get_forces(b200md_ctx* ctx, double* xyz);        /* forces of the last b200md_compute.  b200md_step zeroes the force
+                                                             * buffer inside its fused integrate kernel: after a step the
+                                                             * forces (and the half-step-shifted kinetic energy of the
+                                                             * leapfrog integrators, which needs them) are only valid after
+                                                             * another b200md_compute -- Context::getState does exactly that */
 int b200md_set_time(b200md_ctx* ctx, double t);
 double b200md_get_time(b200md_ctx* ctx);
 int64_t b200md_get_step_count(b200md_ctx* ctx);

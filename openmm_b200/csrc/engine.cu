@@ -887,9 +887,15 @@ extern "C" int b200md_finalize(b200md_ctx* ctx) {
     nb.packCull = getenv("B200MD_BT_PACK") ? atoi(getenv("B200MD_BT_PACK")) : 1;
     // SM partition between the tile kernel and the reciprocal-space chain (B200MD_PME_SMS=k reserves k SMs; 0 = off)
     for (int w = 0; w < 4; w++) nb.pmeSmMask[w] = 0ull;
+    // Off on one GPU (measured: the chain is latency bound and needs most SMs to be short, profiles/r02_sm_partition.md).
+    // Multi-GPU (peer-memory data plane): the chain is a sequence of kernels that wait for the other ranks, and behind a tile
+    // kernel that holds every SM it would only start when that has drained; here the default reserves as many SMs as the rank
+    // has x planes (one slab CTA each), between 16 and 48.
     if (c->nbdesc.method == B200MD_NB_PME && !c->pmeOnly && c->overlapPme) {
-        const int want = getenv("B200MD_PME_SMS") ? atoi(getenv("B200MD_PME_SMS")) : 0;
-        if (want > 0 && choose_pme_sms(want, nb.pmeSmMask) > 0) nb.pairDynamic = 2;
+        int want = 0;
+        if (c->p2p) want = std::max(16, std::min(48, (c->nbdesc.grid[0] + c->world - 1)/c->world));
+        if (getenv("B200MD_PME_SMS")) want = atoi(getenv("B200MD_PME_SMS"));
+        if (want > 0 && choose_pme_sms(want, nb.pmeSmMask) > 0) { nb.pairDynamic = 2; fft_set_compact(1); }
     }
     // ---- state arrays ----
     c->posq.alloc(NP); c->posq.zero(); c->velm.alloc(NP); c->velm.zero();
@@ -1413,6 +1419,7 @@ static void prepare_list(b200md_ctx* c) {
         CUDA_CHECK(cudaMemcpyAsync(lc, c->listCounters.p, sizeof(lc), cudaMemcpyDeviceToHost, c->stream));
         CUDA_CHECK(cudaStreamSynchronize(c->stream));
         if (h[CT_OVERFLOW] == 2) throw std::runtime_error("B200 platform: neighbour-list construction timed out at a grid barrier (k_list_prep)");
+        if (h[CT_OVERFLOW] == 3) throw std::runtime_error("B200 platform: multi-GPU exchange timed out waiting for a peer rank (every rank must issue the same sequence of calls)");
         const int* cur = lc + LC_STRIDE*(h[CT_CUR] & 1);
         int worst = 0;
         for (int r = 0; r < TILE_REGIONS; r++) worst = std::max(worst, cur[LC_TILES + r]);

@@ -358,6 +358,7 @@ size_t fft_plane_smem_bytes(int ny, int nz);
 size_t fft_line_smem_bytes(int nx);
 bool fft_make_radices(int n, int* radix, int* nstages);
 int pme_fft_launch_count(const PmeDev& pme);
+void fft_set_compact(int on);                   // smaller FFT CTAs (the chain shares the GPU with the tile kernel)
 bool fft_slab_path(const PmeDev& pme);          // the 3-launch slab pipeline is usable for this grid (precondition of the multi-GPU FFT)
 
 void launch_bonded(const NbDev& nb, const BondedDev& bd, int terms, bool energy, cudaStream_t s);

@@ -585,11 +585,20 @@ __global__ void __launch_bounds__(FFT_THREADS) k_fft_slab_inv(PmeDev pme, size_t
     }
 }
 
-// B200MD_FFT_THREADS: threads per CTA (<= FFT_THREADS).  At 128 registers per thread a 512-thread CTA needs a whole SM's
-// register file, a 256-thread CTA half of it: smaller CTAs find room beside the tile kernel.
+// Threads per CTA.  The kernels are compiled for up to 512 threads at 128 registers, i.e. a 512-thread CTA owns a whole SM's
+// register file.  A (y,z) plane keeps 512 threads busy only in its load / store phases (a radix-11 stage of an 88-point
+// line has 8 butterflies per line), a batch of 16 x lines even less: when the reciprocal-space chain shares the GPU with
+// the tile kernel (SM partition, multi-GPU) smaller CTAs let 2-4 of them share one of the few SMs it has.
+// B200MD_FFT_THREADS / B200MD_FFTX_THREADS override (slab kernels / x-line kernel).
+static int g_fft_compact = 0;            // set by fft_set_compact(): the chain runs on a reserved subset of the SMs
+void fft_set_compact(int on) { g_fft_compact = on; }
 static int fft_threads() {
-    static const int t = getenv("B200MD_FFT_THREADS") ? std::min(FFT_THREADS, std::max(64, atoi(getenv("B200MD_FFT_THREADS")))) : FFT_THREADS;
-    return t;
+    static const int env = getenv("B200MD_FFT_THREADS") ? std::min(FFT_THREADS, std::max(64, atoi(getenv("B200MD_FFT_THREADS")))) : 0;
+    return env ? env : (g_fft_compact ? 256 : FFT_THREADS);
+}
+static int fftx_threads() {
+    static const int env = getenv("B200MD_FFTX_THREADS") ? std::min(FFT_THREADS, std::max(64, atoi(getenv("B200MD_FFTX_THREADS")))) : 0;
+    return env ? env : (g_fft_compact ? 128 : fft_threads());
 }
 static dim3 fft_block(int n, int maxLines) {
     (void) n; (void) maxLines;
@@ -617,7 +626,7 @@ struct FftLaunch {
         zs = (2*(size_t) (ZROWS/2)*p.nz + 3*p.nz)*sizeof(real2);
         ys = (2*(size_t) LINE_BATCH*p.ny + 3*p.ny)*sizeof(real2);
         xs = (2*(size_t) LINE_BATCH*p.nx + 3*p.nx)*sizeof(real2);
-        zt = fft_block(p.nz, ZROWS/2); yt = fft_block(p.ny, LINE_BATCH); xt = fft_block(p.nx, LINE_BATCH);
+        zt = fft_block(p.nz, ZROWS/2); yt = fft_block(p.ny, LINE_BATCH); xt = dim3(fftx_threads());
         zb = (p.nx*p.ny + ZROWS - 1)/ZROWS;
         yb = p.nx*((p.nzc + LINE_BATCH - 1)/LINE_BATCH);
         xb = (p.ny*p.nzc + LINE_BATCH - 1)/LINE_BATCH;
