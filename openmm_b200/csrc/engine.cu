@@ -895,7 +895,12 @@ extern "C" int b200md_finalize(b200md_ctx* ctx) {
         int want = 0;
         if (c->p2p) want = std::max(16, std::min(48, (c->nbdesc.grid[0] + c->world - 1)/c->world));
         if (getenv("B200MD_PME_SMS")) want = atoi(getenv("B200MD_PME_SMS"));
-        if (want > 0 && choose_pme_sms(want, nb.pmeSmMask) > 0) { nb.pairDynamic = 2; fft_set_compact(1); }
+        const int got = want > 0 ? choose_pme_sms(want, nb.pmeSmMask) : 0;
+        if (got > 0) {
+            nb.pairDynamic = 2;
+            const int planes = (c->nbdesc.grid[0] + c->world - 1)/c->world;
+            fft_set_compact(planes > got ? 2 : 1);
+        }
     }
     // ---- state arrays ----
     c->posq.alloc(NP); c->posq.zero(); c->velm.alloc(NP); c->velm.zero();

@@ -590,11 +590,11 @@ __global__ void __launch_bounds__(FFT_THREADS) k_fft_slab_inv(PmeDev pme, size_t
 // line has 8 butterflies per line), a batch of 16 x lines even less: when the reciprocal-space chain shares the GPU with
 // the tile kernel (SM partition, multi-GPU) smaller CTAs let 2-4 of them share one of the few SMs it has.
 // B200MD_FFT_THREADS / B200MD_FFTX_THREADS override (slab kernels / x-line kernel).
-static int g_fft_compact = 0;            // set by fft_set_compact(): the chain runs on a reserved subset of the SMs
+static int g_fft_compact = 0;            // fft_set_compact(): the chain runs on a reserved subset of the SMs; 2 = fewer SMs than planes per rank
 void fft_set_compact(int on) { g_fft_compact = on; }
 static int fft_threads() {
     static const int env = getenv("B200MD_FFT_THREADS") ? std::min(FFT_THREADS, std::max(64, atoi(getenv("B200MD_FFT_THREADS")))) : 0;
-    return env ? env : (g_fft_compact ? 256 : FFT_THREADS);
+    return env ? env : (g_fft_compact == 2 ? 256 : FFT_THREADS);       // a plane per SM when there is one: 512 threads finish it in ~2/3 of the time of 256
 }
 static int fftx_threads() {
     static const int env = getenv("B200MD_FFTX_THREADS") ? std::min(FFT_THREADS, std::max(64, atoi(getenv("B200MD_FFTX_THREADS")))) : 0;

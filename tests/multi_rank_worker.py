@@ -47,12 +47,12 @@ e = eng.compute()
 f = eng.get_forces()
 dfmax = float(np.abs(f - fref).max())
 log("x%d engine: E = %.6f, max|dF| = %.3e" % (world, e, dfmax))
-ok = dfmax == 0.0 and abs(e - eref) <= 1e-10*abs(eref)
+ok = dfmax == 0.0 and abs(e - eref) <= 1e-8*abs(eref)      # the energy is a double sum of fp32 terms reduced in another order
 # a second evaluation (exercises the exchange epochs) and component evaluations
 for terms in (31, 8 | 1 | 2 | 4, 16):
     e2 = eng.compute(terms); f2 = eng.get_forces()
     er2 = ref.compute(terms); fr2 = ref.get_forces()
-    ok = ok and float(np.abs(f2 - fr2).max()) == 0.0 and abs(e2 - er2) <= 1e-10*max(1.0, abs(er2))
+    ok = ok and float(np.abs(f2 - fr2).max()) == 0.0 and abs(e2 - er2) <= 1e-8*max(1.0, abs(er2))
 v0 = np.random.default_rng(5).standard_normal((d.natoms, 3))*0.3
 for g in (ref, eng):
     g.set_velocities(v0)
