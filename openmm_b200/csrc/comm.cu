@@ -99,6 +99,58 @@ __global__ void __launch_bounds__(256) k_grid_push(PmeDev pme, CommDev cd) {
     comm_signal(cd, CH_GRID, E, gridDim.x*gridDim.y);
 }
 
+// ---- the same push with the TMA engine (cp.async.bulk), used whenever the slabs are 16-byte aligned ----
+// Stores into peer memory issued by threads are bound by the number of stores an SM keeps in flight: ~6 GB/s per SM,
+// i.e. 4 MB took 31 us from the 22 SMs the reciprocal-space chain has at 4 ranks (profiles/r02_multi_gpu.md).  A bulk copy
+// is ONE instruction per 16 KB: a single thread per CTA streams global -> shared (cp.async.bulk + mbarrier complete_tx)
+// and shared -> the peer's window (cp.async.bulk.global.shared::cta, bulk groups) through a 4-stage ring, and the copy
+// engines keep the links busy whatever the SM count.  SASS: UBLKCP.
+#define PUSH_CHUNK 16384
+#define PUSH_STAGES 4
+__device__ __forceinline__ unsigned int smem_u32(const void* p) { return (unsigned int) __cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_wait(unsigned int bar, unsigned int parity) {
+    asm volatile("{\n .reg .pred p;\n WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @p bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}" :: "r"(bar), "r"(parity) : "memory");
+}
+__global__ void __launch_bounds__(32) k_grid_push_tma(PmeDev pme, CommDev cd, int chunksPerCta) {
+    extern __shared__ __align__(128) unsigned char ring[];            // PUSH_STAGES x PUSH_CHUNK
+    __shared__ __align__(8) unsigned long long bars[PUSH_STAGES];
+    const unsigned long long E = *cd.epoch + 1ull;
+    const size_t planeCells = (size_t) pme.ny*pme.nz;
+    const size_t inboxStride = (size_t) cd.maxPlanes*planeCells;
+    const int q = (int) blockIdx.y + ((int) blockIdx.y >= cd.rank ? 1 : 0);
+    const size_t bytes = (size_t) (cd.xLo[q+1] - cd.xLo[q])*planeCells*sizeof(long long);
+    const char* src = (const char*) (pme.gridFixed + (size_t) cd.xLo[q]*planeCells);
+    char* dst = (char*) ((long long*) (cd.peer[q] + cd.offGridInbox) + (size_t) cd.rank*inboxStride);
+    const size_t first = (size_t) blockIdx.x*chunksPerCta*PUSH_CHUNK;
+    const size_t left = first < bytes ? (bytes - first + PUSH_CHUNK - 1)/PUSH_CHUNK : 0;
+    const int n = (int) (left < (size_t) chunksPerCta ? left : (size_t) chunksPerCta);
+    if (threadIdx.x == 0 && n > 0) {
+        for (int s = 0; s < PUSH_STAGES; s++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&bars[s])));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        auto chunk_bytes = [&](int c) { const size_t r = bytes - first - (size_t) c*PUSH_CHUNK; return (unsigned int) (r < (size_t) PUSH_CHUNK ? r : (size_t) PUSH_CHUNK); };
+        auto load = [&](int c) {
+            const unsigned int bar = smem_u32(&bars[c % PUSH_STAGES]), nb = chunk_bytes(c);
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(nb) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         :: "r"(smem_u32(ring + (size_t) (c % PUSH_STAGES)*PUSH_CHUNK)), "l"(src + first + (size_t) c*PUSH_CHUNK), "r"(nb), "r"(bar) : "memory");
+        };
+        const int ahead = PUSH_STAGES - 1;
+        for (int c = 0; c < n && c < ahead; c++) load(c);
+        for (int c = 0; c < n; c++) {
+            mbar_wait(smem_u32(&bars[c % PUSH_STAGES]), (unsigned int) ((c/PUSH_STAGES) & 1));
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                         :: "l"(dst + first + (size_t) c*PUSH_CHUNK), "r"(smem_u32(ring + (size_t) (c % PUSH_STAGES)*PUSH_CHUNK)), "r"(chunk_bytes(c)) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            if (c + ahead < n) {
+                asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");      // the stage of chunk c-1 has been read: reuse it
+                load(c + ahead);
+            }
+        }
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");                    // every store of this CTA is complete
+    }
+    comm_signal(cd, CH_GRID, E, gridDim.x*gridDim.y);
+}
+
 static int sm_count() {
     static int sms = 0;
     if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
@@ -128,6 +180,17 @@ void launch_pos_wait(const NbDev& nb, const CommDev& cd, cudaStream_t s) {
 }
 void launch_grid_push(const PmeDev& pme, const CommDev& cd, cudaStream_t s) {
     if (cd.world <= 1) return;
+    static const bool useTma = !(getenv("B200MD_PUSH_TMA") && atoi(getenv("B200MD_PUSH_TMA")) == 0);
+    const size_t planeBytes = (size_t) pme.ny*pme.nz*sizeof(long long);
+    if (useTma && planeBytes % 16 == 0) {          // every slab then starts and ends on a 16-byte boundary (window offsets are multiples of 256)
+        static bool attr = false;
+        if (!attr) { cudaFuncSetAttribute(k_grid_push_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, PUSH_STAGES*PUSH_CHUNK); attr = true; }
+        const size_t maxBytes = (size_t) cd.maxPlanes*planeBytes;
+        const int chunks = (int) ((maxBytes + PUSH_CHUNK - 1)/PUSH_CHUNK);
+        const int per = std::max(4, (chunks + 63)/64);                 // <= 64 CTAs per peer, >= 4 chunks per CTA
+        k_grid_push_tma<<<dim3((chunks + per - 1)/per, cd.world - 1), 32, PUSH_STAGES*PUSH_CHUNK, s>>>(pme, cd, per);
+        return;
+    }
     const size_t slab = (size_t) cd.maxPlanes*pme.ny*pme.nz/2;          // 16-byte elements per peer
     const int bx = (int) std::max<size_t>(1, std::min<size_t>((slab + 255)/256/4, (size_t) (4*sm_count()/(cd.world - 1) + 1)));
     k_grid_push<<<dim3(bx, cd.world - 1), 256, 0, s>>>(pme, cd);

@@ -249,9 +249,9 @@ __device__ __forceinline__ void comm_wait(const CommDev& cd, int ch, unsigned lo
 // which then publishes the stage with comm_publish (possibly after a little more work of its own).
 __device__ __forceinline__ bool comm_arrive(const CommDev& cd, int ch, unsigned int nblocks) {
     __shared__ int lastBlock;
-    __threadfence_system();
-    __syncthreads();
+    __syncthreads();                   // the block's stores happen-before thread 0's fence (cumulativity): ONE system fence per CTA
     if (threadIdx.x == 0 && threadIdx.y == 0 && threadIdx.z == 0) {
+        __threadfence_system();
         lastBlock = (atomicAdd(&cd.done[ch], 1u) == nblocks - 1u);
         if (lastBlock) { cd.done[ch] = 0u; __threadfence_system(); }
     }
