@@ -151,15 +151,121 @@ __global__ void __launch_bounds__(32) k_grid_push_tma(PmeDev pme, CommDev cd, in
     comm_signal(cd, CH_GRID, E, gridDim.x*gridDim.y);
 }
 
+// ---- contiguous ranges to every peer through the TMA engine ----
+// One warp-sized CTA per (peer, piece): thread 0 streams `bytes` from src (local) to dst (mapped peer memory) through a
+// PUSH_STAGES-deep ring of PUSH_CHUNK-byte stages.  Used for the positions of the owned atoms (after k_integrate) and for
+// the partial forces of the atoms a rank does not own (three component planes per peer).
+__device__ __forceinline__ void tma_stream(const char* src, char* dst, size_t bytes, unsigned char* ring, unsigned long long* bars) {
+    // caller: one thread; src, dst, bytes multiples of 16
+    const int n = (int) ((bytes + PUSH_CHUNK - 1)/PUSH_CHUNK);
+    if (n == 0) return;
+    for (int s = 0; s < PUSH_STAGES; s++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&bars[s])));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    auto chunk_bytes = [&](int c) { const size_t r = bytes - (size_t) c*PUSH_CHUNK; return (unsigned int) (r < (size_t) PUSH_CHUNK ? r : (size_t) PUSH_CHUNK); };
+    auto load = [&](int c) {
+        const unsigned int bar = smem_u32(&bars[c % PUSH_STAGES]), nb = chunk_bytes(c);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(nb) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     :: "r"(smem_u32(ring + (size_t) (c % PUSH_STAGES)*PUSH_CHUNK)), "l"(src + (size_t) c*PUSH_CHUNK), "r"(nb), "r"(bar) : "memory");
+    };
+    const int ahead = PUSH_STAGES - 1;
+    for (int c = 0; c < n && c < ahead; c++) load(c);
+    for (int c = 0; c < n; c++) {
+        mbar_wait(smem_u32(&bars[c % PUSH_STAGES]), (unsigned int) ((c/PUSH_STAGES) & 1));
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                     :: "l"(dst + (size_t) c*PUSH_CHUNK), "r"(smem_u32(ring + (size_t) (c % PUSH_STAGES)*PUSH_CHUNK)), "r"(chunk_bytes(c)) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        if (c + ahead < n) {
+            asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            load(c + ahead);
+        }
+    }
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+// positions of the owned atoms -> every peer's posq; then CH_POS (the end of a step's exchange: advances the epoch)
+// grid (pieces, world-1)
+__global__ void __launch_bounds__(32) k_pos_push(NbDev nb, CommDev cd, IntegDev in, int pieces) {
+    extern __shared__ __align__(128) unsigned char ring[];
+    __shared__ __align__(8) unsigned long long bars[PUSH_STAGES];
+    const unsigned long long E = *cd.epoch + 1ull;
+    const int q = (int) blockIdx.y + ((int) blockIdx.y >= cd.rank ? 1 : 0);
+    const size_t lo = (size_t) cd.atomLo[cd.rank]*sizeof(float4), hi = (size_t) cd.atomLo[cd.rank + 1]*sizeof(float4);
+    const size_t per = (((hi - lo) + pieces - 1)/pieces + PUSH_CHUNK - 1)/PUSH_CHUNK*PUSH_CHUNK;
+    const size_t b0 = lo + (size_t) blockIdx.x*per, b1 = b0 + per < hi ? b0 + per : hi;
+    if (threadIdx.x == 0 && b0 < b1)
+        tma_stream((const char*) nb.posq + b0, cd.peer[q] + cd.offPosq + b0, b1 - b0, ring, bars);
+    const bool last = comm_arrive(cd, CH_POS, gridDim.x*gridDim.y);
+    if (last && threadIdx.x == 0) {
+        // the momentum sums of this rank's atoms (k_integrate left them in cmScratch) go along, then the flag
+        if (in.fused && in.cmEveryStep) {
+            const unsigned long long step = *in.stepCounter - 1ull;               // k_integrate already advanced the counter
+            const double* mine = in.cmScratch + 4*((step + 1ull) % 3ull);
+            for (int p = 0; p < cd.world; p++) {
+                double* t = (double*) (cd.peer[p] + cd.offCm) + cd.rank*12 + 4*((step + 1ull) % 3ull);
+                for (int k = 0; k < 4; k++) t[k] = ((volatile const double*) mine)[k];
+            }
+        }
+        comm_publish(cd, CH_POS, E);
+        *cd.posNeed = E;
+        *cd.epoch = E;
+    }
+}
+
+// partial forces of the atoms of every other rank -> that rank's inbox, the three component planes as contiguous ranges;
+// the local copies are zeroed by the caller (memset nodes) once this kernel has read them.   grid (3, world-1)
+__global__ void __launch_bounds__(32) k_force_push_tma(NbDev nb, CommDev cd) {
+    extern __shared__ __align__(128) unsigned char ring[];
+    __shared__ __align__(8) unsigned long long bars[PUSH_STAGES];
+    const unsigned long long E = *cd.epoch + 1ull;
+    const int q = (int) blockIdx.y + ((int) blockIdx.y >= cd.rank ? 1 : 0);
+    const int c = blockIdx.x;
+    // the range is widened to even atom indices (16-byte granularity of the bulk copy): the extra element is an atom the
+    // receiver does not own, whose inbox slot it never reads
+    const size_t a0 = (size_t) (cd.atomLo[q] & ~1), a1 = (size_t) ((cd.atomLo[q+1] + 1) & ~1);
+    const size_t lo = ((size_t) c*nb.npad + a0)*sizeof(long long), hi = ((size_t) c*nb.npad + a1)*sizeof(long long);
+    if (threadIdx.x == 0)
+        tma_stream((const char*) nb.force + lo, (char*) win_finbox(cd, q, cd.rank, nb.npad) + lo, hi - lo, ring, bars);
+    comm_signal(cd, CH_FORCE, E, gridDim.x*gridDim.y);
+}
+
 static int sm_count() {
     static int sms = 0;
     if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
     return sms;
 }
 
+static bool push_tma() {
+    static const bool on = !(getenv("B200MD_PUSH_TMA") && atoi(getenv("B200MD_PUSH_TMA")) == 0);
+    return on;
+}
+static void ring_attr(const void* f) { cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, PUSH_STAGES*PUSH_CHUNK); }
+
 void launch_force_push(const NbDev& nb, const CommDev& cd, cudaStream_t s) {
     if (cd.world <= 1) return;
+    if (push_tma()) {
+        static bool attr = false;
+        if (!attr) { ring_attr((const void*) k_force_push_tma); attr = true; }
+        k_force_push_tma<<<dim3(3, cd.world - 1), 32, PUSH_STAGES*PUSH_CHUNK, s>>>(nb, cd);
+        // the pushed partials are consumed: zero the foreign ranges for the next evaluation
+        for (int c = 0; c < 3; c++) {
+            long long* base = nb.force + (size_t) c*nb.npad;
+            if (cd.atomLo[cd.rank] > 0) cudaMemsetAsync(base, 0, sizeof(long long)*(size_t) cd.atomLo[cd.rank], s);
+            if (cd.atomLo[cd.rank + 1] < nb.natoms) cudaMemsetAsync(base + cd.atomLo[cd.rank + 1], 0, sizeof(long long)*(size_t) (nb.natoms - cd.atomLo[cd.rank + 1]), s);
+        }
+        return;
+    }
     k_force_push<<<std::min((nb.natoms + 255)/256, 2*sm_count()), 256, 0, s>>>(nb, cd);
+}
+// positions of the owned atoms to every peer (after k_integrate, which then leaves the position stores and CH_POS to this kernel)
+bool pos_push_available() { return push_tma(); }
+void launch_pos_push(const NbDev& nb, const CommDev& cd, const IntegDev& in, cudaStream_t s) {
+    if (cd.world <= 1) return;
+    static bool attr = false;
+    if (!attr) { ring_attr((const void*) k_pos_push); attr = true; }
+    const size_t bytes = (size_t) (cd.atomLo[cd.rank + 1] - cd.atomLo[cd.rank])*sizeof(float4);
+    const int pieces = (int) std::max<size_t>(1, std::min<size_t>(8, bytes/(4*PUSH_CHUNK)));
+    k_pos_push<<<dim3(pieces, cd.world - 1), 32, PUSH_STAGES*PUSH_CHUNK, s>>>(nb, cd, in, pieces);
 }
 void launch_force_total(const NbDev& nb, const CommDev& cd, cudaStream_t s) {
     if (cd.world <= 1) return;

@@ -801,6 +801,7 @@ static void setup_window(b200md_ctx* c) {
     c->commCounters.alloc(2); c->commCounters.zero();
     c->commDone.alloc(CH_COUNT); c->commDone.zero();
     cd.epoch = c->commCounters.p; cd.posNeed = c->commCounters.p + 1; cd.done = c->commDone.p;
+    cd.posByPush = pos_push_available() ? 1 : 0;
 }
 
 // Ownership: rank q owns the integration units [unitLo[q], unitLo[q+1]) and with them the atoms [atomLo[q], atomLo[q+1]) --
@@ -893,7 +894,9 @@ extern "C" int b200md_finalize(b200md_ctx* ctx) {
     // has x planes (one slab CTA each), between 16 and 48.
     if (c->nbdesc.method == B200MD_NB_PME && !c->pmeOnly && c->overlapPme) {
         int want = 0;
-        if (c->p2p) want = std::max(16, std::min(48, (c->nbdesc.grid[0] + c->world - 1)/c->world));
+        // at least one SM per x plane of this rank; the more ranks, the shorter the tile kernel and the longer (relatively)
+        // the chain of exchanges: 44 / 40 / 64 SMs at 2 / 4 / 8 ranks for an 88^3 grid
+        if (c->p2p) want = std::min(74, std::max((c->nbdesc.grid[0] + c->world - 1)/c->world, 16 + 6*c->world));
         if (getenv("B200MD_PME_SMS")) want = atoi(getenv("B200MD_PME_SMS"));
         const int got = want > 0 ? choose_pme_sms(want, nb.pmeSmMask) : 0;
         if (got > 0) {

@@ -215,6 +215,7 @@ struct CommDev {
     unsigned long long* posNeed;         // local: CH_POS value the next evaluation must wait for (0: positions were set by the host)
     unsigned int* done;                  // local: [CH_COUNT] block-completion counters of the signalling kernels
     int* errFlag;                        // local: sticky error (NbDev::counters + CT_OVERFLOW): a wait that times out raises 3
+    int posByPush;                       // 1: k_integrate writes positions locally only, k_pos_push (TMA) publishes them and CH_POS
 };
 
 #ifdef __CUDACC__
@@ -365,6 +366,8 @@ void launch_bonded(const NbDev& nb, const BondedDev& bd, int terms, bool energy,
 
 void launch_integrate(const NbDev& nb, const UnitDev& units, const IntegDev& integ, const CommDev& cd, cudaStream_t s);
 void launch_force_push(const NbDev& nb, const CommDev& cd, cudaStream_t s);          // partial forces of foreign atoms -> owners' inboxes
+void launch_pos_push(const NbDev& nb, const CommDev& cd, const IntegDev& in, cudaStream_t s);   // owned positions -> every peer (TMA); publishes CH_POS
+bool pos_push_available();
 void launch_force_total(const NbDev& nb, const CommDev& cd, cudaStream_t s);         // compute path: owners total and broadcast, everybody waits
 void launch_vel_push(const NbDev& nb, const CommDev& cd, cudaStream_t s);            // owners' velocities -> everybody (state reads)
 void launch_pos_wait(const NbDev& nb, const CommDev& cd, cudaStream_t s);            // wait for the peers' position stores (state reads)

@@ -281,11 +281,11 @@ __global__ void __launch_bounds__(128) k_integrate(NbDev nb, UnitDev un, IntegDe
         const float4 pn = make_float4(U.x[k].x + d[k].x, U.x[k].y + d[k].y, U.x[k].z + d[k].z, p.w);
         nb.posq[a] = pn;
         nb.velm[a] = make_float4(U.v[k].x, U.v[k].y, U.v[k].z, U.invM[k]);
-        if (multi)
+        if (multi && !cd.posByPush)
             for (int q = 0; q < cd.world; q++) if (q != cd.rank) ((float4*) (cd.peer[q] + cd.offPosq))[a] = pn;
     }
     }   // active
-    if (!in.fused && !multi) return;
+    if (!in.fused && !(multi && !cd.posByPush)) return;
     if (cmFused) {
         double px = 0, py = 0, pz = 0, m = 0;
         _Pragma("unroll") for (int k = 0; k < 4; k++) if (k < U.n && U.invM[k] > 0.f) {
@@ -306,7 +306,7 @@ __global__ void __launch_bounds__(128) k_integrate(NbDev nb, UnitDev un, IntegDe
             if (blockIdx.x == 0) in.cmScratch[4*((step + 2ull) % 3ull) + threadIdx.x] = 0.0;
         }
     }
-    if (multi) {
+    if (multi && !cd.posByPush) {
         // last block: momentum sums of this rank's atoms -> slot [rank][(step+1) % 3] of every rank's table, then CH_POS
         const bool lastBlock = comm_arrive(cd, CH_POS, gridDim.x);
         if (lastBlock && threadIdx.x == 0) {
@@ -386,7 +386,10 @@ void launch_integrate(const NbDev& nb, const UnitDev& units, const IntegDev& int
     if (integ.kind == B200MD_INT_VERLET) k_integrate<B200MD_INT_VERLET><<<grid, 64, 0, s>>>(nb, units, integ, cd);
     else if (integ.kind == B200MD_INT_LANGEVIN) k_integrate<B200MD_INT_LANGEVIN><<<grid, 64, 0, s>>>(nb, units, integ, cd);
     else k_integrate<B200MD_INT_LANGEVIN_MIDDLE><<<grid, 64, 0, s>>>(nb, units, integ, cd);
-    if (!integ.fused && cd.world <= 1) k_step_advance<<<1, 1, 0, s>>>(integ);
+    if (!integ.fused && (cd.world <= 1 || cd.posByPush)) k_step_advance<<<1, 1, 0, s>>>(integ);
+    // multi-GPU, posByPush: the new positions of the owned atoms (one contiguous range) go to every peer through the TMA
+    // engine in a kernel of their own, which also carries the momentum sums and publishes CH_POS
+    if (cd.world > 1 && cd.posByPush) launch_pos_push(nb, cd, integ, s);
 }
 
 // ApplyConstraintsKernel::apply: project the current positions onto the constraints (reference & target identical)
