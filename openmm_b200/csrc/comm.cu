@@ -235,15 +235,18 @@ static int sm_count() {
     return sms;
 }
 
-static bool push_tma() {
-    static const bool on = !(getenv("B200MD_PUSH_TMA") && atoi(getenv("B200MD_PUSH_TMA")) == 0);
-    return on;
+// B200MD_PUSH_TMA: bit 0 charge-grid slabs, bit 1 partial forces, bit 2 positions through the TMA engine.  Default 1: measured
+// at 4 ranks on ApoA1 (profiles/r02_multi_gpu.md) the grid push gains (31 -> 24 us), the force push loses (19.5 -> 24 + 3
+// memset nodes) and the position push is even (k_integrate with peer stores 32 us = 11.7 + 20).
+static int push_tma_mask() {
+    static const int m = getenv("B200MD_PUSH_TMA") ? atoi(getenv("B200MD_PUSH_TMA")) : 1;
+    return m;
 }
 static void ring_attr(const void* f) { cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, PUSH_STAGES*PUSH_CHUNK); }
 
 void launch_force_push(const NbDev& nb, const CommDev& cd, cudaStream_t s) {
     if (cd.world <= 1) return;
-    if (push_tma()) {
+    if (push_tma_mask() & 2) {
         static bool attr = false;
         if (!attr) { ring_attr((const void*) k_force_push_tma); attr = true; }
         k_force_push_tma<<<dim3(3, cd.world - 1), 32, PUSH_STAGES*PUSH_CHUNK, s>>>(nb, cd);
@@ -258,7 +261,7 @@ void launch_force_push(const NbDev& nb, const CommDev& cd, cudaStream_t s) {
     k_force_push<<<std::min((nb.natoms + 255)/256, 2*sm_count()), 256, 0, s>>>(nb, cd);
 }
 // positions of the owned atoms to every peer (after k_integrate, which then leaves the position stores and CH_POS to this kernel)
-bool pos_push_available() { return push_tma(); }
+bool pos_push_available() { return (push_tma_mask() & 4) != 0; }
 void launch_pos_push(const NbDev& nb, const CommDev& cd, const IntegDev& in, cudaStream_t s) {
     if (cd.world <= 1) return;
     static bool attr = false;
@@ -286,7 +289,7 @@ void launch_pos_wait(const NbDev& nb, const CommDev& cd, cudaStream_t s) {
 }
 void launch_grid_push(const PmeDev& pme, const CommDev& cd, cudaStream_t s) {
     if (cd.world <= 1) return;
-    static const bool useTma = !(getenv("B200MD_PUSH_TMA") && atoi(getenv("B200MD_PUSH_TMA")) == 0);
+    const bool useTma = (push_tma_mask() & 1) != 0;
     const size_t planeBytes = (size_t) pme.ny*pme.nz*sizeof(long long);
     if (useTma && planeBytes % 16 == 0) {          // every slab then starts and ends on a 16-byte boundary (window offsets are multiples of 256)
         static bool attr = false;

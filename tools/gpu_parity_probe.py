@@ -60,7 +60,7 @@ def main():
         return child(sys.argv[2], sys.argv[3])
     from oracle import omm
     names = sys.argv[1:] or ["apoa1"]
-    variants = [("close0.32", {"B200MD_CLOSE_NM": "0.32"}, "f32"), ("close0.36", {"B200MD_CLOSE_NM": "0.36"}, "f32"), ("close0.40", {"B200MD_CLOSE_NM": "0.40"}, "f32")]
+    variants = [("close0", {"B200MD_CLOSE_NM": "0"}, "f32"), ("close0.36", {"B200MD_CLOSE_NM": "0.36"}, "f32")]
     report = {}
     for name in names:
         d = load(name)

@@ -34,6 +34,16 @@ __global__ void k_copy(const uint4* src, uint4* dst, size_t n) {
     for (size_t i = blockIdx.x*(size_t) blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x*blockDim.x) dst[i] = src[i];
 }
 
+// many small CTAs, each stores `per` float4 to the target (coalesced or strided by 3), then fences at system scope
+// (every thread, or thread 0 after a barrier) and bumps a local counter: the pattern of k_integrate / k_force_push
+__global__ void k_small_stores(float4* dst, int per, int strided, int fenceAll, unsigned int* done) {
+    const int base = blockIdx.x*per*(strided ? 3 : 1);
+    for (int i = threadIdx.x; i < per; i += blockDim.x) dst[base + (strided ? 3*i : i)] = make_float4(i, 1.f, 2.f, 3.f);
+    if (fenceAll) __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) { if (!fenceAll) __threadfence_system(); atomicAdd(done, 1u); }
+}
+
 static void xwrite(int fd, const void* p, size_t n) { if (write(fd, p, n) != (ssize_t) n) { perror("write"); exit(3); } }
 static void xread(int fd, void* p, size_t n) { size_t got = 0; while (got < n) { ssize_t r = read(fd, (char*) p + got, n - got); if (r <= 0) { perror("read"); exit(3); } got += r; } }
 
@@ -122,6 +132,26 @@ int main(int argc, char** argv) {
         CK(cudaMemcpy(&probe, win + (16u << 20) + 12345, 1, cudaMemcpyDeviceToHost));
         const int from = (rank + world - 1) % world;
         if (probe != (unsigned char) (from + 1)) { fprintf(stderr, "rank %d: wrong data from %d: %d\n", rank, from, probe); return 4; }
+    }
+    barrier();
+    // small-store kernels: 180 CTAs x 64 threads x 192 float4 (3 KB per CTA), local vs peer target
+    {
+        unsigned int* done = nullptr;
+        CK(cudaMalloc(&done, 4)); CK(cudaMemset(done, 0, 4));
+        const int to = (rank + 1) % world;
+        for (int target = 0; target < 2; target++) for (int strided = 0; strided < 2; strided++) for (int fenceAll = 0; fenceAll < 2; fenceAll++) {
+            float4* dst = (float4*) ((target ? peer[to] : win) + (16u << 20));
+            for (int rep = 0; rep < 3; rep++) k_small_stores<<<180, 64>>>(dst, 192, strided, fenceAll, done);
+            CK(cudaDeviceSynchronize());
+            barrier();
+            CK(cudaEventRecord(e0));
+            for (int rep = 0; rep < 20; rep++) k_small_stores<<<180, 64>>>(dst, 192, strided, fenceAll, done);
+            CK(cudaEventRecord(e1));
+            CK(cudaEventSynchronize(e1));
+            float ms = 0; CK(cudaEventElapsedTime(&ms, e0, e1));
+            if (rank == 0) printf("small stores: %s target, %s, fence by %s: %.2f us per kernel\n", target ? "PEER" : "local", strided ? "stride 3" : "coalesced", fenceAll ? "every thread" : "thread 0", 1e3*ms/20);
+            barrier();
+        }
     }
     barrier();
     for (int q = 0; q < world; q++) if (q != rank) cudaIpcCloseMemHandle(peer[q]);
