@@ -419,9 +419,11 @@ __global__ void __launch_bounds__(128) k_constrain_velocities(NbDev nb, UnitDev 
 }
 
 void launch_constrain_positions(const NbDev& nb, const UnitDev& units, float tol, cudaStream_t s) {
+    if (units.nunits == 0) return;          // every atom sits in a general constraint network (constraints.cu)
     k_constrain_positions<<<(units.nunits + 127)/128, 128, 0, s>>>(nb, units, tol);
 }
 void launch_constrain_velocities(const NbDev& nb, const UnitDev& units, float tol, cudaStream_t s) {
+    if (units.nunits == 0) return;
     k_constrain_velocities<<<(units.nunits + 127)/128, 128, 0, s>>>(nb, units, tol);
 }
 
@@ -447,6 +449,7 @@ __global__ void __launch_bounds__(128) k_kinetic_energy(NbDev nb, UnitDev un, fl
 
 void launch_kinetic_energy(const NbDev& nb, const UnitDev& units, const IntegDev& integ, float shiftDt, cudaStream_t s) {
     (void) integ;
+    if (units.nunits == 0) return;
     k_kinetic_energy<<<(units.nunits + 127)/128, 128, 0, s>>>(nb, units, shiftDt);
 }
 
