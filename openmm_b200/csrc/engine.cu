@@ -801,7 +801,7 @@ static void setup_window(b200md_ctx* c) {
     c->commCounters.alloc(2); c->commCounters.zero();
     c->commDone.alloc(CH_COUNT); c->commDone.zero();
     cd.epoch = c->commCounters.p; cd.posNeed = c->commCounters.p + 1; cd.done = c->commDone.p;
-    cd.posByPush = pos_push_available() ? 1 : 0;
+    cd.posByPush = (pos_push_available() || P >= 8) ? 1 : 0;      // per-thread stores to 7 peers cost more than a kernel of bulk copies (k_integrate 40 us at 8 ranks)
 }
 
 // Ownership: rank q owns the integration units [unitLo[q], unitLo[q+1]) and with them the atoms [atomLo[q], atomLo[q+1]) --
