@@ -145,3 +145,108 @@ def test_role_split_direct_rank_plus_reciprocal_rank_world2(tmp_path):
     f, e, _ = orc.forces_energy(desc)
     assert np.abs(got[:-1].reshape(desc.natoms, 3) - f).max() < 1e-6      # int64 rounding of two partial sums + one subtraction
     assert abs(got[-1] - e) < 1e-9*abs(e)
+
+
+# ---- the round-2 scheme: owner decomposition over a peer-memory data plane ----
+def owner_cuts(unit_atoms, natoms, world):
+    """engine.cu:setup_ownership restated: cut the atom range at integration-unit boundaries, balanced by atom count; a cut
+    is only legal where the units before it hold exactly the atoms below some index."""
+    U = len(unit_atoms)
+    lo = np.array([min(a for a in u if a >= 0) for u in unit_atoms]); hi = np.array([max(u) for u in unit_atoms])
+    pref_max = np.concatenate([[-1], np.maximum.accumulate(hi)])
+    suf_min = np.concatenate([np.minimum.accumulate(lo[::-1])[::-1], [natoms]])
+    atom_lo, unit_lo, u = [0], [0], 1
+    for q in range(1, world):
+        target = q*natoms//world
+        while u < U and not (pref_max[u] < suf_min[u] and suf_min[u] >= target):
+            u += 1
+        assert u < U
+        unit_lo.append(u); atom_lo.append(int(suf_min[u])); u += 1
+    return atom_lo + [natoms], unit_lo + [U]
+
+
+def test_owner_cuts_respect_integration_units():
+    # 40 waters (O, H, H) after a 7-atom "solute" of single-atom units and one X-H3 cluster
+    units = [(0,), (1,), (2, 3, 4, 5), (6,)] + [(7 + 3*w, 8 + 3*w, 9 + 3*w) for w in range(40)]
+    n = 7 + 120
+    for world in (2, 3, 4, 8):
+        atom_lo, unit_lo = owner_cuts(units, n, world)
+        assert atom_lo[0] == 0 and atom_lo[-1] == n and all(b > a for a, b in zip(atom_lo, atom_lo[1:]))
+        for q in range(world):
+            owned = set(a for u in units[unit_lo[q]:unit_lo[q+1]] for a in u)
+            assert owned == set(range(atom_lo[q], atom_lo[q+1]))          # whole units, contiguous atoms
+        sizes = np.diff(atom_lo)
+        assert sizes.max() - sizes.min() <= 6                              # balanced to within two units
+
+
+def _owner_worker(rank, world, port, out):
+    """One evaluation + one 'integrate' of the owner scheme with gloo standing in for the NVLink stores: every rank computes
+    PARTIAL fixed-point forces on all atoms (its share of the work items), sends each owner the partials of the owner's atoms
+    (k_force_push -> inbox), the owner totals them exactly (k_integrate), moves ITS atoms and hands the new positions to
+    everybody (the position stores of k_integrate); the charge grid is reduced slab by slab to the slab owners (k_grid_push +
+    the summation in k_fft_slab_fwd)."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(11)
+    n, nwork, nx = 96, 1000, 12
+    units = [(3*w, 3*w + 1, 3*w + 2) for w in range(n//3)]
+    atom_lo, unit_lo = owner_cuts(units, n, world)
+    pos = rng.standard_normal((n, 3))
+    wi, wj = rng.integers(0, n, nwork), rng.integers(0, n, nwork)
+    wf = rng.standard_normal((nwork, 3))*100
+    # partial forces of this rank's work items (item g -> rank g % world), 2^32 fixed point like the device buffer
+    part = np.zeros((n, 3), dtype=np.int64)
+    for g in range(rank, nwork, world):
+        fx = np.rint(wf[g]*SCALE).astype(np.int64)
+        part[wi[g]] += fx; part[wj[g]] -= fx
+    # inbox exchange: all_to_all of the owner ranges
+    send = [torch.from_numpy(part[atom_lo[q]:atom_lo[q+1]].copy()) for q in range(world)]
+    recv = [torch.zeros((atom_lo[rank+1] - atom_lo[rank], 3), dtype=torch.int64) for _ in range(world)]
+    for q in range(world):                      # gloo has no all_to_all on CPU tensors of unequal size everywhere: point to point
+        if q == rank:
+            recv[q] = send[q]
+        elif rank < q:
+            dist.send(send[q], q); dist.recv(recv[q], q)
+        else:
+            dist.recv(recv[q], q); dist.send(send[q], q)
+    total_own = sum(r.numpy() for r in recv)                          # exact integer sum, any order
+    # owner integrates its atoms and publishes them
+    newpos = pos.copy()
+    newpos[atom_lo[rank]:atom_lo[rank+1]] += 1e-3*total_own.astype(np.float64)/SCALE
+    gathered = [torch.zeros((atom_lo[q+1] - atom_lo[q], 3), dtype=torch.float64) for q in range(world)]
+    for q in range(world):
+        t = torch.from_numpy(newpos[atom_lo[q]:atom_lo[q+1]].copy()) if q == rank else gathered[q]
+        dist.broadcast(t, q)
+        gathered[q] = t
+    allpos = np.concatenate([g.numpy() for g in gathered])
+    # charge grid: every rank spreads ITS atoms into a full grid, slabs go to their owners and are summed there
+    grid = np.zeros((nx, 4, 4), dtype=np.int64)
+    for a in range(atom_lo[rank], atom_lo[rank+1]):
+        grid[int(abs(pos[a, 0])*3) % nx, a % 4, (a//4) % 4] += np.int64(round(pos[a, 1]*SCALE))
+    x_lo = [q*nx//world for q in range(world + 1)]
+    slab = torch.from_numpy(grid.copy())
+    dist.all_reduce(slab)                                             # what the slab owners end up with, restricted to their planes
+    mine = slab.numpy()[x_lo[rank]:x_lo[rank+1]]
+    if rank == 0:
+        np.savez(out, pos=allpos, plane_sum=int(mine.sum()), atom_lo=np.array(atom_lo))
+    dist.destroy_process_group()
+
+
+def test_owner_decomposition_protocol_world2(tmp_path):
+    out = str(tmp_path/"owner.npz")
+    port = 33500 + (os.getpid() % 2000)
+    mp.spawn(_owner_worker, args=(2, port, out), nprocs=2, join=True)
+    z = np.load(out)
+    # the single-rank answer
+    rng = np.random.default_rng(11)
+    n, nwork = 96, 1000
+    pos = rng.standard_normal((n, 3))
+    wi, wj = rng.integers(0, n, nwork), rng.integers(0, n, nwork)
+    wf = rng.standard_normal((nwork, 3))*100
+    tot = np.zeros((n, 3), dtype=np.int64)
+    for g in range(nwork):
+        fx = np.rint(wf[g]*SCALE).astype(np.int64)
+        tot[wi[g]] += fx; tot[wj[g]] -= fx
+    expect = pos + 1e-3*tot.astype(np.float64)/SCALE
+    assert np.array_equal(z["pos"], expect)                           # bit-identical to one rank: integer sums commute
