@@ -49,7 +49,7 @@ if os.path.exists(rep):
             return None
         x = float(row[col[k]].replace(",", ""))
         u = units[col[k]]
-        return x*{"Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "usecond": 1e3, "msecond": 1e6, "second": 1e9}.get(u, 1.0)
+        return x*{"Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "usecond": 1e3, "msecond": 1e6, "second": 1e9, "us": 1e3, "ms": 1e6, "s": 1e9}.get(u, 1.0)
     best = {}
     for row in r[2:]:
         name = short(row[col["Kernel Name"]])
