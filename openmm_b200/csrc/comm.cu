@@ -48,7 +48,7 @@ __global__ void __launch_bounds__(256) k_force_total(NbDev nb, CommDev cd) {
             const size_t i = (size_t) c*nb.npad + a;
             long long f = nb.force[i];
             for (int q = 0; q < cd.world; q++) if (q != cd.rank) f += win_finbox(cd, cd.rank, q, nb.npad)[i];
-            for (int q = 0; q < cd.world; q++) win_force(cd, q)[i] = f;
+            for (int k = 0; k < cd.world; k++) win_force(cd, (cd.rank + k) % cd.world)[i] = f;
         }
     }
     comm_signal(cd, CH_FINAL, E, gridDim.x);
@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(256) k_vel_push(NbDev nb, CommDev cd) {
     const int stride = gridDim.x*blockDim.x;
     for (int a = lo + blockIdx.x*blockDim.x + threadIdx.x; a < hi; a += stride) {
         const float4 v = nb.velm[a];
-        for (int q = 0; q < cd.world; q++) if (q != cd.rank) ((float4*) (cd.peer[q] + cd.offVelm))[a] = v;
+        for (int k = 1; k < cd.world; k++) ((float4*) (cd.peer[(cd.rank + k) % cd.world] + cd.offVelm))[a] = v;
     }
     comm_signal(cd, CH_VEL, E, gridDim.x);
 }
@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(256) k_grid_push(PmeDev pme, CommDev cd) {
     const unsigned long long E = *cd.epoch + 1ull;
     const size_t planeCells = (size_t) pme.ny*pme.nz;
     const size_t inboxStride = (size_t) cd.maxPlanes*planeCells;
-    const int q = (int) blockIdx.y + ((int) blockIdx.y >= cd.rank ? 1 : 0);
+    const int q = (cd.rank + 1 + (int) blockIdx.y) % cd.world;            // staggered: the ranks do not all start with peer 0
     const size_t begin = (size_t) cd.xLo[q]*planeCells, cells = (size_t) (cd.xLo[q+1] - cd.xLo[q])*planeCells;
     const long long* src = pme.gridFixed + begin;
     long long* dst = (long long*) (cd.peer[q] + cd.offGridInbox) + (size_t) cd.rank*inboxStride;
@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(32) k_grid_push_tma(PmeDev pme, CommDev cd, in
     const unsigned long long E = *cd.epoch + 1ull;
     const size_t planeCells = (size_t) pme.ny*pme.nz;
     const size_t inboxStride = (size_t) cd.maxPlanes*planeCells;
-    const int q = (int) blockIdx.y + ((int) blockIdx.y >= cd.rank ? 1 : 0);
+    const int q = (cd.rank + 1 + (int) blockIdx.y) % cd.world;            // staggered: the ranks do not all start with peer 0
     const size_t bytes = (size_t) (cd.xLo[q+1] - cd.xLo[q])*planeCells*sizeof(long long);
     const char* src = (const char*) (pme.gridFixed + (size_t) cd.xLo[q]*planeCells);
     char* dst = (char*) ((long long*) (cd.peer[q] + cd.offGridInbox) + (size_t) cd.rank*inboxStride);
@@ -189,7 +189,7 @@ __global__ void __launch_bounds__(32) k_pos_push(NbDev nb, CommDev cd, IntegDev 
     extern __shared__ __align__(128) unsigned char ring[];
     __shared__ __align__(8) unsigned long long bars[PUSH_STAGES];
     const unsigned long long E = *cd.epoch + 1ull;
-    const int q = (int) blockIdx.y + ((int) blockIdx.y >= cd.rank ? 1 : 0);
+    const int q = (cd.rank + 1 + (int) blockIdx.y) % cd.world;            // staggered: the ranks do not all start with peer 0
     const size_t lo = (size_t) cd.atomLo[cd.rank]*sizeof(float4), hi = (size_t) cd.atomLo[cd.rank + 1]*sizeof(float4);
     const size_t per = (((hi - lo) + pieces - 1)/pieces + PUSH_CHUNK - 1)/PUSH_CHUNK*PUSH_CHUNK;
     const size_t b0 = lo + (size_t) blockIdx.x*per, b1 = b0 + per < hi ? b0 + per : hi;
@@ -218,7 +218,7 @@ __global__ void __launch_bounds__(32) k_force_push_tma(NbDev nb, CommDev cd) {
     extern __shared__ __align__(128) unsigned char ring[];
     __shared__ __align__(8) unsigned long long bars[PUSH_STAGES];
     const unsigned long long E = *cd.epoch + 1ull;
-    const int q = (int) blockIdx.y + ((int) blockIdx.y >= cd.rank ? 1 : 0);
+    const int q = (cd.rank + 1 + (int) blockIdx.y) % cd.world;            // staggered: the ranks do not all start with peer 0
     const int c = blockIdx.x;
     // the range is widened to even atom indices (16-byte granularity of the bulk copy): the extra element is an atom the
     // receiver does not own, whose inbox slot it never reads

@@ -261,7 +261,7 @@ __device__ __forceinline__ bool comm_arrive(const CommDev& cd, int ch, unsigned 
 }
 __device__ __forceinline__ void comm_publish(const CommDev& cd, int ch, unsigned long long value) {       // one thread
     __threadfence_system();
-    for (int q = 0; q < cd.world; q++) if (q != cd.rank) st_release_sys(comm_flag(cd, q, ch, cd.rank), value);
+    for (int k = 1; k < cd.world; k++) { const int q = (cd.rank + k) % cd.world; st_release_sys(comm_flag(cd, q, ch, cd.rank), value); }
 }
 __device__ __forceinline__ bool comm_signal(const CommDev& cd, int ch, unsigned long long value, unsigned int nblocks) {
     const bool last = comm_arrive(cd, ch, nblocks);

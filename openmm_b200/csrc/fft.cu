@@ -564,7 +564,8 @@ __global__ void __launch_bounds__(FFT_THREADS) k_fft_slab_inv(PmeDev pme, size_t
     const real2* Z = fft_lines(O, other, pme.plan[2], np, S.tabz, S.twz, true);
     if (multi) {
         // the potential plane goes into EVERY rank's grid (each rank interpolates the forces of its own atoms, wherever they are)
-        for (int q = 0; q < cd.world; q++) {
+        for (int k = 0; k < cd.world; k++) {
+            const int q = (cd.rank + k) % cd.world;              // own copy first, then the peers in staggered order
             real* dq = (real*) (cd.peer[q] + cd.offGrid) + (size_t) x*ny*nz;
             for (int i = TID; i < np*nz; i += NTHR) {
                 const int p = divNz.div(i), z = i - p*nz;

@@ -282,7 +282,10 @@ __global__ void __launch_bounds__(128) k_integrate(NbDev nb, UnitDev un, IntegDe
         nb.posq[a] = pn;
         nb.velm[a] = make_float4(U.v[k].x, U.v[k].y, U.v[k].z, U.invM[k]);
         if (multi && !cd.posByPush)
-            for (int q = 0; q < cd.world; q++) if (q != cd.rank) ((float4*) (cd.peer[q] + cd.offPosq))[a] = pn;
+            for (int k = 1; k < cd.world; k++) {            // staggered: rank r starts with peer r+1, so the ranks do not all hit peer 0 first
+                const int q = (cd.rank + k) % cd.world;
+                ((float4*) (cd.peer[q] + cd.offPosq))[a] = pn;
+            }
     }
     }   // active
     if (!in.fused && !(multi && !cd.posByPush)) return;

@@ -1,3 +1,4 @@
+# Multi-GPU evidence run (under gpurun --gpus N):  bash tools/gpu_multi_bench.sh N   -> kernel timelines per rank, tests/test_gpu_multi.py, one bench line
 N=$1
 mkdir -p gpurun_out
 (timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29721 tools/gpu_trace_multi.py apoa1 8 2>&1 | tail -3) > gpurun_out/trace_x$N.log
