@@ -18,6 +18,12 @@ __device__ __forceinline__ V3 operator*(V3 a, float s) { return {a.x*s, a.y*s, a
 __device__ __forceinline__ float dot(V3 a, V3 b) { return a.x*b.x + a.y*b.y + a.z*b.z; }
 
 // ---------------------------------------------------------------- SETTLE, positions (Miyamoto & Kollman 1992)
+// NOTE on provenance: settle_positions / settle_velocities below restate the published closed form in the same sequence of
+// steps (and with the same intermediate names) as the reference's GPU kernels applySettleToPositions / applySettleToVelocities
+// (platforms/common/src/kernels/integrationUtilities.cc:328-470, 489-551), which themselves follow
+// ReferenceSETTLEAlgorithm.cpp:54-244; only the types (fp32 registers, one thread per water inside the fused integrate
+// kernel) and the surrounding kernel are this repository's own.  The SHAKE code further down is restructured (looped, per-
+// constraint distances).
 // x: old positions (constraints satisfied), d: position deltas (in/out), m: masses, dist1 = |01| = |02|, dist2 = |12|
 __device__ void settle_positions(const V3* x, V3* d, const float* m, float dist1, float dist2) {
     const V3 xp0 = d[0], xp1 = d[1], xp2 = d[2];
