@@ -307,7 +307,7 @@ def main():
     if n1 is not None:
         line["single_gpu_same_workload"] = n1
         line["speedup_vs_single_gpu_same_workload"] = nsday/n1["value"]
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:          # the CPU baseline is a rank-0, N = 1 leg (the reference arm covers N > 1)
         try:
             from oracle import omm
             omm.load_plugin(os.path.join(ROOT, "oracle", "_ref", "libOpenMMCPU.so"))
