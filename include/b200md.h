@@ -97,6 +97,14 @@ int b200md_set_constraints(b200md_ctx* ctx, int n, const int* p1, const int* p2,
  * ContextImpl can still fall back to another platform (ContextImpl.cpp:152-166).                                      */
 int b200md_check_constraints(int natoms, const double* mass, int n, const int* p1, const int* p2, const double* distance,
                              char* msg, int msglen);
+/* The host half of the CCMA setup (ReferenceCCMAAlgorithm's constructor, ReferenceCCMAAlgorithm.cpp:42-202), without a
+ * context or a device: which constraints form general networks, their connected components, and the approximate inverse of
+ * the coupling matrix in CSR form (angles = the HarmonicAngleForce terms, as ReferenceConstraints.cpp:163-177 collects
+ * them).  out_order[k] = index, in the caller's arrays, of CCMA constraint k (component by component); row_start has
+ * *out_nccma + 1 entries.  Returns the number of non-zeros, -2 if cap is too small, -1 on error.  Test hook.            */
+int b200md_ccma_setup_probe(int natoms, const double* mass, int ncon, const int* p1, const int* p2, const double* distance,
+                            int nangles, const int* a1, const int* a2, const int* a3, const double* theta0,
+                            int* out_ncomp, int* out_nccma, int* out_order, int* row_start, int* col, float* val, int cap);
 /* RemoveCMMotionKernel (kernels.h:1464-1483); frequency <= 0 disables.                               */
 int b200md_set_cm_remover(b200md_ctx* ctx, int frequency);
 /* RemoveCMMotionKernel::execute (kernels.h:1483): subtract the centre-of-mass velocity now.          */

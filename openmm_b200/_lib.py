@@ -39,6 +39,7 @@ SIGNATURES = {
     "b200md_set_bonded_groups": (C.c_int, [_P, C.c_int, C.c_int, _I]),
     "b200md_set_constraints": (C.c_int, [_P, C.c_int, _I, _I, _D]),
     "b200md_check_constraints": (C.c_int, [C.c_int, _D, C.c_int, _I, _I, _D, C.c_char_p, C.c_int]),
+    "b200md_ccma_setup_probe": (C.c_int, [C.c_int, _D, C.c_int, _I, _I, _D, C.c_int, _I, _I, _I, _D, _I, _I, _I, _I, _I, _F, C.c_int]),
     "b200md_set_cm_remover": (C.c_int, [_P, C.c_int]),
     "b200md_remove_cm_motion": (C.c_int, [_P]),
     "b200md_finalize": (C.c_int, [_P]),

@@ -526,11 +526,21 @@ static void build_units(b200md_ctx* c) {
 // bonds of the column's constraint (a dense solve of ~50-100 unknowns) instead of the reference's global sparse QR
 // (:137-190, QUERN): the inverse decays by ~3x per bond, entries below the reference's cut-off 0.02 (ReferenceConstraints.cpp:183)
 // are dropped either way, and CCMA only needs an approximate inverse -- it iterates to the tolerance.
-static void build_ccma(b200md_ctx* c) {
+// host-side result of the CCMA setup; pure function of the System (no device), so that it can be probed on a CPU
+// (b200md_ccma_setup_probe, tests/test_ccma_cpu.py)
+struct CcmaInput {
+    int natoms;
+    const std::vector<double>& mass;
+    const std::vector<int>& ccmaCons; const std::vector<int>& conI; const std::vector<int>& conJ; const std::vector<double>& conD;
+    const std::vector<int>& angI; const std::vector<int>& angJ; const std::vector<int>& angK; const std::vector<double>& angT0;
+};
+struct CcmaHost {
+    int ncomp = 0;
+    std::vector<int> order, compCon, compAtom, atoms, aStart, aCon, rowStart, col;
+    std::vector<int2> conAtoms; std::vector<float> dist, redMass, val;
+};
+static void ccma_host_setup(const CcmaInput* c, CcmaHost& H) {
     const int nc = (int) c->ccmaCons.size();
-    c->ccma = CcmaDev{};
-    if (nc == 0) return;
-    require(!c->p2p && c->world == 1, "general (CCMA) constraint networks are not supported in multi-GPU runs");
     const int N = c->natoms;
     // ---- components ----
     std::vector<int> parent(N);
@@ -651,16 +661,56 @@ static void build_ccma(b200md_ctx* c) {
     for (int i = 0; i < nc; i++) for (auto& el : colOut[i]) inv[el.first].push_back(std::make_pair(i, el.second));
     std::vector<int> rowStart(1, 0), col; std::vector<float> val;
     for (int j = 0; j < nc; j++) { for (auto& el : inv[j]) { col.push_back(el.first); val.push_back(el.second); } rowStart.push_back((int) col.size()); }
+    H.ncomp = ncomp;
+    H.order = order; H.compCon = compCon; H.compAtom = compAtom; H.atoms = atoms; H.aStart = aStart; H.aCon = aCon;
+    H.rowStart = rowStart; H.col = col; H.conAtoms = conAtoms; H.dist = dist; H.redMass = redMass; H.val = val;
+}
+
+static void build_ccma(b200md_ctx* c) {
+    const int nc = (int) c->ccmaCons.size();
+    c->ccma = CcmaDev{};
+    if (nc == 0) return;
+    require(!c->p2p && c->world == 1, "general (CCMA) constraint networks are not supported in multi-GPU runs");
+    const CcmaInput in{c->natoms, c->mass, c->ccmaCons, c->conI, c->conJ, c->conD, c->angI, c->angJ, c->angK, c->angT0};
+    CcmaHost H;
+    ccma_host_setup(&in, H);
     // ---- device ----
-    c->ccCompCon.upload(compCon); c->ccCompAtom.upload(compAtom); c->ccConAtoms.upload(conAtoms); c->ccDist.upload(dist); c->ccRedMass.upload(redMass);
-    c->ccRowStart.upload(rowStart); c->ccCol.upload(col); c->ccVal.upload(val); c->ccAtoms.upload(atoms); c->ccAStart.upload(aStart); c->ccACon.upload(aCon);
+    c->ccCompCon.upload(H.compCon); c->ccCompAtom.upload(H.compAtom); c->ccConAtoms.upload(H.conAtoms); c->ccDist.upload(H.dist); c->ccRedMass.upload(H.redMass);
+    c->ccRowStart.upload(H.rowStart); c->ccCol.upload(H.col); c->ccVal.upload(H.val); c->ccAtoms.upload(H.atoms); c->ccAStart.upload(H.aStart); c->ccACon.upload(H.aCon);
     c->ccRij.alloc(nc); c->ccDelta1.alloc(nc); c->ccDelta2.alloc(nc); c->ccXold.alloc(c->npad); c->ccXunc.alloc(c->npad);
     CcmaDev& cc = c->ccma;
-    cc.ncomp = ncomp; cc.ncon = nc; cc.natomsC = (int) atoms.size();
+    cc.ncomp = H.ncomp; cc.ncon = nc; cc.natomsC = (int) H.atoms.size();
     cc.compConStart = c->ccCompCon.p; cc.compAtomStart = c->ccCompAtom.p; cc.conAtoms = c->ccConAtoms.p; cc.conDist = c->ccDist.p; cc.conRedMass = c->ccRedMass.p;
     cc.rowStart = c->ccRowStart.p; cc.col = c->ccCol.p; cc.val = c->ccVal.p; cc.atoms = c->ccAtoms.p; cc.aStart = c->ccAStart.p; cc.aCon = c->ccACon.p;
     cc.rij = c->ccRij.p; cc.delta1 = c->ccDelta1.p; cc.delta2 = c->ccDelta2.p; cc.xold = c->ccXold.p; cc.xunc = c->ccXunc.p;
     cc.maxIter = 150;                   // ReferenceCCMAAlgorithm.cpp:55
+}
+
+// CCMA host setup without a context or a device (tests): classification + approximate inverse of the coupling matrix.
+// out_order[k] = index (into the caller's constraint arrays) of sorted constraint k; CSR in the SORTED numbering.
+// Returns the number of non-zeros (or -1; -2 if cap is too small).
+extern "C" int b200md_ccma_setup_probe(int natoms, const double* mass, int ncon, const int* p1, const int* p2, const double* dist,
+                                       int nangles, const int* a1, const int* a2, const int* a3, const double* theta0,
+                                       int* out_ncomp, int* out_nccma, int* out_order, int* row_start, int* col, float* val, int cap) {
+    try {
+        std::vector<double> m(mass, mass + natoms), cd(dist, dist + ncon), t0(theta0, theta0 + nangles);
+        std::vector<int> ci(p1, p1 + ncon), cj(p2, p2 + ncon), ai(a1, a1 + nangles), aj(a2, a2 + nangles), ak(a3, a3 + nangles);
+        std::vector<int4> ua; std::vector<int> ut; std::vector<float4> up; std::vector<int> ccmaCons;
+        std::string err;
+        if (!classify_units(natoms, m.data(), ci, cj, cd, ua, ut, up, err, &ccmaCons)) { g_create_error = err; return -1; }
+        *out_nccma = (int) ccmaCons.size();
+        *out_ncomp = 0;
+        if (ccmaCons.empty()) { row_start[0] = 0; return 0; }
+        const CcmaInput in{natoms, m, ccmaCons, ci, cj, cd, ai, aj, ak, t0};
+        CcmaHost H;
+        ccma_host_setup(&in, H);
+        *out_ncomp = H.ncomp;
+        if ((int) H.col.size() > cap) return -2;
+        for (size_t k = 0; k < H.order.size(); k++) out_order[k] = ccmaCons[H.order[k]];
+        for (size_t k = 0; k < H.rowStart.size(); k++) row_start[k] = H.rowStart[k];
+        for (size_t k = 0; k < H.col.size(); k++) { col[k] = H.col[k]; val[k] = H.val[k]; }
+        return (int) H.col.size();
+    } catch (std::exception& e) { g_create_error = e.what(); return -1; }
 }
 
 // dry run of the constraint classification (no context, no device): 0 = every constraint is supported

@@ -478,3 +478,56 @@ void orc_step(int kind, int n, double dt, double friction, const double* mass, c
     }
     free(xn);
 }
+
+/* ---- CCMA: ReferenceCCMAAlgorithm::applyConstraints (ReferenceCCMAAlgorithm.cpp:235-316), positions or velocities ----
+ * ncon constraints (ai, aj, dist), inverse masses invm, reference geometry x (constraints satisfied), target xp (new positions,
+ * or velocities when constrain_velocities != 0).  The (approximate) inverse of the coupling matrix comes in CSR form
+ * (row_start, col, val): the reference computes its own from a sparse QR (:137-190); the algorithm iterates to the
+ * tolerance with any reasonable approximation.  Returns the number of iterations used (maxit if it did not converge). */
+int orc_ccma(int ncon, const int* ai, const int* aj, const double* dist, const double* invm, const double* x, double* xp,
+             const int* row_start, const int* col, const double* val, int constrain_velocities, double tol, int maxit) {
+    double* r = (double*) malloc(sizeof(double)*4*(size_t) ncon);            /* r_ij and d_ij^2 (:255-262) */
+    double* delta = (double*) malloc(sizeof(double)*(size_t) ncon);
+    double* tmp = (double*) malloc(sizeof(double)*(size_t) ncon);
+    for (int k = 0; k < ncon; k++) {
+        for (int d = 0; d < 3; d++) r[4*k+d] = x[3*ai[k]+d] - x[3*aj[k]+d];
+        r[4*k+3] = r[4*k]*r[4*k] + r[4*k+1]*r[4*k+1] + r[4*k+2]*r[4*k+2];
+    }
+    const double lower = 1 - 2*tol + tol*tol, upper = 1 + 2*tol + tol*tol;          /* :263-264 */
+    int it = 0;
+    while (it < maxit) {
+        int converged = 0;
+        for (int k = 0; k < ncon; k++) {
+            double rp[3];
+            for (int d = 0; d < 3; d++) rp[d] = xp[3*ai[k]+d] - xp[3*aj[k]+d];
+            const double rrpr = rp[0]*r[4*k] + rp[1]*r[4*k+1] + rp[2]*r[4*k+2];
+            const double red = 0.5/(invm[ai[k]] + invm[aj[k]]);                     /* reducedMasses, :246-252 */
+            if (constrain_velocities) {
+                delta[k] = -2*red*rrpr/r[4*k+3];                                     /* :277-280 */
+                if (fabs(delta[k]) <= tol) converged++;
+            }
+            else {
+                const double rp2 = rp[0]*rp[0] + rp[1]*rp[1] + rp[2]*rp[2];
+                const double d2 = dist[k]*dist[k];
+                delta[k] = red*(d2 - rp2)/rrpr;                                      /* :282-291 */
+                if (rp2 >= lower*d2 && rp2 <= upper*d2) converged++;
+            }
+        }
+        if (converged == ncon) break;
+        it++;
+        for (int k = 0; k < ncon; k++) {                                             /* :298-305 */
+            double s = 0;
+            for (int e = row_start[k]; e < row_start[k+1]; e++) s += val[e]*delta[col[e]];
+            tmp[k] = s;
+        }
+        for (int k = 0; k < ncon; k++) {                                             /* :306-312 */
+            for (int d = 0; d < 3; d++) {
+                const double dr = r[4*k+d]*tmp[k];
+                xp[3*ai[k]+d] += dr*invm[ai[k]];
+                xp[3*aj[k]+d] -= dr*invm[aj[k]];
+            }
+        }
+    }
+    free(r); free(delta); free(tmp);
+    return it;
+}

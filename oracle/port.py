@@ -48,6 +48,8 @@ def lib():
         L.orc_step.argtypes = [C.c_int, C.c_int, C.c_double, C.c_double, D, D, D, D, C.c_int, I, I, I, D, D]
         L.orc_fft3d_forward.restype = None
         L.orc_fft3d_forward.argtypes = [C.c_int, C.c_int, C.c_int, D, D]
+        L.orc_ccma.restype = C.c_int
+        L.orc_ccma.argtypes = [C.c_int, I, I, D, D, D, D, I, I, D, C.c_int, C.c_double, C.c_int]
         L.orc_num_threads.restype = C.c_int
         _lib = L
     return _lib
