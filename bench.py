@@ -305,6 +305,8 @@ def main():
                          "note": "compute (FP32/SFU) bound kernel: arithmetic intensity ~%.0f flop/B; see DESIGN.md" % (flops/alg_bytes)},
             "phases_us": phases, "list_builds_in_timed_region": int(st1["list_builds"] - st0["list_builds"])}
     if n1 is not None:
+        line["scaling_basis"] = ("N > 1 runs ApoA1 (BASELINE.json configs[3]); the N = 1 default of this bench is DHFR (configs[1]), so a scaling "
+                                 "efficiency must be formed against single_gpu_same_workload (ApoA1 on ONE GPU, measured by rank 0 in this run)")
         line["single_gpu_same_workload"] = n1
         line["speedup_vs_single_gpu_same_workload"] = nsday/n1["value"]
     if not args.no_cpu_baseline and world == 1:          # the CPU baseline is a rank-0, N = 1 leg (the reference arm covers N > 1)
