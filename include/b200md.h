@@ -170,6 +170,10 @@ int b200md_synchronize(b200md_ctx* ctx);
  * broadcasts the 128 bytes by any means (torch.distributed in bench.py) and hands it to every rank.
  * mode 0: replicated atoms, tile list and PME atoms sharded, one int64 all-reduce of the forces per step. */
 int b200md_comm_unique_id(void* id128);
+/* Test hook, no context and no device: the ownership cuts b200md_finalize makes for `world` ranks (atom_lo, unit_lo: world + 1
+ * entries; rank q owns the atoms [atom_lo[q], atom_lo[q+1]) = whole integration units).  Returns the number of units.   */
+int b200md_ownership_probe(int natoms, const double* mass, int ncon, const int* p1, const int* p2, const double* distance,
+                           int world, int* atom_lo, int* unit_lo);
 int b200md_comm_init(b200md_ctx* ctx, int rank, int world, const void* id128);
 
 /* ---------------------------------------------------------------------------------------------------

@@ -67,6 +67,7 @@ SIGNATURES = {
     "b200md_apply_velocity_constraints": (C.c_int, [_P, C.c_double]),
     "b200md_synchronize": (C.c_int, [_P]),
     "b200md_comm_unique_id": (C.c_int, [_P]),
+    "b200md_ownership_probe": (C.c_int, [C.c_int, _D, C.c_int, _I, _I, _D, C.c_int, _I, _I]),
     "b200md_comm_init": (C.c_int, [_P, C.c_int, C.c_int, _P]),
     "b200md_get_stats": (C.c_int, [_P, C.POINTER(Stats)]),
     "b200md_time_phase": (C.c_int, [_P, C.c_int, C.c_int, _D]),

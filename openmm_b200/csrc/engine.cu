@@ -857,29 +857,46 @@ static void setup_window(b200md_ctx* c) {
 // Ownership: rank q owns the integration units [unitLo[q], unitLo[q+1]) and with them the atoms [atomLo[q], atomLo[q+1]) --
 // cuts are only made where the units before the cut hold exactly the atoms below some index (always the case for the usual
 // molecule-by-molecule atom order).
-static void setup_ownership(b200md_ctx* c) {
-    CommDev& cd = c->cd;
-    const int P = cd.world, N = c->natoms, U = (int) c->hUnitAtoms.size();
+// pure function (no device): the cuts for `P` ranks over `units` (sorted by first atom); atomLo / unitLo get P + 1 entries
+static void ownership_cuts(const std::vector<int4>& units, int N, int P, int* atomLo, int* unitLo) {
+    const int U = (int) units.size();
     std::vector<int> prefMax(U + 1, -1), sufMin(U + 1, N);
     auto lohi = [&](int u, int& lo, int& hi) {
-        const int4 a = c->hUnitAtoms[u]; const int v[4] = {a.x, a.y, a.z, a.w};
+        const int4 a = units[u]; const int v[4] = {a.x, a.y, a.z, a.w};
         lo = N; hi = -1;
         for (int k = 0; k < 4; k++) if (v[k] >= 0) { lo = std::min(lo, v[k]); hi = std::max(hi, v[k]); }
     };
     for (int u = 0; u < U; u++) { int lo, hi; lohi(u, lo, hi); prefMax[u+1] = std::max(prefMax[u], hi); }
     for (int u = U - 1; u >= 0; u--) { int lo, hi; lohi(u, lo, hi); sufMin[u] = std::min(sufMin[u+1], lo); }
-    cd.unitLo[0] = 0; cd.atomLo[0] = 0; cd.unitLo[P] = U; cd.atomLo[P] = N;
+    unitLo[0] = 0; atomLo[0] = 0; unitLo[P] = U; atomLo[P] = N;
     int u = 1;
     for (int q = 1; q < P; q++) {
         const long long target = (long long) q*N/P;
         // first valid cut at or after the target atom
         while (u < U && !(prefMax[u] < sufMin[u] && sufMin[u] >= target)) u++;
         require(u < U, "multi-GPU: cannot cut the atom range at integration-unit boundaries (molecules are not contiguous in atom order)");
-        cd.unitLo[q] = u; cd.atomLo[q] = sufMin[u];
+        unitLo[q] = u; atomLo[q] = sufMin[u];
         u++;
     }
-    for (int q = 0; q < P; q++) require(cd.atomLo[q+1] > cd.atomLo[q] && cd.unitLo[q+1] > cd.unitLo[q], "multi-GPU: a rank would own no atoms");
+    for (int q = 0; q < P; q++) require(atomLo[q+1] > atomLo[q] && unitLo[q+1] > unitLo[q], "multi-GPU: a rank would own no atoms");
+}
+static void setup_ownership(b200md_ctx* c) {
+    CommDev& cd = c->cd;
+    ownership_cuts(c->hUnitAtoms, c->natoms, cd.world, cd.atomLo, cd.unitLo);
     cd.errFlag = c->counters.p + CT_OVERFLOW;
+}
+// the same without a context or a device (tests): constraints -> integration units -> cuts for `world` ranks
+extern "C" int b200md_ownership_probe(int natoms, const double* mass, int ncon, const int* p1, const int* p2, const double* dist,
+                                      int world, int* atom_lo, int* unit_lo) {
+    try {
+        if (world < 1 || world > B200MD_MAX_RANKS) return -1;
+        std::vector<int> ci(p1, p1 + ncon), cj(p2, p2 + ncon); std::vector<double> cd(dist, dist + ncon);
+        std::vector<int4> ua; std::vector<int> ut; std::vector<float4> up; std::vector<int> ccma;
+        std::string err;
+        if (!classify_units(natoms, mass, ci, cj, cd, ua, ut, up, err, &ccma)) { g_create_error = err; return -1; }
+        ownership_cuts(ua, natoms, world, atom_lo, unit_lo);
+        return (int) ua.size();
+    } catch (std::exception& e) { g_create_error = e.what(); return -1; }
 }
 
 // ---------------------------------------------------------------- tile pools

@@ -3,8 +3,8 @@
 // + TestCuda<X>.cpp do for the CUDA platform.  Built by plugin/Makefile (target `reftests`) with
 //   -DTEST_HEADER="\"TestEwald.h\"" -DTEST_CALLS="testTriclinic(); testPMEParameters();"
 // The reference header's own main() is renamed away; TEST_CALLS lists the test functions whose features the B200
-// platform implements (Ewald summation, LJPME, parameter offsets, periodic bonded forces and general CCMA constraint
-// networks are outside the hot path -- SURVEY.md section 8 -- and are not called).
+// platform implements (plugin/Makefile has the list per header; not called: Ewald summation, LJPME, two NonbondedForce
+// objects, virtual sites and everything that needs a Custom*Force -- outside the hot path).
 #include "openmm/Platform.h"
 #include "openmm/OpenMMException.h"
 #include <cstdlib>

@@ -250,3 +250,64 @@ def test_owner_decomposition_protocol_world2(tmp_path):
         tot[wi[g]] += fx; tot[wj[g]] -= fx
     expect = pos + 1e-3*tot.astype(np.float64)/SCALE
     assert np.array_equal(z["pos"], expect)                           # bit-identical to one rank: integer sums commute
+
+
+def test_engine_ownership_cuts_on_the_real_systems_match_the_model():
+    """b200md_ownership_probe runs the engine's own classification + cuts (no device): on DHFR and ApoA1 every rank owns whole
+    integration units, the ranges partition the atoms, they are balanced to a few atoms, and they equal owner_cuts() above."""
+    import ctypes as C
+    from conftest import ROOT
+    from openmm_b200 import systems, _lib
+    lib = _lib.load()
+    D, I = C.POINTER(C.c_double), C.POINTER(C.c_int)
+    for name in ("dhfr", "apoa1"):
+        d = systems.SystemDesc.load(os.path.join(ROOT, "data", name + ".npz"))
+        n = d.natoms
+        mass = np.ascontiguousarray(d.masses, np.float64)
+        ci, cj, cd = np.ascontiguousarray(d.con_i, np.int32), np.ascontiguousarray(d.con_j, np.int32), np.ascontiguousarray(d.con_d, np.float64)
+        # the model's units: SETTLE waters / X-H_n clusters / single atoms, from the constraint graph
+        adj = [[] for _ in range(n)]
+        for a, b in zip(ci, cj):
+            adj[a].append(int(b)); adj[b].append(int(a))
+        seen, units = np.zeros(n, bool), []
+        for a in range(n):
+            if seen[a]:
+                continue
+            comp, stack = [], [a]
+            seen[a] = True
+            while stack:
+                x = stack.pop(); comp.append(x)
+                for y in adj[x]:
+                    if not seen[y]:
+                        seen[y] = True; stack.append(y)
+            units.append(tuple(sorted(comp)))
+        units.sort()
+        for world in (2, 4, 8):
+            alo = np.zeros(world + 1, np.int32); ulo = np.zeros(world + 1, np.int32)
+            nu = lib.b200md_ownership_probe(n, mass.ctypes.data_as(D), len(ci), ci.ctypes.data_as(I), cj.ctypes.data_as(I), cd.ctypes.data_as(D),
+                                            world, alo.ctypes.data_as(I), ulo.ctypes.data_as(I))
+            assert nu == len(units)
+            m_alo, m_ulo = owner_cuts(units, n, world)
+            assert list(alo) == m_alo and list(ulo) == m_ulo
+            sizes = np.diff(alo)
+            assert sizes.min() > 0 and sizes.max() - sizes.min() <= 8
+
+
+def test_octet_rotation_schedule_of_the_tile_kernel_visits_every_pair_once():
+    """Index logic of nonbonded.cu:pair_tiles restated: four groups of eight rotations inside 8-lane octets, then the octets move
+    on by 8 lanes.  Every (i lane, j slot) pair must be met exactly once, the mask bit consumed must be that slot's, and after the
+    last rotation every j (and its force total) must be back in its home lane."""
+    holder = list(range(32))                    # holder[lane] = home lane (slot) of the j atom the lane holds
+    met = np.zeros((32, 32), int)
+    for g in range(4):
+        slot_base = [(((lane >> 3) + g) & 3) << 3 for lane in range(32)]
+        for k in range(8):
+            for lane in range(32):
+                slot = slot_base[lane] | (((lane & 7) + k) & 7)         # what the kernel uses for the mask bit and the close-pair queue
+                assert holder[lane] == slot
+                met[lane, slot] += 1
+            holder = [holder[(lane & ~7) | ((lane + 1) & 7)] for lane in range(32)]      # srcIn
+        assert all(holder[lane] == slot_base[lane] | (lane & 7) for lane in range(32))    # the octet is home again: sums are folded
+        holder = [holder[(lane + 8) & 31] for lane in range(32)]                          # srcOut
+    assert (met == 1).all()
+    assert holder == list(range(32))
