@@ -28,8 +28,9 @@ struct BoxDev {
 };
 
 // precision of the spectral pipeline (charge grid -> FFT -> convolution -> potential grid); the input grid is int64
-// fixed point either way.  fp32 measured sufficient: the 1e-3 level recip force errors seen on ApoA1 came from lattice-
-// shifted fp32 coordinates, not from the transform (identical errors with a double pipeline).
+// fixed point either way.  fp32 is sufficient: a double pipeline (make dbl) changes the reciprocal-space force error by
+// nothing on DHFR, ApoA1 and the 894-ion fixture.  What DID matter is the precision of the B-spline weights in spreading
+// and interpolation, which are double (pme.cu; profiles/r02_parity_probe.md).
 #ifdef B200MD_REAL_DOUBLE      // experiment build (make dbl -> libb200md_dbl.so): double spectral pipeline, for error attribution only
 typedef double real;
 typedef double2 real2;

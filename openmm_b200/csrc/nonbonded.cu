@@ -12,6 +12,9 @@
 // emitted, so there is no static "exclusion tile" set and no host involvement.  There are two complete lists
 // (NbDev::list[2]): a build always fills the one that is not current and flips counters[CT_CUR] on the device.
 // A build is two launches, k_list_prep and k_build_tiles, that return at once unless counters[CT_REBUILD] is raised.
+// The tile kernel (k_pair) is fp32 with two exceptions that the parity against the Reference platform asked for: pairs closer
+// than NbDev::closeCut2 are queued per warp and evaluated in double from the exact coordinates (close_pair_double), and the
+// fp32 force sums are folded every 8 terms (the j atoms rotate in four octets): see the comments at pair_tiles.
 #include "engine.h"
 #include "../../include/b200md.h"
 #include <algorithm>
