@@ -325,12 +325,21 @@ double orc_pme_reciprocal(int n, const double* pos, const double* q, const doubl
 }
 
 /* ------------------------------------------------------------------------------------------------------------
- * Bonded terms (ReferenceHarmonicBondIxn.cpp, ReferenceAngleBondIxn.cpp, ReferenceProperDihedralBond.cpp) */
-double orc_bonds(int nb, const int* bi, const int* bj, const double* r0, const double* k, const double* pos, double* forces) {
+ * Bonded terms (ReferenceHarmonicBondIxn.cpp, ReferenceAngleBondIxn.cpp, ReferenceProperDihedralBond.cpp).  The _pbc
+ * forms take the box of a force whose usesPeriodicBoundaryConditions() is set: every displacement the term is built
+ * from goes through the minimum image (ReferenceHarmonicBondIxn.cpp:86-89, ReferenceAngleBondIxn.cpp:121-128,
+ * ReferenceProperDihedralBond.cpp:91-100); box == NULL is the plain form. */
+static void delta(const double* pos, int from, int to, const double* box, double* d) {
+    for (int c = 0; c < 3; c++) d[c] = pos[3*to+c] - pos[3*from+c];
+    if (box) min_image(d, box);
+}
+
+double orc_bonds_pbc(int nb, const int* bi, const int* bj, const double* r0, const double* k, const double* pos, const double* box, double* forces) {
     double e = 0;
     for (int b = 0; b < nb; b++) {
         const int i = bi[b], j = bj[b];
-        double d[3] = {pos[3*i]-pos[3*j], pos[3*i+1]-pos[3*j+1], pos[3*i+2]-pos[3*j+2]};
+        double d[3];
+        delta(pos, j, i, box, d);
         const double r = sqrt(d[0]*d[0] + d[1]*d[1] + d[2]*d[2]);
         const double dr = r - r0[b];
         e += 0.5*k[b]*dr*dr;
@@ -339,16 +348,21 @@ double orc_bonds(int nb, const int* bi, const int* bj, const double* r0, const d
     }
     return e;
 }
+double orc_bonds(int nb, const int* bi, const int* bj, const double* r0, const double* k, const double* pos, double* forces) {
+    return orc_bonds_pbc(nb, bi, bj, r0, k, pos, NULL, forces);
+}
 
 static void cross3(const double* a, const double* b, double* c) { c[0] = a[1]*b[2]-a[2]*b[1]; c[1] = a[2]*b[0]-a[0]*b[2]; c[2] = a[0]*b[1]-a[1]*b[0]; }
 static double dot3(const double* a, const double* b) { return a[0]*b[0]+a[1]*b[1]+a[2]*b[2]; }
 
-double orc_angles(int na, const int* ai, const int* aj, const int* ak, const double* th0, const double* kk, const double* pos, double* forces) {
+double orc_angles_pbc(int na, const int* ai, const int* aj, const int* ak, const double* th0, const double* kk, const double* pos, const double* box,
+                      double* forces) {
     double e = 0;
     for (int a = 0; a < na; a++) {
         const int i = ai[a], j = aj[a], k = ak[a];
         double v0[3], v1[3], cp[3], c1[3], c3[3];
-        for (int c = 0; c < 3; c++) { v0[c] = pos[3*j+c]-pos[3*i+c]; v1[c] = pos[3*j+c]-pos[3*k+c]; }
+        delta(pos, i, j, box, v0);
+        delta(pos, k, j, box, v1);
         cross3(v0, v1, cp);
         double rp = sqrt(dot3(cp, cp)); if (rp < 1e-6) rp = 1e-6;
         const double r21 = dot3(v0, v0), r23 = dot3(v1, v1);
@@ -364,14 +378,19 @@ double orc_angles(int na, const int* ai, const int* aj, const int* ak, const dou
     }
     return e;
 }
+double orc_angles(int na, const int* ai, const int* aj, const int* ak, const double* th0, const double* kk, const double* pos, double* forces) {
+    return orc_angles_pbc(na, ai, aj, ak, th0, kk, pos, NULL, forces);
+}
 
-double orc_torsions(int nt, const int* ti, const int* tj, const int* tk, const int* tl, const int* per, const double* phase, const double* kk,
-                    const double* pos, double* forces) {
+double orc_torsions_pbc(int nt, const int* ti, const int* tj, const int* tk, const int* tl, const int* per, const double* phase, const double* kk,
+                        const double* pos, const double* box, double* forces) {
     double e = 0;
     for (int t = 0; t < nt; t++) {
         const int a = ti[t], b = tj[t], c = tk[t], d = tl[t];
         double v0[3], v1[3], v2[3], cp0[3], cp1[3], cc[3];
-        for (int x = 0; x < 3; x++) { v0[x] = pos[3*a+x]-pos[3*b+x]; v1[x] = pos[3*c+x]-pos[3*b+x]; v2[x] = pos[3*c+x]-pos[3*d+x]; }
+        delta(pos, b, a, box, v0);
+        delta(pos, b, c, box, v1);
+        delta(pos, d, c, box, v2);
         cross3(v0, v1, cp0); cross3(v1, v2, cp1);
         const double n0 = dot3(cp0, cp0), n1 = dot3(cp1, cp1);
         double cs = dot3(cp0, cp1)/sqrt(n0*n1); if (cs > 1) cs = 1; if (cs < -1) cs = -1;
@@ -394,6 +413,10 @@ double orc_torsions(int nt, const int* ti, const int* tj, const int* tk, const i
         }
     }
     return e;
+}
+double orc_torsions(int nt, const int* ti, const int* tj, const int* tk, const int* tl, const int* per, const double* phase, const double* kk,
+                    const double* pos, double* forces) {
+    return orc_torsions_pbc(nt, ti, tj, tk, tl, per, phase, kk, pos, NULL, forces);
 }
 
 /* ------------------------------------------------------------------------------------------------------------

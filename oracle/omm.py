@@ -41,6 +41,7 @@ def lib():
             "omm_nonbonded_set_exceptions_periodic": (None, [P, C.c_int]), "omm_force_set_group": (None, [P, C.c_int]),
             "omm_bonds_create": (P, [C.c_int, I, I, D, D]), "omm_angles_create": (P, [C.c_int, I, I, I, D, D]),
             "omm_torsions_create": (P, [C.c_int, I, I, I, I, I, D, D]), "omm_cmmotion_create": (P, [C.c_int]),
+            "omm_bonded_set_periodic": (None, [P, C.c_int, C.c_int]),
             "omm_integrator_create": (P, [C.c_int, C.c_double, C.c_double, C.c_double, C.c_int, C.c_double]),
             "omm_integrator_destroy": (None, [P]), "omm_integrator_step": (C.c_int, [P, C.c_int]),
             "omm_context_create": (P, [P, P, C.c_char_p, C.c_char_p]), "omm_context_destroy": (None, [P]),
@@ -108,8 +109,9 @@ class Simulation:
     """System + Integrator + Context on one platform, from a SystemDesc."""
 
     def __init__(self, desc, platform="Reference", integrator=(0, 0.0, 0.0, 0.001), seed=7, constraint_tol=1e-5,
-                 pme=None, props="", recip_group=None):
-        """integrator = (kind, temperature, friction, dt); pme = (alpha, nx, ny, nz) to pin the PME parameters."""
+                 pme=None, props="", recip_group=None, bonded_periodic=False):
+        """integrator = (kind, temperature, friction, dt); pme = (alpha, nx, ny, nz) to pin the PME parameters;
+        bonded_periodic: setUsesPeriodicBoundaryConditions(true) on the three bonded forces."""
         L = lib()
         self.L = L
         self.n = desc.natoms
@@ -136,14 +138,17 @@ class Simulation:
         L.omm_system_add_force(self.sys, nb)
         if len(desc.bond_i):
             f = L.omm_bonds_create(len(desc.bond_i), _ip(_i32(desc.bond_i)), _ip(_i32(desc.bond_j)), _dp(_f64(desc.bond_r0)), _dp(_f64(desc.bond_k)))
+            L.omm_bonded_set_periodic(f, 0, int(bonded_periodic))
             L.omm_system_add_force(self.sys, f)
         if len(desc.angle_i):
             f = L.omm_angles_create(len(desc.angle_i), _ip(_i32(desc.angle_i)), _ip(_i32(desc.angle_j)), _ip(_i32(desc.angle_k)),
                                     _dp(_f64(desc.angle_t0)), _dp(_f64(desc.angle_kk)))
+            L.omm_bonded_set_periodic(f, 1, int(bonded_periodic))
             L.omm_system_add_force(self.sys, f)
         if len(desc.tor_i):
             f = L.omm_torsions_create(len(desc.tor_i), _ip(_i32(desc.tor_i)), _ip(_i32(desc.tor_j)), _ip(_i32(desc.tor_k)), _ip(_i32(desc.tor_l)),
                                       _ip(_i32(desc.tor_n)), _dp(_f64(desc.tor_phase)), _dp(_f64(desc.tor_kk)))
+            L.omm_bonded_set_periodic(f, 2, int(bonded_periodic))
             L.omm_system_add_force(self.sys, f)
         if desc.cm_frequency:
             L.omm_system_add_force(self.sys, L.omm_cmmotion_create(desc.cm_frequency))

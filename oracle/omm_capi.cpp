@@ -116,6 +116,12 @@ void* omm_torsions_create(int n, const int* i, const int* j, const int* k, const
     for (int b = 0; b < n; b++) f->addTorsion(i[b], j[b], k[b], l[b], per[b], phase[b], kk[b]);
     return f;
 }
+// kind: 0 HarmonicBondForce, 1 HarmonicAngleForce, 2 PeriodicTorsionForce (each class has its own, non-virtual setter)
+void omm_bonded_set_periodic(void* f, int kind, int p) {
+    if (kind == 0) ((HarmonicBondForce*) f)->setUsesPeriodicBoundaryConditions(p != 0);
+    else if (kind == 1) ((HarmonicAngleForce*) f)->setUsesPeriodicBoundaryConditions(p != 0);
+    else ((PeriodicTorsionForce*) f)->setUsesPeriodicBoundaryConditions(p != 0);
+}
 void* omm_cmmotion_create(int freq) { return new CMMotionRemover(freq); }
 
 // ---------------------------------------------------------------- Integrators

@@ -36,12 +36,12 @@ def lib():
         L.orc_exceptions14.argtypes = [C.c_int, I, I, D, D, D, D, D]
         L.orc_pme_reciprocal.restype = C.c_double
         L.orc_pme_reciprocal.argtypes = [C.c_int, D, D, D, C.c_double, C.c_int, C.c_int, C.c_int, D]
-        L.orc_bonds.restype = C.c_double
-        L.orc_bonds.argtypes = [C.c_int, I, I, D, D, D, D]
-        L.orc_angles.restype = C.c_double
-        L.orc_angles.argtypes = [C.c_int, I, I, I, D, D, D, D]
-        L.orc_torsions.restype = C.c_double
-        L.orc_torsions.argtypes = [C.c_int, I, I, I, I, I, D, D, D, D]
+        L.orc_bonds_pbc.restype = C.c_double
+        L.orc_bonds_pbc.argtypes = [C.c_int, I, I, D, D, D, D, D]
+        L.orc_angles_pbc.restype = C.c_double
+        L.orc_angles_pbc.argtypes = [C.c_int, I, I, I, D, D, D, D, D]
+        L.orc_torsions_pbc.restype = C.c_double
+        L.orc_torsions_pbc.argtypes = [C.c_int, I, I, I, I, I, D, D, D, D, D]
         L.orc_settle.restype = None
         L.orc_settle.argtypes = [C.c_int, I, I, I, D, D, D, D, D]
         L.orc_step.restype = None
@@ -85,8 +85,9 @@ def exclusion_csr(n, ei, ej):
     return start, np.array(lst if lst else [0], dtype=np.int32)
 
 
-def forces_energy(desc, positions=None, pme=None, terms=None):
-    """(forces [N,3], energy, parts) of a SystemDesc; pme = (alpha, nx, ny, nz) overrides desc.pme_parameters()."""
+def forces_energy(desc, positions=None, pme=None, terms=None, bonded_periodic=False):
+    """(forces [N,3], energy, parts) of a SystemDesc; pme = (alpha, nx, ny, nz) overrides desc.pme_parameters();
+    bonded_periodic: the bonded forces use the minimum image (Force::usesPeriodicBoundaryConditions)."""
     L = lib()
     n = desc.natoms
     pos = _d(desc.positions if positions is None else positions)
@@ -111,14 +112,16 @@ def forces_energy(desc, positions=None, pme=None, terms=None):
         parts["reciprocal"] = L.orc_pme_reciprocal(n, _dp(pos), _dp(q), _dp(box), alpha, nx, ny, nz, _dp(f))
         if ne:
             parts["exclusion"] = L.orc_exclusion_correction(ne, _ip(ei), _ip(ej), _dp(pos), _dp(q), _dp(box), 0, alpha, _dp(f))
+    bbox = _dp(box) if bonded_periodic else None          # NULL = plain displacements
     if len(desc.bond_i):
-        parts["bonds"] = L.orc_bonds(len(desc.bond_i), _ip(_i(desc.bond_i)), _ip(_i(desc.bond_j)), _dp(_d(desc.bond_r0)), _dp(_d(desc.bond_k)), _dp(pos), _dp(f))
+        parts["bonds"] = L.orc_bonds_pbc(len(desc.bond_i), _ip(_i(desc.bond_i)), _ip(_i(desc.bond_j)), _dp(_d(desc.bond_r0)), _dp(_d(desc.bond_k)), _dp(pos),
+                                         bbox, _dp(f))
     if len(desc.angle_i):
-        parts["angles"] = L.orc_angles(len(desc.angle_i), _ip(_i(desc.angle_i)), _ip(_i(desc.angle_j)), _ip(_i(desc.angle_k)),
-                                       _dp(_d(desc.angle_t0)), _dp(_d(desc.angle_kk)), _dp(pos), _dp(f))
+        parts["angles"] = L.orc_angles_pbc(len(desc.angle_i), _ip(_i(desc.angle_i)), _ip(_i(desc.angle_j)), _ip(_i(desc.angle_k)),
+                                           _dp(_d(desc.angle_t0)), _dp(_d(desc.angle_kk)), _dp(pos), bbox, _dp(f))
     if len(desc.tor_i):
-        parts["torsions"] = L.orc_torsions(len(desc.tor_i), _ip(_i(desc.tor_i)), _ip(_i(desc.tor_j)), _ip(_i(desc.tor_k)), _ip(_i(desc.tor_l)),
-                                           _ip(_i(desc.tor_n)), _dp(_d(desc.tor_phase)), _dp(_d(desc.tor_kk)), _dp(pos), _dp(f))
+        parts["torsions"] = L.orc_torsions_pbc(len(desc.tor_i), _ip(_i(desc.tor_i)), _ip(_i(desc.tor_j)), _ip(_i(desc.tor_k)), _ip(_i(desc.tor_l)),
+                                               _ip(_i(desc.tor_n)), _dp(_d(desc.tor_phase)), _dp(_d(desc.tor_kk)), _dp(pos), bbox, _dp(f))
     return f, float(sum(parts.values())), parts
 
 

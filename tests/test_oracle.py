@@ -150,3 +150,65 @@ def test_baseline_config0_hello_sodium_chloride_on_the_reference_platform():
     frames = [l for l in out.splitlines() if l.startswith("REMARK 250")]
     assert len(frames) > 10
     assert "time=0.000 ps; energy=-297.971 kcal/mole" in frames[0]
+
+
+def _wrapped_chains(seed=3):
+    """Eight 4-atom chains (3 bonds, 2 angles, 1 torsion each) in a triclinic cell, every ATOM wrapped into the cell on
+    its own, so that bonded terms straddle the faces (the situation of TestPeriodicTorsionForce.h:110-151 testPeriodic)."""
+    rng = np.random.default_rng(seed)
+    box = np.array([[2.4, 0, 0], [0.5, 2.2, 0], [-0.4, 0.6, 2.0]])
+    nmol = 8
+    n = 4*nmol
+    pos = np.zeros((n, 3))
+    for m in range(nmol):
+        p = rng.uniform(-0.2, 0.2, 3) + box.sum(0)*rng.uniform(0, 1) * np.array([1, 0, 0]) + rng.uniform(0, 1, 3) @ box
+        for a in range(4):
+            pos[4*m+a] = p
+            p = p + 0.15*rng.normal(size=3)/np.sqrt(3) + np.array([0.1, 0.05, -0.08])
+    # wrap atom by atom: c, then b, then a (the order of the reduced cell)
+    for a in range(n):
+        for axis in (2, 1, 0):
+            pos[a] -= np.floor(pos[a, axis]/box[axis, axis])*box[axis]
+    mol = np.arange(n)//4
+    q = np.tile([0.3, -0.3, 0.2, -0.2], nmol)
+    d = systems.SystemDesc(masses=np.full(n, 12.0), charges=q, sigmas=np.full(n, 0.3), epsilons=np.full(n, 0.4), positions=pos, box=box,
+                           method=systems.NB_PME, cutoff=0.9)
+    first = 4*np.arange(nmol)
+    d.bond_i = np.concatenate([first, first+1, first+2]).astype(np.int32)
+    d.bond_j = d.bond_i + 1
+    d.bond_r0 = np.full(len(d.bond_i), 0.15)
+    d.bond_k = np.full(len(d.bond_i), 2.0e5)
+    d.angle_i = np.concatenate([first, first+1]).astype(np.int32)
+    d.angle_j, d.angle_k = d.angle_i + 1, d.angle_i + 2
+    d.angle_t0 = np.full(len(d.angle_i), 1.9)
+    d.angle_kk = np.full(len(d.angle_i), 400.0)
+    d.tor_i = first.astype(np.int32)
+    d.tor_j, d.tor_k, d.tor_l = d.tor_i + 1, d.tor_i + 2, d.tor_i + 3
+    d.tor_n = np.tile([1, 2, 3, 2], 2).astype(np.int32)
+    d.tor_phase = np.tile([0.0, np.pi, 0.4, 1.1], 2)
+    d.tor_kk = np.full(nmol, 8.0)
+    ei, ej = np.nonzero((mol[:, None] == mol[None, :]) & (np.arange(n)[:, None] < np.arange(n)[None, :]))
+    d.exc_i, d.exc_j = ei.astype(np.int32), ej.astype(np.int32)
+    d.exc_qq, d.exc_sigma, d.exc_eps = np.zeros(len(ei)), np.ones(len(ei)), np.zeros(len(ei))
+    return d.rounded()
+
+
+def test_port_periodic_bonded_terms_match_live_reference():
+    """Force::usesPeriodicBoundaryConditions on HarmonicBondForce / HarmonicAngleForce / PeriodicTorsionForce: the minimum
+    image on every displacement (ReferenceHarmonicBondIxn.cpp:86-89, ReferenceAngleBondIxn.cpp:121-128,
+    ReferenceProperDihedralBond.cpp:91-100), in a triclinic cell, with atoms of one molecule on different sides of a face."""
+    omm = _live()
+    d = _wrapped_chains()
+    pme = d.pme_parameters()
+    # the molecules really are split: some bonded neighbours are more than half a cell apart before the minimum image
+    raw = np.linalg.norm(d.positions[d.bond_i] - d.positions[d.bond_j], axis=1)
+    assert (raw > 1.0).sum() >= 3
+    f, e, parts = port.forces_energy(d, pme=pme, bonded_periodic=True)
+    fr, er = omm.Simulation(d, "Reference", pme=pme, bonded_periodic=True).forces_energy()
+    assert relative_force_error(f, fr) < 1e-8
+    assert abs(e - er) < 1e-8*max(1.0, abs(er))
+    # and the flag matters: without it both sides agree with each other on a very different answer
+    f0, e0, _ = port.forces_energy(d, pme=pme)
+    fr0, er0 = omm.Simulation(d, "Reference", pme=pme).forces_energy()
+    assert relative_force_error(f0, fr0) < 1e-8 and abs(e0 - er0) < 1e-8*abs(er0)
+    assert e0 > 10*e
