@@ -482,10 +482,74 @@ void orc_settle(int nw, const int* a0, const int* a1, const int* a2, const doubl
 /* One deterministic integrator step for rigid-water systems (noise term omitted: compare at temperature 0).
  * kind 0 Verlet (ReferenceVerletDynamics.cpp), 1 Langevin (ReferenceStochasticDynamics.cpp:89-194).
  * forces: at the current positions.  SETTLE clusters as in orc_settle (nw may be 0). */
+/* Velocity form of SETTLE (ReferenceSETTLEAlgorithm::applyToVelocities, ReferenceSETTLEAlgorithm.cpp:197-244): for every
+ * rigid triangle find the three impulses t_c along the unit bond vectors e_c (c = AB, BC, CA) that remove the relative
+ * velocity along each bond, for three arbitrary masses.  The reference writes the solution of the 3x3 system in closed form
+ * (:229-235); here the system is assembled from its definition -- impulse t_c changes atom p_c by +e_c t_c/m and atom q_c by
+ * -e_c t_c/m (:236-238) -- and solved by elimination.  x: positions with the constraints satisfied; v in/out. */
+void orc_settle_velocities(int nw, const int* a0, const int* a1, const int* a2, const double* mass, const double* x, double* v) {
+    static const int P[3] = {0, 1, 2}, Q[3] = {1, 2, 0};          /* bond c runs from atom P[c] to atom Q[c] of the triangle */
+    for (int w = 0; w < nw; w++) {
+        const int at[3] = {a0[w], a1[w], a2[w]};
+        double e[3][3], A[3][4];
+        for (int c = 0; c < 3; c++) {
+            double len = 0;
+            for (int k = 0; k < 3; k++) { e[c][k] = x[3*at[Q[c]]+k] - x[3*at[P[c]]+k]; len += e[c][k]*e[c][k]; }
+            len = sqrt(len);
+            for (int k = 0; k < 3; k++) e[c][k] /= len;
+        }
+        for (int c = 0; c < 3; c++) {
+            double vrel = 0;
+            for (int k = 0; k < 3; k++) vrel += (v[3*at[Q[c]]+k] - v[3*at[P[c]]+k])*e[c][k];
+            A[c][3] = -vrel;
+            for (int d = 0; d < 3; d++) {
+                /* change of (v_Q[c] - v_P[c]).e_c per unit impulse on bond d */
+                double onQ = 0, onP = 0;
+                if (P[d] == Q[c]) onQ += 1.0/mass[at[Q[c]]];
+                if (Q[d] == Q[c]) onQ -= 1.0/mass[at[Q[c]]];
+                if (P[d] == P[c]) onP += 1.0/mass[at[P[c]]];
+                if (Q[d] == P[c]) onP -= 1.0/mass[at[P[c]]];
+                A[c][d] = (onQ - onP)*dot3(e[d], e[c]);
+            }
+        }
+        for (int p = 0; p < 3; p++) {                              /* 3x3 elimination with partial pivoting */
+            int piv = p;
+            for (int r = p+1; r < 3; r++) if (fabs(A[r][p]) > fabs(A[piv][p])) piv = r;
+            for (int q = 0; q < 4; q++) { const double t = A[p][q]; A[p][q] = A[piv][q]; A[piv][q] = t; }
+            for (int r = p+1; r < 3; r++) { const double f = A[r][p]/A[p][p]; for (int q = p; q < 4; q++) A[r][q] -= f*A[p][q]; }
+        }
+        double t[3];
+        for (int p = 2; p >= 0; p--) { double acc = A[p][3]; for (int q = p+1; q < 3; q++) acc -= A[p][q]*t[q]; t[p] = acc/A[p][p]; }
+        for (int c = 0; c < 3; c++)
+            for (int k = 0; k < 3; k++) { v[3*at[P[c]]+k] += e[c][k]*t[c]/mass[at[P[c]]]; v[3*at[Q[c]]+k] -= e[c][k]*t[c]/mass[at[Q[c]]]; }
+    }
+}
+
+/* One deterministic step (no random force: temperature 0).  kind 0: leapfrog Verlet (ReferenceVerletDynamics.cpp), 1: Langevin
+ * (ReferenceStochasticDynamics.cpp:89-194), 2: LangevinMiddle (ReferenceLangevinMiddleDynamics.cpp:54-127: kick, velocity
+ * constraints, half drift, friction, half drift, position constraints, velocity correction by the constraint displacement). */
 void orc_step(int kind, int n, double dt, double friction, const double* mass, const double* forces, double* x, double* v,
               int nw, const int* a0, const int* a1, const int* a2, const double* d1, const double* d2) {
     double* xn = (double*) malloc(sizeof(double)*3*n);
     const double vscale = exp(-dt*friction), fscale = (friction == 0 ? dt : (1-vscale)/friction);
+    if (kind == 2) {
+        double* xu = (double*) malloc(sizeof(double)*3*n);
+        for (int i = 0; i < n; i++) if (mass[i] > 0) for (int k = 0; k < 3; k++) v[3*i+k] += dt*forces[3*i+k]/mass[i];
+        if (nw > 0) orc_settle_velocities(nw, a0, a1, a2, mass, x, v);
+        for (int i = 0; i < n; i++) for (int k = 0; k < 3; k++) {
+            if (mass[i] > 0) {
+                xn[3*i+k] = x[3*i+k] + 0.5*dt*v[3*i+k];
+                v[3*i+k] *= vscale;
+                xn[3*i+k] += 0.5*dt*v[3*i+k];
+            }
+            else xn[3*i+k] = x[3*i+k];
+            xu[3*i+k] = xn[3*i+k];
+        }
+        if (nw > 0) orc_settle(nw, a0, a1, a2, d1, d2, mass, x, xn);
+        for (int i = 0; i < n; i++) if (mass[i] > 0) for (int k = 0; k < 3; k++) { v[3*i+k] += (xn[3*i+k]-xu[3*i+k])/dt; x[3*i+k] = xn[3*i+k]; }
+        free(xu); free(xn);
+        return;
+    }
     for (int i = 0; i < n; i++) {
         const double im = mass[i] > 0 ? 1.0/mass[i] : 0.0;
         for (int k = 0; k < 3; k++) {

@@ -44,6 +44,8 @@ def lib():
         L.orc_torsions_pbc.argtypes = [C.c_int, I, I, I, I, I, D, D, D, D, D]
         L.orc_settle.restype = None
         L.orc_settle.argtypes = [C.c_int, I, I, I, D, D, D, D, D]
+        L.orc_settle_velocities.restype = None
+        L.orc_settle_velocities.argtypes = [C.c_int, I, I, I, D, D, D]
         L.orc_step.restype = None
         L.orc_step.argtypes = [C.c_int, C.c_int, C.c_double, C.c_double, D, D, D, D, C.c_int, I, I, I, D, D]
         L.orc_fft3d_forward.restype = None
@@ -155,7 +157,7 @@ def settle_clusters(desc):
 
 
 def step(desc, kind, dt, friction, x, v, forces, clusters):
-    """One deterministic (zero-temperature) Verlet (0) / Langevin (1) step with SETTLE; x, v modified in place."""
+    """One deterministic (zero-temperature) Verlet (0) / Langevin (1) / LangevinMiddle (2) step with SETTLE; x, v modified in place."""
     L = lib()
     a0, a1, a2, d1, d2 = clusters
     L.orc_step(kind, desc.natoms, dt, friction, _dp(_d(desc.masses)), _dp(_d(forces)), _dp(x), _dp(v), len(a0), _ip(a0), _ip(a1), _ip(a2), _dp(d1), _dp(d2))

@@ -116,25 +116,44 @@ def test_port_matches_live_reference_platform(name):
     assert abs(e - er) < 1e-8*max(1.0, abs(er))
 
 
-@pytest.mark.parametrize("kind", [0, 1])
-def test_port_integrator_matches_live_reference(kind):
-    """Deterministic updates (Verlet; Langevin with zero friction and zero temperature) with SETTLE, 5 steps
-    (ReferenceVerletDynamics.cpp, ReferenceStochasticDynamics.cpp:89-194, ReferenceSETTLEAlgorithm.cpp)."""
+@pytest.mark.parametrize("kind,friction", [(0, 0.0), (1, 0.0), (1, 5.0), (2, 0.0), (2, 5.0)])
+def test_port_integrator_matches_live_reference(kind, friction):
+    """Deterministic updates (Verlet; Langevin and LangevinMiddle at zero temperature, with and without friction) with
+    SETTLE on positions and -- LangevinMiddle -- on velocities, 5 steps (ReferenceVerletDynamics.cpp,
+    ReferenceStochasticDynamics.cpp:89-194, ReferenceLangevinMiddleDynamics.cpp:54-127, ReferenceSETTLEAlgorithm.cpp)."""
     omm = _live()
     d = systems.water_box(3, cutoff=0.45).rounded()
     pme = d.pme_parameters()
-    sim = omm.Simulation(d, "Reference", integrator=(kind, 0.0, 0.0, 0.002), pme=pme, constraint_tol=1e-10)
+    sim = omm.Simulation(d, "Reference", integrator=(kind, 0.0, friction, 0.002), pme=pme, constraint_tol=1e-10)
     x = d.positions.copy()
     v = np.zeros_like(x)
     cl = port.settle_clusters(d)
     for _ in range(5):
         f, _, _ = port.forces_energy(d, positions=x, pme=pme)
-        port.step(d, kind, 0.002, 0.0, x, v, f, cl)
+        port.step(d, kind, 0.002, friction, x, v, f, cl)
     sim.step(5)
     st = sim.state(positions=True, velocities=True)
     # measured 4e-9 nm after 5 steps (the port integrates from its own forces, which differ from the reference's at 1e-9)
     assert np.abs(x - st["positions"]).max() < 1e-7
     assert np.abs(v - st["velocities"]).max() < 1e-4
+    assert np.abs(v).max() > 0.05            # the molecules did move: the comparison is not of zeros
+
+
+def test_port_velocity_settle_removes_bond_velocities_for_unequal_masses():
+    """ReferenceSETTLEAlgorithm::applyToVelocities (:197-244) allows three different masses; after it the relative velocity
+    along every bond of the triangle is zero and the total momentum of the molecule is unchanged."""
+    L = port.lib()
+    rng = np.random.default_rng(11)
+    x = np.array([[0.0, 0.0, 0.0], [0.0957, 0.0, 0.0], [-0.024, 0.0927, 0.0]]) + 0.3
+    m = np.array([15.999, 1.008, 2.014])
+    v = rng.normal(size=(3, 3))
+    p0 = (m[:, None]*v).sum(0)
+    a = [np.array([k], dtype=np.int32) for k in range(3)]
+    L.orc_settle_velocities(1, port._ip(a[0]), port._ip(a[1]), port._ip(a[2]), port._dp(m), port._dp(x), port._dp(v))
+    for i, j in ((0, 1), (1, 2), (2, 0)):
+        e = (x[j]-x[i])/np.linalg.norm(x[j]-x[i])
+        assert abs(np.dot(v[j]-v[i], e)) < 1e-13
+    assert np.abs((m[:, None]*v).sum(0) - p0).max() < 1e-13
 
 
 def test_baseline_config0_hello_sodium_chloride_on_the_reference_platform():
