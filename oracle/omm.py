@@ -42,6 +42,10 @@ def lib():
             "omm_bonds_create": (P, [C.c_int, I, I, D, D]), "omm_angles_create": (P, [C.c_int, I, I, I, D, D]),
             "omm_torsions_create": (P, [C.c_int, I, I, I, I, I, D, D]), "omm_cmmotion_create": (P, [C.c_int]),
             "omm_bonded_set_periodic": (None, [P, C.c_int, C.c_int]),
+            "omm_nonbonded_add_global": (C.c_int, [P, C.c_char_p, C.c_double]),
+            "omm_nonbonded_add_particle_offset": (C.c_int, [P, C.c_char_p, C.c_int, C.c_double, C.c_double, C.c_double]),
+            "omm_nonbonded_add_exception_offset": (C.c_int, [P, C.c_char_p, C.c_int, C.c_double, C.c_double, C.c_double]),
+            "omm_context_set_parameter": (C.c_int, [P, C.c_char_p, C.c_double]),
             "omm_integrator_create": (P, [C.c_int, C.c_double, C.c_double, C.c_double, C.c_int, C.c_double]),
             "omm_integrator_destroy": (None, [P]), "omm_integrator_step": (C.c_int, [P, C.c_int]),
             "omm_context_create": (P, [P, P, C.c_char_p, C.c_char_p]), "omm_context_destroy": (None, [P]),
@@ -109,9 +113,11 @@ class Simulation:
     """System + Integrator + Context on one platform, from a SystemDesc."""
 
     def __init__(self, desc, platform="Reference", integrator=(0, 0.0, 0.0, 0.001), seed=7, constraint_tol=1e-5,
-                 pme=None, props="", recip_group=None, bonded_periodic=False):
+                 pme=None, props="", recip_group=None, bonded_periodic=False, nb_globals=None, particle_offsets=(), exception_offsets=()):
         """integrator = (kind, temperature, friction, dt); pme = (alpha, nx, ny, nz) to pin the PME parameters;
-        bonded_periodic: setUsesPeriodicBoundaryConditions(true) on the three bonded forces."""
+        bonded_periodic: setUsesPeriodicBoundaryConditions(true) on the three bonded forces; nb_globals = {name: default},
+        particle_offsets = [(name, particle, dq, dsigma, deps)], exception_offsets = [(name, exception index, dqq, dsigma, deps)]
+        (NonbondedForce parameter offsets)."""
         L = lib()
         self.L = L
         self.n = desc.natoms
@@ -135,6 +141,12 @@ class Simulation:
             L.omm_nonbonded_set_pme(nb, pme[0], pme[1], pme[2], pme[3])
         if recip_group is not None:
             L.omm_nonbonded_set_recip_group(nb, recip_group)
+        for name, default in (nb_globals or {}).items():
+            L.omm_nonbonded_add_global(nb, name.encode(), default)
+        for name, idx, dq, ds, de in particle_offsets:
+            L.omm_nonbonded_add_particle_offset(nb, name.encode(), int(idx), dq, ds, de)
+        for name, idx, dq, ds, de in exception_offsets:
+            L.omm_nonbonded_add_exception_offset(nb, name.encode(), int(idx), dq, ds, de)
         L.omm_system_add_force(self.sys, nb)
         if len(desc.bond_i):
             f = L.omm_bonds_create(len(desc.bond_i), _ip(_i32(desc.bond_i)), _ip(_i32(desc.bond_j)), _dp(_f64(desc.bond_r0)), _dp(_f64(desc.bond_k)))
@@ -158,6 +170,9 @@ class Simulation:
         if not self.ctx:
             raise RuntimeError("Context creation failed: " + L.omm_last_error().decode())
         self.set_positions(desc.positions)
+
+    def set_parameter(self, name, value):
+        self._ck(self.L.omm_context_set_parameter(self.ctx, name.encode(), value))
 
     def _ck(self, rc):
         if rc != 0:

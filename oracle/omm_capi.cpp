@@ -82,6 +82,14 @@ void omm_nonbonded_get_exceptions(void* f, int* i, int* j, double* qq, double* s
     NonbondedForce* nb = (NonbondedForce*) f;
     for (int k = 0; k < nb->getNumExceptions(); k++) nb->getExceptionParameters(k, i[k], j[k], qq[k], sigma[k], eps[k]);
 }
+// global parameters and parameter offsets (NonbondedForce.h addGlobalParameter / addParticleParameterOffset / addExceptionParameterOffset)
+int omm_nonbonded_add_global(void* f, const char* name, double defaultValue) { return ((NonbondedForce*) f)->addGlobalParameter(name, defaultValue); }
+int omm_nonbonded_add_particle_offset(void* f, const char* name, int particle, double dq, double dsigma, double deps) {
+    return ((NonbondedForce*) f)->addParticleParameterOffset(name, particle, dq, dsigma, deps);
+}
+int omm_nonbonded_add_exception_offset(void* f, const char* name, int exception, double dqq, double dsigma, double deps) {
+    return ((NonbondedForce*) f)->addExceptionParameterOffset(name, exception, dqq, dsigma, deps);
+}
 void omm_force_destroy(void* f) { delete (Force*) f; }
 void omm_nonbonded_set_method(void* f, int method, double cutoff, double ewaldTol) {
     NonbondedForce* nb = (NonbondedForce*) f;
@@ -213,6 +221,12 @@ int omm_context_get_state(void* c, int n, double* pos, double* vel, double* frc,
 int omm_context_get_pme(void* c, void* nbforce, double* alpha, int* nx, int* ny, int* nz) {
     OMM_TRY
     ((NonbondedForce*) nbforce)->getPMEParametersInContext(*(Context*) c, *alpha, *nx, *ny, *nz);
+    return 0;
+    OMM_CATCH(-1)
+}
+int omm_context_set_parameter(void* c, const char* name, double value) {
+    OMM_TRY
+    ((Context*) c)->setParameter(name, value);
     return 0;
     OMM_CATCH(-1)
 }

@@ -87,9 +87,32 @@ def exclusion_csr(n, ei, ej):
     return start, np.array(lst if lst else [0], dtype=np.int32)
 
 
-def forces_energy(desc, positions=None, pme=None, terms=None, bonded_periodic=False):
+def with_parameter_offsets(desc, values, particle_offsets=(), exception_offsets=()):
+    """The SystemDesc the force field sees when the global parameters have `values` (ReferenceCalcNonbondedForceKernel::
+    computeParameters, ReferenceKernels.cpp:1077-1121): every offset (name, index, dq, dsigma, deps) adds value*scale to the
+    base charge / sigma / epsilon of its particle, or to chargeProd / sigma / epsilon of its exception.  An exception that
+    has an offset stays a 1-4 even when its base parameters are zero (:873-895); here every exception is evaluated anyway.
+    NOT affected by the current values: the dispersion coefficient, which the reference computes once from the parameters'
+    DEFAULT values (NonbondedForceImpl.cpp:241-258; ReferenceKernels.cpp:962) -- pass that one to forces_energy()."""
+    import copy
+    d = copy.copy(desc)
+    d.charges, d.sigmas, d.epsilons = _d(desc.charges).copy(), _d(desc.sigmas).copy(), _d(desc.epsilons).copy()
+    d.exc_qq, d.exc_sigma, d.exc_eps = _d(desc.exc_qq).copy(), _d(desc.exc_sigma).copy(), _d(desc.exc_eps).copy()
+    for name, idx, dq, ds, de in particle_offsets:
+        d.charges[idx] += values[name]*dq
+        d.sigmas[idx] += values[name]*ds
+        d.epsilons[idx] += values[name]*de
+    for name, idx, dq, ds, de in exception_offsets:
+        d.exc_qq[idx] += values[name]*dq
+        d.exc_sigma[idx] += values[name]*ds
+        d.exc_eps[idx] += values[name]*de
+    return d
+
+
+def forces_energy(desc, positions=None, pme=None, terms=None, bonded_periodic=False, dispersion_coefficient=None):
     """(forces [N,3], energy, parts) of a SystemDesc; pme = (alpha, nx, ny, nz) overrides desc.pme_parameters();
-    bonded_periodic: the bonded forces use the minimum image (Force::usesPeriodicBoundaryConditions)."""
+    bonded_periodic: the bonded forces use the minimum image (Force::usesPeriodicBoundaryConditions);
+    dispersion_coefficient: overrides desc.dispersion_coefficient() (parameter offsets: see with_parameter_offsets)."""
     L = lib()
     n = desc.natoms
     pos = _d(desc.positions if positions is None else positions)
@@ -104,7 +127,7 @@ def forces_energy(desc, positions=None, pme=None, terms=None, bonded_periodic=Fa
     parts["direct"] = L.orc_direct(n, _dp(pos), _dp(q), _dp(sig), _dp(eps), _dp(box), desc.method, desc.cutoff, alpha, desc.rf_dielectric,
                                    int(desc.use_switch), desc.switch_distance, _ip(start), _ip(lst), _dp(f))
     if desc.method in (2, 4) and desc.use_dispersion:
-        parts["dispersion"] = desc.dispersion_coefficient()/(box[0]*box[4]*box[8])
+        parts["dispersion"] = (desc.dispersion_coefficient() if dispersion_coefficient is None else dispersion_coefficient)/(box[0]*box[4]*box[8])
     ne = len(desc.exc_i)
     ei, ej = _i(desc.exc_i), _i(desc.exc_j)
     if ne:

@@ -156,6 +156,36 @@ def test_port_velocity_settle_removes_bond_velocities_for_unequal_masses():
     assert np.abs((m[:, None]*v).sum(0) - p0).max() < 1e-13
 
 
+def test_port_parameter_offsets_match_live_reference():
+    """NonbondedForce global parameters with particle and exception offsets (SURVEY.md section 8 row a2,
+    ReferenceKernels.cpp:1077-1121): at the default values and after Context::setParameter, PME with bonded terms.  The two
+    exception offsets sit on water O-H exclusions whose base parameters are zero (they must become live 1-4 terms,
+    :873-895); the dispersion correction keeps the DEFAULT values (NonbondedForceImpl.cpp:241-258)."""
+    omm = _live()
+    d = systems.water_box(3, cutoff=0.45, rigid=False).rounded()
+    pme = d.pme_parameters()
+    glob = {"lambda_q": 0.25, "lambda_lj": 1.0}
+    p_off = [("lambda_q", 0, 0.3, 0.0, 0.0), ("lambda_q", 1, -0.3, 0.0, 0.0), ("lambda_lj", 3, 0.0, 0.02, 0.25), ("lambda_lj", 6, 0.1, -0.01, 0.5),
+             ("lambda_q", 6, 0.05, 0.0, 0.0)]
+    e_off = [("lambda_lj", 0, 0.04, 0.2, 0.3), ("lambda_q", 4, -0.02, 0.15, 0.1)]
+    assert d.exc_qq[0] == 0 and d.exc_eps[0] == 0
+    sim = omm.Simulation(d, "Reference", pme=pme, nb_globals=glob, particle_offsets=p_off, exception_offsets=e_off)
+    disp = port.with_parameter_offsets(d, glob, p_off, e_off).dispersion_coefficient()
+    seen = []
+    for values in (glob, {"lambda_q": -0.5, "lambda_lj": 0.4}):
+        for name, value in values.items():
+            sim.set_parameter(name, value)
+        eff = port.with_parameter_offsets(d, values, p_off, e_off)
+        f, e, parts = port.forces_energy(eff, pme=pme, dispersion_coefficient=disp)
+        fr, er = sim.forces_energy()
+        assert relative_force_error(f, fr) < 1e-8
+        assert abs(e - er) < 1e-8*max(1.0, abs(er))
+        seen.append(e)
+    assert abs(seen[0] - seen[1]) > 1.0                    # the parameters do change the answer
+    # and the dispersion term of the second state, computed from ITS parameters, would have been different
+    assert abs(port.with_parameter_offsets(d, {"lambda_q": -0.5, "lambda_lj": 0.4}, p_off, e_off).dispersion_coefficient() - disp) > 1e-6*abs(disp)
+
+
 def test_baseline_config0_hello_sodium_chloride_on_the_reference_platform():
     """BASELINE.json configs[0]: examples/HelloSodiumChloride.cpp as shipped (6 ions, NoCutoff + GBSA-OBC, LangevinMiddle),
     compiled by oracle/Makefile from the source where it lies, on the reference's own Reference platform.  The first frame
